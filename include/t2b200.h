@@ -1,0 +1,106 @@
+/*
+ * t2b200 -- C-ABI of the B200-native DVB-T2 demodulation + FEC hot path.
+ *
+ * Plain C: opaque context, plain pointers and sizes, int status returns.  Every entry point names
+ * the reference interface it replaces (paths relative to Oleg-Malyutin/sdr_receiver_dvb_t2 src/).
+ * The C++ facade classes in sdr_receiver_dvb_t2_b200/host/ keep the reference's per-stage
+ * signatures and forward to these calls; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Pointers: every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer of
+ * the context's GPU; the library detects which (cudaPointerGetAttributes) and stages host buffers
+ * through its own pinned/device scratch on the context's stream.  All calls are asynchronous with
+ * respect to device memory and synchronous with respect to host memory they were given: when a
+ * call that received a host OUTPUT pointer returns, that buffer is filled.  t2b200_sync() drains
+ * the stream.  There is no CPU fallback: without a usable GPU every compute call fails with
+ * T2B200_ERR_CUDA.
+ */
+#ifndef T2B200_H
+#define T2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct t2b200_ctx t2b200_ctx;
+
+enum {
+  T2B200_OK = 0,
+  T2B200_ERR_ARG = 1,       /* bad argument (null pointer, unknown code, size mismatch)        */
+  T2B200_ERR_CUDA = 2,      /* CUDA runtime error or no device; see t2b200_last_error()        */
+  T2B200_ERR_STATE = 3,     /* tables for this stage were not configured                        */
+  T2B200_ERR_NOMEM = 4
+};
+
+/* dvbt2_definition.h:61-85 -- same numeric values as the reference enums */
+enum { T2B200_C1_2 = 0, T2B200_C3_5, T2B200_C2_3, T2B200_C3_4, T2B200_C4_5, T2B200_C5_6 };
+enum { T2B200_MOD_QPSK = 0, T2B200_MOD_16QAM, T2B200_MOD_64QAM, T2B200_MOD_256QAM };
+enum { T2B200_FEC_SHORT = 0, T2B200_FEC_NORMAL = 1 };
+/* extra LDPC code ids beyond fec/rate (tables present in the reference, never instantiated there:
+ * LDPC/dvb_t2_tables.hh:874,1198,1232) */
+enum { T2B200_CODE_SHORT_1_4 = 12, T2B200_CODE_SHORT_B8 = 13, T2B200_CODE_SHORT_B9 = 14 };
+
+/* flags of t2b200_ldpc_decode */
+enum {
+  /* Reference batch semantics (ldpc_decoder.cpp:262-268, LDPC/layered_decoder.hh:174): codewords
+   * are decoded in lock-step groups of 32, every lane iterates until ALL 32 pass the parity test or
+   * 25 trials are spent.  Without it every codeword stops on its own (native mode).              */
+  T2B200_LDPC_GROUP32 = 1,
+  /* Fuse bch_decoder::execute (bch_decoder.cpp:139-142): emit only the first K_bch bits of each
+   * word, XORed with the BB-scrambler PRBS (bch_decoder.cpp:50-61).                              */
+  T2B200_LDPC_BCH_DESCRAMBLE = 2,
+  /* Pack output bits MSB-first, 8 per byte (row stride = ceil(bits/8)); default is the reference
+   * layout, one byte per bit (ldpc_decoder.cpp:270-277).                                        */
+  T2B200_LDPC_PACK_BITS = 4,
+  /* Also return the int8 posteriors (debug / parity tests): post_out int8[n][N].                */
+  T2B200_LDPC_WANT_POST = 8
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int  t2b200_create(int device, t2b200_ctx** out);
+void t2b200_destroy(t2b200_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own */
+int  t2b200_set_stream(t2b200_ctx* ctx, void* cuda_stream);
+int  t2b200_sync(t2b200_ctx* ctx);
+const char* t2b200_last_error(const t2b200_ctx* ctx);
+const char* t2b200_version(void);
+/* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
+long long t2b200_launch_count(const t2b200_ctx* ctx);
+
+/* ---- K5 + K6: LDPC decode (+ BCH-parity strip and BB descramble) -------------------------- */
+/* LDPC code geometry (ldpc_decoder.cpp:177-245, bch_decoder.cpp:79-131). code = ldpc code id:
+ * fec_type(0 short,1 normal) and code_rate map to an id with t2b200_ldpc_code_id().            */
+int t2b200_ldpc_code_id(int fec_type, int code_rate);
+int t2b200_ldpc_n(int code);        /* 64800 / 16200 */
+int t2b200_ldpc_k(int code);        /* K_ldpc */
+int t2b200_ldpc_k_bch(int code);    /* K_bch (0 for the L1-only codes) */
+
+/*
+ * Replaces ldpc_decoder::execute (ldpc_decoder.cpp:157-301) -> LDPCDecoder::operator()
+ * (LDPC/layered_decoder.hh:168-180) and, with T2B200_LDPC_BCH_DESCRAMBLE, bch_decoder::execute
+ * (bch_decoder.cpp:63-164).
+ *   llr         int8[n_codewords][N], codeword (transmitted) order, positive => bit 0
+ *   bits_out    per codeword K (or K_bch) bits; one byte per bit, or packed (flag)
+ *   trials_left int32[n_codewords] or NULL: the reference's `count` for the codeword's group
+ *               (>= 0 converged, < 0 "could not recover": the reference drops the whole group)
+ *   iterations  int32[n_codewords] or NULL: update() passes executed
+ *   post_out    int8[n_codewords][N] or NULL (needs T2B200_LDPC_WANT_POST)
+ *   max_trials  reference value 25 (ldpc_decoder.h:62); 0 < max_trials <= 60
+ * With GROUP32 a trailing partial group (n_codewords % 32 lanes) is decoded as a smaller lock-step
+ * group; the reference never sees one (llr_demapper.cpp:749-765 only emits full batches).
+ */
+int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, int n_codewords,
+                       uint8_t* bits_out, int32_t* trials_left, int32_t* iterations,
+                       int8_t* post_out, int max_trials, unsigned flags);
+
+/* Replaces bch_decoder::execute alone (bch_decoder.cpp:63-164) for callers that kept the
+ * byte-per-bit LDPC output: out[w][i] = in[w][i] ^ prbs[i], i < K_bch.                          */
+int t2b200_bch_descramble(t2b200_ctx* ctx, int code, const uint8_t* bits_in, int n_words,
+                          uint8_t* bits_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2B200_H */

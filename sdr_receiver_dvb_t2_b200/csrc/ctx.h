@@ -1,0 +1,58 @@
+// Internal context of libt2b200 (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/t2b200.h"
+
+struct LdpcDeviceCode;   // ldpc.cu
+struct FftPlan;          // fft.cu
+struct SymbolTables;     // equalizer.cu
+struct TiDemapState;     // demap.cu
+
+struct Scratch {
+  void* p = nullptr; size_t cap = 0; bool pinned_host = false;
+};
+
+struct t2b200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  std::map<int, LdpcDeviceCode*> ldpc;        // by code id
+  uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes
+  unsigned* d_group_sync = nullptr; size_t group_sync_cap = 0;
+  std::map<int, FftPlan*> fft;                // by log2 n
+  SymbolTables* sym[3] = {nullptr, nullptr, nullptr};
+  TiDemapState* ti = nullptr;
+  // staging scratch, grown on demand
+  Scratch dev[8];
+  Scratch pin[8];
+};
+
+#define T2_CUDA(ctx, call)                                                            \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+      return T2B200_ERR_CUDA;                                                         \
+    }                                                                                 \
+  } while (0)
+
+// true if p is device-accessible memory of this process (device or managed)
+bool t2_is_device_ptr(const void* p);
+// grow-on-demand scratch; slot identifies the user
+int t2_dev_scratch(t2b200_ctx* ctx, int slot, size_t bytes, void** out);
+int t2_pin_scratch(t2b200_ctx* ctx, int slot, size_t bytes, void** out);
+// Bring `bytes` at src (host or device) into device memory; returns a device pointer (src itself if
+// already on the device). Async on ctx->stream; pageable host memory is staged through pinned scratch.
+int t2_to_device(t2b200_ctx* ctx, int slot, const void* src, size_t bytes, const void** dptr);
+// Output side: returns a device pointer to write to (dst itself if device memory, else scratch)
+int t2_out_device(t2b200_ctx* ctx, int slot, void* dst, size_t bytes, void** dptr);
+// Copy a scratch-produced result back to a host dst and wait for it (no-op if dst was device memory)
+int t2_finish_out(t2b200_ctx* ctx, void* dst, const void* dptr, size_t bytes);

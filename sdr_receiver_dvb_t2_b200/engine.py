@@ -1,0 +1,165 @@
+"""ctypes binding of include/t2b200.h.
+
+Arrays may be numpy arrays (host memory) or torch CUDA tensors (device memory, passed by
+data_ptr()); the C library detects which.  No computation happens here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM = range(5)
+LDPC_GROUP32, LDPC_BCH_DESCRAMBLE, LDPC_PACK_BITS, LDPC_WANT_POST = 1, 2, 4, 8
+C1_2, C3_5, C2_3, C3_4, C4_5, C5_6 = range(6)
+MOD_QPSK, MOD_16QAM, MOD_64QAM, MOD_256QAM = range(4)
+FEC_SHORT, FEC_NORMAL = 0, 1
+
+# every symbol include/t2b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    't2b200_create', 't2b200_destroy', 't2b200_set_stream', 't2b200_sync', 't2b200_last_error',
+    't2b200_version', 't2b200_launch_count',
+    't2b200_ldpc_code_id', 't2b200_ldpc_n', 't2b200_ldpc_k', 't2b200_ldpc_k_bch',
+    't2b200_ldpc_decode', 't2b200_bch_descramble',
+]
+
+
+class T2Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, 'libt2b200.so')
+
+
+def lib():
+    """Load (building first if a source is newer) libt2b200.so.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        _build.build()
+    except Exception as e:  # no nvcc on the GPU box: the prebuilt library must be there
+        if not os.path.exists(lib_path()):
+            raise T2Error('libt2b200.so is missing and cannot be built: %s' % e)
+    L = C.CDLL(lib_path())
+    vp, i32, u32 = C.c_void_p, C.c_int, C.c_uint
+    L.t2b200_create.argtypes = [i32, C.POINTER(vp)]
+    L.t2b200_destroy.argtypes = [vp]
+    L.t2b200_destroy.restype = None
+    L.t2b200_set_stream.argtypes = [vp, vp]
+    L.t2b200_sync.argtypes = [vp]
+    L.t2b200_last_error.argtypes = [vp]
+    L.t2b200_last_error.restype = C.c_char_p
+    L.t2b200_version.restype = C.c_char_p
+    L.t2b200_launch_count.argtypes = [vp]
+    L.t2b200_launch_count.restype = C.c_longlong
+    L.t2b200_ldpc_decode.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, u32]
+    L.t2b200_bch_descramble.argtypes = [vp, i32, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """address of a numpy array / torch tensor / None"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags['C_CONTIGUOUS']
+        return a.ctypes.data
+    if hasattr(a, 'data_ptr'):
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def _is_torch(a):
+    return hasattr(a, 'data_ptr') and not isinstance(a, np.ndarray)
+
+
+def _like(ref, shape, dtype_np):
+    """allocate an output next to `ref`: numpy -> numpy, torch cuda tensor -> torch cuda tensor"""
+    if _is_torch(ref):
+        import torch
+        td = {np.uint8: torch.uint8, np.int8: torch.int8, np.int32: torch.int32,
+              np.float32: torch.float32, np.complex64: torch.complex64}[dtype_np]
+        return torch.empty(shape, dtype=td, device=ref.device)
+    return np.empty(shape, dtype_np)
+
+
+class Engine:
+    """One t2b200 context = one GPU + one stream."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.t2b200_create(device, C.byref(h))
+        if rc != OK:
+            raise T2Error('t2b200_create(device=%d) failed (rc=%d): no usable CUDA device; '
+                          'there is no CPU fallback' % (device, rc))
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self._chk(self.L.t2b200_set_stream(self.h, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.t2b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise T2Error('t2b200 rc=%d: %s' % (rc, self.L.t2b200_last_error(self.h).decode()))
+
+    def sync(self):
+        self._chk(self.L.t2b200_sync(self.h))
+
+    def set_stream(self, stream):
+        self._chk(self.L.t2b200_set_stream(self.h, C.c_void_p(stream or 0)))
+
+    @property
+    def launches(self):
+        return self.L.t2b200_launch_count(self.h)
+
+    # ---- LDPC (+ BCH strip / descramble) ----
+    def ldpc_code_id(self, fec_type, code_rate):
+        return self.L.t2b200_ldpc_code_id(fec_type, code_rate)
+
+    def ldpc_geometry(self, code):
+        return self.L.t2b200_ldpc_n(code), self.L.t2b200_ldpc_k(code), self.L.t2b200_ldpc_k_bch(code)
+
+    def ldpc_decode(self, code, llr, flags=LDPC_GROUP32, max_trials=25, want_status=True, out=None):
+        """llr int8[n][N] -> dict(bits, trials_left, iterations[, post])"""
+        N, K, KB = self.ldpc_geometry(code)
+        n = llr.shape[0]
+        assert llr.shape[1] == N
+        k_out = KB if flags & LDPC_BCH_DESCRAMBLE else K
+        row = k_out // 8 if flags & LDPC_PACK_BITS else k_out
+        bits = out if out is not None else _like(llr, (n, row), np.uint8)
+        tl = _like(llr, (n,), np.int32) if want_status else None
+        it = _like(llr, (n,), np.int32) if want_status else None
+        post = _like(llr, (n, N), np.int8) if flags & LDPC_WANT_POST else None
+        self._chk(self.L.t2b200_ldpc_decode(self.h, code, _ptr(llr), n, _ptr(bits), _ptr(tl), _ptr(it), _ptr(post),
+                                            max_trials, flags))
+        r = {'bits': bits, 'trials_left': tl, 'iterations': it}
+        if post is not None:
+            r['post'] = post
+        return r
+
+    def bch_descramble(self, code, bits):
+        N, K, KB = self.ldpc_geometry(code)
+        n = bits.shape[0]
+        assert bits.shape[1] == K
+        out = _like(bits, (n, KB), np.uint8)
+        self._chk(self.L.t2b200_bch_descramble(self.h, code, _ptr(bits), n, _ptr(out)))
+        return out
