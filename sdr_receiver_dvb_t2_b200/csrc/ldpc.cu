@@ -34,14 +34,24 @@ namespace {
 
 constexpr int kThreads = 384;          // 360 check nodes of a layer + 24 idle lanes (12 warps)
 constexpr int kSyncStride = 64;        // group-sync words per group (max_trials + 1 <= 64)
+constexpr int kMaxLayers = 90;         // q of the rate-1/2 normal code
+constexpr int kMaxEdgeWords = 648;     // max q * CNL over all codes (rate 3/5 normal: 72 * 9)
 
+// Passed by value: the whole schedule lives in the kernel-parameter constant bank, so the per-layer
+// (base, shift) pairs are fetched through the uniform datapath, not through the LSU.
 struct LdpcParams {
   const int8_t* llr; uint8_t* bits; int32_t* trials_left; int32_t* iters; int8_t* post_out;
+  const uint8_t* level; const uint8_t* prbs; unsigned* gsync;
   int n_cw, group_lanes, max_trials; unsigned flags;
   int N, K, q, k_out;
-  const uint32_t* edge; const uint8_t* cnt; const int16_t* cidx; const uint8_t* nlev; const uint8_t* level;
-  const uint8_t* prbs; unsigned* gsync;
+  // CN (i,j) data edge c reads posterior 360*g + (j + shift) mod 360 = j + ea - (j >= et ? 360 : 0)
+  uint16_t ea[kMaxEdgeWords];         // [q][CNL]: 360*g + shift
+  uint16_t et[kMaxEdgeWords];         // [q][CNL]: 360 - shift
+  uint32_t shared[kMaxLayers];        // per layer: data-edge slots whose bit another CN of the layer also uses
+  int16_t cidx[kMaxLayers];           // row of level[] for layers with shared bits
+  uint8_t cnt[kMaxLayers], nlev[kMaxLayers];
 };
+static_assert(sizeof(LdpcParams) <= 4000, "kernel parameter block");
 
 template <typename ST> struct StateCodec;
 template <> struct StateCodec<uint32_t> {       // <= 15 slots: signs[0,15) idx[15,20) m0[20,26) m1[26,32)
@@ -61,87 +71,117 @@ template <> struct StateCodec<uint64_t> {       // <= 32 slots: signs in the low
   }
 };
 
-__device__ __forceinline__ int rot360(int j, int sh) { int t = j + sh; return t >= 360 ? t - 360 : t; }
+// min/max through PTX so that the optimiser cannot range-narrow the int8-valued data into packed
+// 16-bit lanes (it then spends more PRMT pack/unpack instructions than it saves)
+__device__ __forceinline__ int smin(int a, int b) { int r; asm("min.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ int smax(int a, int b) { int r; asm("max.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 
-// One check node, both passes (LDPC/layered_decoder.hh:87-107 + algorithms.hh:250-291).
+enum SlotMode { ALL_SLOTS, PREDICATED, BRANCHED };
+
+// One check node (LDPC/layered_decoder.hh:87-107 + algorithms.hh:250-291), split so that the edges
+// of a layer that are private to the check node and the edges it shares with another check node of
+// the same layer can be read / written at different times.
 template <int CNL, typename ST>
-__device__ __forceinline__ void check_node(int8_t* __restrict__ post, ST* __restrict__ state,
-                                           const uint32_t* __restrict__ edge_i, int cnt, int i, int j,
-                                           int K, int q)
-{
-  constexpr int SLOTS = CNL + 2;
-  ST w = state[i * 360 + j];
-  uint32_t sg; int idx, m0c, m1c;
-  StateCodec<ST>::unpack(w, sg, idx, m0c, m1c);
+struct CheckNode {
+  static constexpr int SLOTS = CNL + 2;
   int inp[SLOTS], adr[SLOTS];
-  int key0 = 1 << 20, key1 = 1 << 20, sx = 0;
-  const bool hasB = (i | j) != 0;
+  int key0, key1, sx;
+  // minus the stored message of the previous iteration (clamp(out,-32,31)), by sign and by "is arg-min"
+  int nb_neg0, nb_pos0, nb_neg1, nb_pos1, idx;
+  uint32_t sg, nsg;
+  int8_t* post;
 
-  auto edge_in = [&](int slot, int a) {
-    int pv = post[a];
-    int m = (slot == idx) ? m1c : m0c;                       // stored message magnitude (<= 32)
-    int bl = ((sg >> slot) & 1u) ? -m : min(m, 31);          // clamp(out, -32, 31)
-    int v = max(min(pv - bl, 127), -128);                    // vqsub
-    inp[slot] = v; adr[slot] = a;
-    int mag = max(min(abs(v), 127) - 1, 0);                  // vqabs, then unsigned vqsub beta
-    int key = (mag << 5) | slot;
-    key1 = min(key1, max(key0, key));
-    key0 = min(key0, key);
-    sx ^= v;
-  };
-#pragma unroll
-  for (int c = 0; c < CNL; ++c)
-    if (c < cnt) {
-      uint32_t e = __ldg(edge_i + c);
-      edge_in(c, (int)(e & 0xffffu) + rot360(j, (int)(e >> 16)));
-    }
-  edge_in(CNL, K + 360 * i + j);
-  if (hasB) edge_in(CNL + 1, i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + j - 1);
-
-  const int m0 = key0 >> 5, idn = key0 & 31, m1 = key1 >> 5;
-  uint32_t nsg = 0;
-  auto edge_out = [&](int slot) {
-    int v = inp[slot];
-    int mg = (slot == idn) ? m1 : m0;                        // other(mags[i], mins[0], mins[1])
-    bool neg = ((sx ^ v) < 0);                               // sign of the product of the other links
-    int o = neg ? -mg : mg;
-    post[adr[slot]] = (int8_t)max(min(v + o, 127), -128);    // vqadd
-    nsg |= (uint32_t)neg << slot;
-  };
-#pragma unroll
-  for (int c = 0; c < CNL; ++c)
-    if (c < cnt) edge_out(c);
-  edge_out(CNL);
-  if (hasB) edge_out(CNL + 1);
-  state[i * 360 + j] = StateCodec<ST>::pack(nsg, idn, min(m0, 32), min(m1, 32));
-}
-
-// bad() for the check nodes of row j in every layer (LDPC/layered_decoder.hh:65-82)
-template <int CNL>
-__device__ __forceinline__ int syndrome_rows(const int8_t* __restrict__ post, const LdpcParams& p, int j)
-{
-  int bad = 0;
-  for (int i = 0; i < p.q; ++i) {
-    const int cnt = __ldg(p.cnt + i);
-    const uint32_t* edge_i = p.edge + i * CNL;
-    int x = 0, nz = 1;
-#pragma unroll
-    for (int c = 0; c < CNL; ++c)
-      if (c < cnt) {
-        uint32_t e = __ldg(edge_i + c);
-        int pv = post[(int)(e & 0xffffu) + rot360(j, (int)(e >> 16))];
-        x ^= pv; nz &= (pv != 0);
-      }
-    int pa = post[p.K + 360 * i + j];
-    x ^= pa; nz &= (pa != 0);
-    if (i | j) {
-      int pb = post[i ? p.K + 360 * (i - 1) + j : p.K + 360 * (p.q - 1) + j - 1];
-      x ^= pb; nz &= (pb != 0);
-    }
-    bad |= (x < 0) | !nz;
+  __device__ __forceinline__ void begin(int8_t* post_, ST w) {
+    post = post_;
+    int m0c, m1c;
+    StateCodec<ST>::unpack(w, sg, idx, m0c, m1c);
+    nb_neg0 = m0c; nb_pos0 = -smin(m0c, 31); nb_neg1 = m1c; nb_pos1 = -smin(m1c, 31);
+    key0 = 1 << 20; key1 = 1 << 20; sx = 0; nsg = 0;
   }
-  return bad;
-}
+  __device__ __forceinline__ void edge_in(int slot, int a, bool active) {
+    const int pv = post[a];
+    const bool neg = (sg >> slot) & 1u;
+    int nbl = neg ? nb_neg0 : nb_pos0;
+    if (slot == idx) nbl = neg ? nb_neg1 : nb_pos1;
+    const int v = smax(__viaddmin_s32(pv, nbl, 127), -128);   // vqsub(posterior, stored message)
+    const int mag = __viaddmin_s32_relu(abs(v), -1, 126);     // vqabs, then unsigned vqsub of beta = 1
+    int key = mag * 32 + slot;
+    if (!active) key = 1 << 20;
+    if (active) { inp[slot] = v; adr[slot] = a; }
+    key1 = smin(key1, smax(key0, key));
+    key0 = smin(key0, key);
+    sx ^= active ? v : 0;
+  }
+  __device__ __forceinline__ void edge_out(int slot, int m0, int m1, int idn, bool active) {
+    const int v = inp[slot];
+    const bool neg = ((sx ^ v) < 0);                          // sign of the product of the other links
+    int o = neg ? -m0 : m0;                                   // other(mags[i], mins[0], mins[1]) with that sign
+    if (slot == idn) o = neg ? -m1 : m1;
+    if (active) post[adr[slot]] = (int8_t)smax(__viaddmin_s32(v, o, 127), -128);   // vqadd
+    if (neg && active) nsg |= 1u << slot;
+  }
+  // Data slots: ALL_SLOTS  - every c < CNL is an edge (regular layer, nothing shared);
+  //             PREDICATED - slot c takes part iff c < cnt and bit c of mask; inactive slots are
+  //                          computed and discarded so the loads still issue back to back;
+  //             BRANCHED   - same condition by (warp-uniform) branches: few active slots.
+  template <SlotMode MODE>
+  __device__ __forceinline__ void load(const uint16_t* ea, const uint16_t* et, int cnt, uint32_t mask,
+                                       bool with_parity, int i, int j, int K, int q) {
+#pragma unroll
+    for (int c = 0; c < CNL; ++c) {
+      const bool on = MODE == ALL_SLOTS ? true : (c < cnt && ((mask >> c) & 1u));
+      if (MODE == BRANCHED && !on) continue;
+      int a = j + (int)ea[c];
+      if (j >= (int)et[c]) a -= 360;
+      edge_in(c, a, on);
+    }
+    if (with_parity) {
+      edge_in(CNL, K + 360 * i + j, true);
+      const bool hasB = (i | j) != 0;
+      edge_in(CNL + 1, i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + (hasB ? j - 1 : 0), hasB);
+    }
+  }
+  template <SlotMode MODE>
+  __device__ __forceinline__ void store(int cnt, uint32_t mask, bool with_parity, int i, int j) {
+    const int m0 = key0 >> 5, idn = key0 & 31, m1 = key1 >> 5;
+#pragma unroll
+    for (int c = 0; c < CNL; ++c) {
+      const bool on = MODE == ALL_SLOTS ? true : (c < cnt && ((mask >> c) & 1u));
+      if (MODE == BRANCHED && !on) continue;
+      edge_out(c, m0, m1, idn, on);
+    }
+    if (with_parity) {
+      edge_out(CNL, m0, m1, idn, true);
+      edge_out(CNL + 1, m0, m1, idn, (i | j) != 0);
+    }
+  }
+  // ---- shared-edge fast path: the slot number is a run-time (warp-uniform) value ----
+  // minus the stored message for `slot`: everything that does not depend on the posterior
+  __device__ __forceinline__ int stored_neg(int slot) const {
+    const bool neg = (sg >> slot) & 1u;
+    int nbl = neg ? nb_neg0 : nb_pos0;
+    if (slot == idx) nbl = neg ? nb_neg1 : nb_pos1;
+    return nbl;
+  }
+  __device__ __forceinline__ int shared_in(int slot, int a, int nbl) {
+    const int v = smax(__viaddmin_s32((int)post[a], nbl, 127), -128);
+    const int key = __viaddmin_s32_relu(abs(v), -1, 126) * 32 + slot;
+    key1 = smin(key1, smax(key0, key));
+    key0 = smin(key0, key);
+    sx ^= v;
+    return v;
+  }
+  __device__ __forceinline__ void shared_out(int slot, int a, int v, int m0, int m1, int idn) {
+    const bool neg = ((sx ^ v) < 0);
+    int o = neg ? -m0 : m0;
+    if (slot == idn) o = neg ? -m1 : m1;
+    post[a] = (int8_t)smax(__viaddmin_s32(v, o, 127), -128);
+    if (neg) nsg |= 1u << slot;
+  }
+  __device__ __forceinline__ ST finish() const {
+    return StateCodec<ST>::pack(nsg, key0 & 31, smin(key0 >> 5, 32), smin(key1 >> 5, 32));
+  }
+};
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
 {
@@ -150,19 +190,83 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
   return v;
 }
 
+// 32 hard-decision bits starting at bit position P of the packed sign plane
+__device__ __forceinline__ uint32_t bits32(const uint32_t* hb, int P)
+{
+  return __funnelshift_r(hb[P >> 5], hb[(P >> 5) + 1], P & 31);
+}
+
+// bad() (LDPC/layered_decoder.hh:65-82) on a snapshot of the posteriors.  The sign plane hb[] (one bit
+// per posterior) is packed 128 posteriors per warp step; then each thread XORs, for 32 check nodes at a
+// time, the rotated 32-bit windows of the sign plane that the layer's edges select.  A zero posterior
+// fails its checks (vsign gives 0), and every bit takes part in at least one check.
+template <int CNL>
+__device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uint32_t* __restrict__ hb,
+                                            const LdpcParams& p)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwords = (p.N + 31) >> 5;
+  const int nchunks = (p.N + 127) >> 7;                      // 128 posteriors = 32 lanes x 4 bytes
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(post);
+  uint32_t anyzero = 0;
+  for (int ch = warp; ch < nchunks; ch += kThreads / 32) {
+    const int wi = ch * 32 + lane;
+    uint32_t w = wi * 4 < p.N ? pw[wi] : 0x01010101u;        // N is a multiple of 4
+    anyzero |= (w - 0x01010101u) & ~w & 0x80808080u;         // some byte == 0
+    uint32_t nib = ((((w >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;   // 4 sign bits
+    nib <<= 4 * (lane & 7);
+    nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+    nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+    nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+    if ((lane & 7) == 0 && ch * 4 + (lane >> 3) < nwords + 2) hb[ch * 4 + (lane >> 3)] = nib;
+  }
+  if (tid < 2 && (nchunks * 4) < nwords + 2) hb[nwords + tid] = 0;
+  int bad = anyzero != 0;
+  __syncthreads();
+  for (int t = tid; t < p.q * 12; t += kThreads) {
+    const int i = t / 12, w = t - 12 * i;
+    const int cnt = p.cnt[i];
+    uint32_t x = 0;
+#pragma unroll
+    for (int c = 0; c < CNL; ++c)
+      if (c < cnt) {
+        const int sh = 360 - (int)p.et[i * CNL + c], base = (int)p.ea[i * CNL + c] - sh;
+        int o = 32 * w + sh;
+        if (o >= 360) o -= 360;
+        uint32_t r = bits32(hb, base + o);
+        if (o > 328) {                                    // the 32-bit window wraps inside the 360-bit group
+          const int n1 = 360 - o;
+          r = (r & ((1u << n1) - 1u)) | (bits32(hb, base) << n1);
+        }
+        x ^= r;
+      }
+    x ^= bits32(hb, p.K + 360 * i + 32 * w);
+    if (i) x ^= bits32(hb, p.K + 360 * (i - 1) + 32 * w);
+    else {
+      uint32_t r = bits32(hb, p.K + 360 * (p.q - 1) + 32 * w - 1);
+      if (w == 0) r &= ~1u;                               // check node (0,0) has a single parity edge
+      x ^= r;
+    }
+    if (w == 11) x &= 0xffu;
+    bad |= (x != 0);
+  }
+  return bad;
+}
+
 template <int CNL, typename ST>
-__global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const LdpcParams p)
+__global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   int8_t* post = reinterpret_cast<int8_t*>(smem);
   ST* state = reinterpret_cast<ST*>(smem + ((p.N + 15) & ~15));
+  const int R = p.N - p.K;
+  uint32_t* hb = reinterpret_cast<uint32_t*>(state + R);
   __shared__ int s_flag;
 
   const int tid = threadIdx.x;
   const int GL = p.group_lanes;
   const int lane = blockIdx.x % GL, slot = blockIdx.x / GL, nslots = gridDim.x / GL;
   const int n_groups = (p.n_cw + GL - 1) / GL;
-  const int R = p.N - p.K;
 
   for (int g = slot; g < n_groups; g += nslots) {
     const int lanes_here = min(GL, p.n_cw - g * GL);
@@ -178,10 +282,9 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const LdpcPara
     }
     __syncthreads();
 
-    int trials = p.max_trials, iters = 0, lane_bad = 0;
+    int trials = p.max_trials, iters = 0;
     for (;;) {
-      int bad = (tid < 360) ? syndrome_rows<CNL>(post, p, tid) : 0;
-      lane_bad = __syncthreads_or(bad);
+      const int lane_bad = __syncthreads_or(syndrome_bad<CNL>(post, hb, p));
       int group_bad = lane_bad;
       if (GL > 1) {
         if (tid == 0) {
@@ -197,18 +300,68 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const LdpcPara
       if (!(group_bad && --trials >= 0)) break;
       // ---- one update() ----
       for (int i = 0; i < p.q; ++i) {
-        const int cnt = __ldg(p.cnt + i);
-        const int nl = __ldg(p.nlev + i);
-        const uint32_t* edge_i = p.edge + i * CNL;
+        const int cnt = p.cnt[i];
+        const int nl = p.nlev[i];
+        const uint16_t* ea = p.ea + i * CNL;
+        const uint16_t* et = p.et + i * CNL;
+        CheckNode<CNL, ST> cn;
         if (nl == 1) {
-          if (tid < 360) check_node<CNL, ST>(post, state, edge_i, cnt, i, tid, p.K, p.q);
+          if (tid < 360) {
+            cn.begin(post, state[i * 360 + tid]);
+            if (cnt == CNL) {
+              cn.template load<ALL_SLOTS>(ea, et, cnt, ~0u, true, i, tid, p.K, p.q);
+              cn.template store<ALL_SLOTS>(cnt, ~0u, true, i, tid);
+            } else {
+              cn.template load<PREDICATED>(ea, et, cnt, ~0u, true, i, tid, p.K, p.q);
+              cn.template store<PREDICATED>(cnt, ~0u, true, i, tid);
+            }
+            state[i * 360 + tid] = cn.finish();
+          }
           __syncthreads();
         } else {
-          const int mylev = (tid < 360) ? __ldg(p.level + (int)__ldg(p.cidx + i) * 360 + tid) : 0;
-          for (int l = 1; l <= nl; ++l) {
-            if (mylev == l) check_node<CNL, ST>(post, state, edge_i, cnt, i, tid, p.K, p.q);
-            __syncthreads();
+          // Two check nodes of this layer use the same bit: the reference runs j = 0..359 serially, so
+          // the smaller j must finish that bit first.  Private edges go in parallel (before / after),
+          // shared edges are resolved level by level along the dependency chains.
+          const uint32_t sh = p.shared[i];
+          int mylev = 0;
+          if (tid < 360) {
+            mylev = __ldg(p.level + (int)p.cidx[i] * 360 + tid);
+            cn.begin(post, state[i * 360 + tid]);
+            cn.template load<PREDICATED>(ea, et, cnt, ~sh, true, i, tid, p.K, p.q);
           }
+          if (__popc(sh) == 2) {
+            // one pair of shared edges (the common case): addresses and stored messages are prepared
+            // up front so that a level is just load -> min/sign merge -> store on two posteriors
+            const int cA = __ffs(sh) - 1, cB = 31 - __clz(sh);
+            int aA = tid + (int)ea[cA], aB = tid + (int)ea[cB];
+            if (tid >= (int)et[cA]) aA -= 360;
+            if (tid >= (int)et[cB]) aB -= 360;
+            if (tid >= 360) { aA = 0; aB = 0; }
+            const int nA = cn.stored_neg(cA), nB = cn.stored_neg(cB);
+            for (int l = 1; l <= nl; ++l) {
+              if (mylev == l) {
+                const int vA = cn.shared_in(cA, aA, nA);
+                const int vB = cn.shared_in(cB, aB, nB);
+                const int m0 = cn.key0 >> 5, idn = cn.key0 & 31, m1 = cn.key1 >> 5;
+                cn.shared_out(cA, aA, vA, m0, m1, idn);
+                cn.shared_out(cB, aB, vB, m0, m1, idn);
+              }
+              __syncthreads();
+            }
+          } else {
+            for (int l = 1; l <= nl; ++l) {
+              if (mylev == l) {
+                cn.template load<BRANCHED>(ea, et, cnt, sh, false, i, tid, p.K, p.q);
+                cn.template store<BRANCHED>(cnt, sh, false, i, tid);
+              }
+              __syncthreads();
+            }
+          }
+          if (tid < 360) {
+            cn.template store<PREDICATED>(cnt, ~sh, true, i, tid);
+            state[i * 360 + tid] = cn.finish();
+          }
+          __syncthreads();
         }
       }
       ++iters;
@@ -308,8 +461,8 @@ struct LdpcDeviceCode {
   int cnl = 0;              // instantiated bucket
   size_t state_bytes = 4, smem = 0;
   int blocks_per_sm = 0;
-  uint32_t* d_edge = nullptr; uint8_t* d_cnt = nullptr; int16_t* d_cidx = nullptr;
-  uint8_t* d_nlev = nullptr; uint8_t* d_level = nullptr;
+  uint8_t* d_level = nullptr;
+  LdpcParams proto;         // schedule part of the kernel parameters, filled once
 };
 
 static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
@@ -321,25 +474,26 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
   const LdpcSchedule& s = d->s;
   d->cnl = 0;
   for (int b : kCnlBuckets) if (b >= s.cnl_max) { d->cnl = b; break; }
-  if (!d->cnl) { delete d; ctx->err = "LDPC code degree not instantiated"; return T2B200_ERR_ARG; }
+  if (!d->cnl || s.q > kMaxLayers || s.q * d->cnl > kMaxEdgeWords) {
+    delete d; ctx->err = "LDPC code geometry not instantiated"; return T2B200_ERR_ARG;
+  }
   d->state_bytes = d->cnl + 2 <= 15 ? 4 : 8;
-  d->smem = (size_t)((s.N + 15) & ~15) + (size_t)s.R * d->state_bytes;
-  // edge table re-strided to the instantiated CNL
-  std::vector<uint32_t> edge((size_t)s.q * d->cnl, 0);
-  for (int i = 0; i < s.q; ++i)
-    for (int c = 0; c < s.cnl_max; ++c) edge[(size_t)i * d->cnl + c] = s.edge[(size_t)i * s.cnl_max + c];
+  // posteriors | check-node state | packed sign plane (+ 2 padding words, rounded)
+  d->smem = (size_t)((s.N + 15) & ~15) + (size_t)s.R * d->state_bytes + (size_t)(((s.N + 31) / 32 + 3) & ~1) * 4;
+  LdpcParams& p = d->proto;
+  memset(&p, 0, sizeof(p));
+  p.N = s.N; p.K = s.K; p.q = s.q;
+  for (int i = 0; i < s.q; ++i) {
+    for (int c = 0; c < s.cnl_max; ++c) {
+      p.ea[i * d->cnl + c] = (uint16_t)(s.edge[(size_t)i * s.cnl_max + c] & 0xffffu);
+      p.et[i * d->cnl + c] = (uint16_t)(s.edge[(size_t)i * s.cnl_max + c] >> 16);
+    }
+    p.shared[i] = s.shared[i]; p.cidx[i] = s.conflict_index[i]; p.cnt[i] = s.cnt[i]; p.nlev[i] = s.nlev[i];
+  }
   std::vector<uint8_t> level = s.level; if (level.empty()) level.resize(360, 1);
-  T2_CUDA(ctx, cudaMalloc(&d->d_edge, edge.size() * 4));
-  T2_CUDA(ctx, cudaMalloc(&d->d_cnt, s.q));
-  T2_CUDA(ctx, cudaMalloc(&d->d_cidx, s.q * 2));
-  T2_CUDA(ctx, cudaMalloc(&d->d_nlev, s.q));
   T2_CUDA(ctx, cudaMalloc(&d->d_level, level.size()));
-  T2_CUDA(ctx, cudaMemcpyAsync(d->d_edge, edge.data(), edge.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  T2_CUDA(ctx, cudaMemcpyAsync(d->d_cnt, s.cnt.data(), s.q, cudaMemcpyHostToDevice, ctx->stream));
-  T2_CUDA(ctx, cudaMemcpyAsync(d->d_cidx, s.conflict_index.data(), s.q * 2, cudaMemcpyHostToDevice, ctx->stream));
-  T2_CUDA(ctx, cudaMemcpyAsync(d->d_nlev, s.nlev.data(), s.q, cudaMemcpyHostToDevice, ctx->stream));
-  T2_CUDA(ctx, cudaMemcpyAsync(d->d_level, level.data(), level.size(), cudaMemcpyHostToDevice, ctx->stream));
-  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+  T2_CUDA(ctx, cudaMemcpy(d->d_level, level.data(), level.size(), cudaMemcpyHostToDevice));
+  p.level = d->d_level;
   T2_CUDA(ctx, occupancy_dispatch(d->cnl, d->smem, &d->blocks_per_sm));
   if (d->blocks_per_sm < 1) { ctx->err = "LDPC kernel does not fit on an SM"; return T2B200_ERR_CUDA; }
   ctx->ldpc[code] = d;
@@ -350,9 +504,8 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
 void t2_ldpc_free(t2b200_ctx* ctx)
 {
   for (auto& kv : ctx->ldpc) {
-    LdpcDeviceCode* d = kv.second;
-    cudaFree(d->d_edge); cudaFree(d->d_cnt); cudaFree(d->d_cidx); cudaFree(d->d_nlev); cudaFree(d->d_level);
-    delete d;
+    cudaFree(kv.second->d_level);
+    delete kv.second;
   }
   ctx->ldpc.clear();
 }
@@ -401,7 +554,7 @@ extern "C" int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, 
   }
   const size_t out_row = (flags & T2B200_LDPC_PACK_BITS) ? (size_t)k_out / 8 : (size_t)k_out;
 
-  LdpcParams p{};
+  LdpcParams p = d->proto;
   const void* d_llr; void *d_bits = nullptr, *d_tr = nullptr, *d_it = nullptr, *d_post = nullptr;
   if ((rc = t2_to_device(ctx, 0, llr, (size_t)n_cw * s.N, &d_llr))) return rc;
   if (bits_out && (rc = t2_out_device(ctx, 1, bits_out, out_row * n_cw, &d_bits))) return rc;
@@ -413,8 +566,7 @@ extern "C" int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, 
   p.post_out = (int8_t*)d_post;
   p.n_cw = n_cw; p.max_trials = max_trials; p.flags = flags;
   p.group_lanes = (flags & T2B200_LDPC_GROUP32) ? 32 : 1;
-  p.N = s.N; p.K = s.K; p.q = s.q; p.k_out = k_out;
-  p.edge = d->d_edge; p.cnt = d->d_cnt; p.cidx = d->d_cidx; p.nlev = d->d_nlev; p.level = d->d_level;
+  p.k_out = k_out;
   p.prbs = ctx->d_prbs;
 
   const int capacity = d->blocks_per_sm * ctx->sm_count;

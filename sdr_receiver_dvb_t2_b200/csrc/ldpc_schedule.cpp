@@ -36,11 +36,14 @@ bool t2_build_ldpc_schedule(int code, LdpcSchedule& s)
     s.links_total += 360 * (int)layer[i].size();
   }
   s.edge.assign((size_t)q * s.cnl_max, 0);
-  s.conflict_index.assign(q, -1); s.nlev.assign(q, 1); s.level.clear(); s.total_substeps = 0;
+  s.shared.assign(q, 0); s.conflict_index.assign(q, -1); s.nlev.assign(q, 1); s.level.clear(); s.total_substeps = 0;
   for (int i = 0; i < q; ++i) {
     auto& L = layer[i];
     for (size_t c = 0; c < L.size(); ++c)
-      s.edge[(size_t)i * s.cnl_max + c] = (uint32_t)(360 * L[c].g) | ((uint32_t)((360 - L[c].jx) % 360) << 16);
+    {
+      const int sh = (360 - L[c].jx) % 360;
+      s.edge[(size_t)i * s.cnl_max + c] = (uint32_t)(360 * L[c].g + sh) | ((uint32_t)(360 - sh) << 16);
+    }
     // shared bits: two entries of the same bit-group in this layer
     std::array<std::vector<int>, 360> before;   // before[j] = check nodes that must run before j
     bool conflict = false;
@@ -48,6 +51,7 @@ bool t2_build_ldpc_schedule(int code, LdpcSchedule& s)
       for (size_t y = x + 1; y < L.size(); ++y)
         if (L[x].g == L[y].g) {
           conflict = true;
+          s.shared[i] |= (1u << x) | (1u << y);
           for (int m = 0; m < 360; ++m) {
             int ja = (L[x].jx + m) % 360, jb = (L[y].jx + m) % 360;
             before[std::max(ja, jb)].push_back(std::min(ja, jb));

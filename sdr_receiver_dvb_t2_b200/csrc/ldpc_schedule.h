@@ -17,8 +17,11 @@ struct LdpcSchedule {
   int cnl_max = 0;                 // most data edges on any check node (LINKS_MAX_CN - 2)
   int links_total = 0;
   std::vector<uint8_t> cnt;        // [q] data edges per check node of layer i
-  std::vector<uint32_t> edge;      // [q][cnl_max]  bit-group base (low 16) | shift (high 16):
-                                   //   CN (i,j) edge c reads posterior base + (j + shift) mod 360
+  std::vector<uint32_t> edge;      // [q][cnl_max]  (360*g + shift) in the low 16 bits | (360 - shift) << 16:
+                                   //   CN (i,j) edge c reads posterior 360*g + (j + shift) mod 360
+                                   //   = j + low16 - (j >= high16 ? 360 : 0)
+  std::vector<uint32_t> shared;    // [q] bit c set: data edge c of this layer reads a bit-group that another
+                                   //   edge of the same layer reads too (two check nodes share each such bit)
   // Exact emulation of the reference's serial j = 0..359 order inside a layer: two check nodes of
   // one layer that share a bit must run smaller-j first.  level[][] is the longest-chain depth.
   std::vector<int16_t> conflict_index;  // [q] row into level[], or -1 when the layer has no shared bit

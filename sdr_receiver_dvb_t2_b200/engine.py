@@ -104,7 +104,7 @@ class Engine:
         self.h = h
         self.device = device
         if stream is not None:
-            self._chk(self.L.t2b200_set_stream(self.h, C.c_void_p(stream)))
+            self.set_stream(stream)
 
     def close(self):
         if getattr(self, 'h', None):
@@ -125,7 +125,15 @@ class Engine:
         self._chk(self.L.t2b200_sync(self.h))
 
     def set_stream(self, stream):
-        self._chk(self.L.t2b200_set_stream(self.h, C.c_void_p(stream or 0)))
+        """stream: a cudaStream_t handle as int (torch: stream.cuda_stream); 0 = the legacy default
+        stream (what torch's default stream is), None = back to the context's own stream"""
+        if stream is None:
+            h = 0
+        elif stream == 0:
+            h = 1          # cudaStreamLegacy
+        else:
+            h = stream
+        self._chk(self.L.t2b200_set_stream(self.h, C.c_void_p(h)))
 
     @property
     def launches(self):
