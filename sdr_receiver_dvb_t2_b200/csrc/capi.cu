@@ -116,6 +116,10 @@ void t2b200_destroy(t2b200_ctx* ctx)
   if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
   for (auto& s : ctx->dev) if (s.p) cudaFree(s.p);
   for (auto& s : ctx->pin) if (s.p) cudaFreeHost(s.p);
+  if (ctx->s_in) {
+    cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_in[i]); cudaEventDestroy(ctx->ev_k[i]); cudaEventDestroy(ctx->ev_out[i]); }
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

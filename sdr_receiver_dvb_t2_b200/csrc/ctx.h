@@ -22,6 +22,8 @@ struct t2b200_ctx {
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of the host-buffer pipelines
+  cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
   std::string err;
   long long launches = 0;
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id

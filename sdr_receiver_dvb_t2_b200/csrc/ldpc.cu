@@ -533,6 +533,106 @@ extern "C" int t2b200_ldpc_n(int code) { auto t = t2_ldpc_code_data(code); retur
 extern "C" int t2b200_ldpc_k(int code) { auto t = t2_ldpc_code_data(code); return t ? t->K : 0; }
 extern "C" int t2b200_ldpc_k_bch(int code) { return t2_ldpc_k_bch(code); }
 
+// Launch the decoder on device-resident buffers (all pointers device memory or null).
+// sync_off: first group-sync row this launch may use (rows are zeroed by the caller).
+static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, int n_cw, uint8_t* d_bits,
+                       int32_t* d_tr, int32_t* d_it, int8_t* d_post, int max_trials, unsigned flags, int k_out,
+                       size_t sync_off, cudaStream_t st)
+{
+  LdpcParams p = d->proto;
+  p.llr = d_llr; p.bits = d_bits; p.trials_left = d_tr; p.iters = d_it; p.post_out = d_post;
+  p.n_cw = n_cw; p.max_trials = max_trials; p.flags = flags;
+  p.group_lanes = (flags & T2B200_LDPC_GROUP32) ? 32 : 1;
+  p.k_out = k_out;
+  p.prbs = ctx->d_prbs;
+  const int capacity = d->blocks_per_sm * ctx->sm_count;
+  int grid;
+  if (p.group_lanes > 1) {
+    const int n_groups = (n_cw + 31) / 32;
+    const int slots = std::min(capacity / 32, n_groups);
+    if (slots < 1) { ctx->err = "GPU cannot co-schedule one 32-lane group"; return T2B200_ERR_CUDA; }
+    grid = slots * 32;
+    p.gsync = ctx->d_group_sync + sync_off * kSyncStride;
+  } else {
+    grid = std::min(capacity, n_cw);
+  }
+  T2_CUDA(ctx, launch_dispatch(d->cnl, p, grid, d->smem, st));
+  ctx->launches++;
+  return T2B200_OK;
+}
+
+static int ensure_group_sync(t2b200_ctx* ctx, int n_groups, cudaStream_t st)
+{
+  const size_t need = (size_t)n_groups * kSyncStride * sizeof(unsigned);
+  if (ctx->group_sync_cap < need) {
+    T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
+    ctx->d_group_sync = nullptr; ctx->group_sync_cap = 0;
+    T2_CUDA(ctx, cudaMalloc(&ctx->d_group_sync, need + need / 2));
+    ctx->group_sync_cap = need + need / 2;
+  }
+  T2_CUDA(ctx, cudaMemsetAsync(ctx->d_group_sync, 0, need, st));
+  return T2B200_OK;
+}
+
+// Host-buffer path: the batch is cut into chunks that flow through a 3-stage pipeline
+// (H2D on one copy stream | decode on the context stream | D2H on another copy stream) over
+// double-buffered device scratch, so PCIe transfers hide behind the decode of the neighbour chunks.
+static int ldpc_decode_pipelined(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* llr, int n_cw, uint8_t* bits_out,
+                                 int32_t* trials_left, int32_t* iterations, int max_trials, unsigned flags,
+                                 int k_out, size_t out_row)
+{
+  const int N = d->s.N;
+  const int chunk = 512;
+  const int n_chunks = (n_cw + chunk - 1) / chunk;
+  int rc;
+  if (!ctx->s_in) {
+    T2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    T2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      T2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      T2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+      T2_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  void *b_in, *b_out, *b_tr, *b_it;
+  if ((rc = t2_dev_scratch(ctx, 0, 2 * (size_t)chunk * N, &b_in))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 1, 2 * (size_t)chunk * out_row, &b_out))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 2, 4 * (size_t)n_cw, &b_tr))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 3, 4 * (size_t)n_cw, &b_it))) return rc;
+  if (flags & T2B200_LDPC_GROUP32)
+    if ((rc = ensure_group_sync(ctx, (n_cw + 31) / 32 + n_chunks, ctx->stream))) return rc;
+  // the copy streams must not start before earlier work on the context stream (memset above, previous calls)
+  T2_CUDA(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
+  T2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[0], 0));
+  T2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[0], 0));
+  size_t sync_off = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b = c & 1, c0 = c * chunk, n = std::min(chunk, n_cw - c0);
+    int8_t* din = (int8_t*)b_in + (size_t)b * chunk * N;
+    uint8_t* dout = (uint8_t*)b_out + (size_t)b * chunk * out_row;
+    if (c >= 2) T2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[b], 0));      // decode c-2 consumed din
+    T2_CUDA(ctx, cudaMemcpyAsync(din, llr + (size_t)c0 * N, (size_t)n * N, cudaMemcpyHostToDevice, ctx->s_in));
+    T2_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+    T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+    if (c >= 2) T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // D2H c-2 drained dout
+    if ((rc = ldpc_launch(ctx, d, din, n, bits_out ? dout : nullptr, (int32_t*)b_tr + c0, (int32_t*)b_it + c0, nullptr,
+                          max_trials, flags, k_out, sync_off, ctx->stream))) return rc;
+    sync_off += (n + 31) / 32;
+    T2_CUDA(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
+    if (bits_out) {
+      T2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
+      T2_CUDA(ctx, cudaMemcpyAsync(bits_out + (size_t)c0 * out_row, dout, (size_t)n * out_row, cudaMemcpyDeviceToHost, ctx->s_out));
+      T2_CUDA(ctx, cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+    }
+  }
+  if (trials_left) T2_CUDA(ctx, cudaMemcpyAsync(trials_left, b_tr, 4 * (size_t)n_cw, cudaMemcpyDeviceToHost, ctx->stream));
+  if (iterations) T2_CUDA(ctx, cudaMemcpyAsync(iterations, b_it, 4 * (size_t)n_cw, cudaMemcpyDeviceToHost, ctx->stream));
+  T2_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return T2B200_OK;
+}
+
 extern "C" int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, int n_cw, uint8_t* bits_out,
                                   int32_t* trials_left, int32_t* iterations, int8_t* post_out,
                                   int max_trials, unsigned flags)
@@ -554,42 +654,22 @@ extern "C" int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, 
   }
   const size_t out_row = (flags & T2B200_LDPC_PACK_BITS) ? (size_t)k_out / 8 : (size_t)k_out;
 
-  LdpcParams p = d->proto;
+  const bool host_in = !t2_is_device_ptr(llr);
+  const bool host_out = !bits_out || !t2_is_device_ptr(bits_out);
+  if (host_in && host_out && n_cw > 512 && !(flags & T2B200_LDPC_WANT_POST) &&
+      (!trials_left || !t2_is_device_ptr(trials_left)) && (!iterations || !t2_is_device_ptr(iterations)))
+    return ldpc_decode_pipelined(ctx, d, llr, n_cw, bits_out, trials_left, iterations, max_trials, flags, k_out, out_row);
+
   const void* d_llr; void *d_bits = nullptr, *d_tr = nullptr, *d_it = nullptr, *d_post = nullptr;
   if ((rc = t2_to_device(ctx, 0, llr, (size_t)n_cw * s.N, &d_llr))) return rc;
   if (bits_out && (rc = t2_out_device(ctx, 1, bits_out, out_row * n_cw, &d_bits))) return rc;
   if (trials_left && (rc = t2_out_device(ctx, 2, trials_left, 4 * (size_t)n_cw, &d_tr))) return rc;
   if (iterations && (rc = t2_out_device(ctx, 3, iterations, 4 * (size_t)n_cw, &d_it))) return rc;
   if ((flags & T2B200_LDPC_WANT_POST) && (rc = t2_out_device(ctx, 4, post_out, (size_t)n_cw * s.N, &d_post))) return rc;
-
-  p.llr = (const int8_t*)d_llr; p.bits = (uint8_t*)d_bits; p.trials_left = (int32_t*)d_tr; p.iters = (int32_t*)d_it;
-  p.post_out = (int8_t*)d_post;
-  p.n_cw = n_cw; p.max_trials = max_trials; p.flags = flags;
-  p.group_lanes = (flags & T2B200_LDPC_GROUP32) ? 32 : 1;
-  p.k_out = k_out;
-  p.prbs = ctx->d_prbs;
-
-  const int capacity = d->blocks_per_sm * ctx->sm_count;
-  int grid;
-  if (p.group_lanes > 1) {
-    const int n_groups = (n_cw + 31) / 32;
-    int slots = std::min(capacity / 32, n_groups);
-    if (slots < 1) { ctx->err = "GPU cannot co-schedule one 32-lane group"; return T2B200_ERR_CUDA; }
-    grid = slots * 32;
-    size_t need = (size_t)n_groups * kSyncStride * sizeof(unsigned);
-    if (ctx->group_sync_cap < need) {
-      if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
-      T2_CUDA(ctx, cudaMalloc(&ctx->d_group_sync, need));
-      ctx->group_sync_cap = need;
-    }
-    T2_CUDA(ctx, cudaMemsetAsync(ctx->d_group_sync, 0, need, ctx->stream));
-    p.gsync = ctx->d_group_sync;
-  } else {
-    grid = std::min(capacity, n_cw);
-  }
-  T2_CUDA(ctx, launch_dispatch(d->cnl, p, grid, d->smem, ctx->stream));
-  ctx->launches++;
-
+  if (flags & T2B200_LDPC_GROUP32)
+    if ((rc = ensure_group_sync(ctx, (n_cw + 31) / 32, ctx->stream))) return rc;
+  if ((rc = ldpc_launch(ctx, d, (const int8_t*)d_llr, n_cw, (uint8_t*)d_bits, (int32_t*)d_tr, (int32_t*)d_it,
+                        (int8_t*)d_post, max_trials, flags, k_out, 0, ctx->stream))) return rc;
   if (bits_out && (rc = t2_finish_out(ctx, bits_out, d_bits, out_row * n_cw))) return rc;
   if (trials_left && (rc = t2_finish_out(ctx, trials_left, d_tr, 4 * (size_t)n_cw))) return rc;
   if (iterations && (rc = t2_finish_out(ctx, iterations, d_it, 4 * (size_t)n_cw))) return rc;
