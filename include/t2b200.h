@@ -100,6 +100,42 @@ int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, int n_codew
 int t2b200_bch_descramble(t2b200_ctx* ctx, int code, const uint8_t* bits_in, int n_words,
                           uint8_t* bits_out);
 
+/* ---- K3: time / cell de-interleaver + cyclic-Q-delay removal ------------------------------- */
+/* Host-side table builders (no GPU needed):
+ * cell de-interleaver permutation of time_deinterleaver::address_cell_deinterleaving
+ * (time_deinterleaver.cpp:174-266): perm_out int32[n_fec_blocks * cells_per_fec];
+ * bit de-interleaver + demux address table of llr_demapper::address_generator
+ * (llr_demapper.cpp:110-130, constants llr_demapper.h:64-78): address_out int32[64800 | 16200].        */
+int t2b200_cell_permutation(int n_fec_blocks, int cells_per_fec, int32_t* perm_out);
+int t2b200_demap_address_table(int fec_type, int mod, int code_rate, int32_t* address_out);
+
+/* Replaces time_deinterleaver::start for one PLP (time_deinterleaver.cpp:38-145): geometry from
+ * (fec_type, mod), permutation for plp_num_blocks_max FEC blocks.  permutation == NULL builds it
+ * natively; the drop-in facade may pass the reference's own table.                                     */
+int t2b200_ti_configure(t2b200_ctx* ctx, int plp, int fec_type, int mod, int n_fec_blocks_max,
+                        const int32_t* permutation);
+
+/* Replaces the cell loop of time_deinterleaver::execute (time_deinterleaver.cpp:316-374) for whole TI
+ * blocks: cells_in = complex<float> cells of n_ti_blocks consecutive TI blocks in arrival order
+ * (block b holds n_fec_per_block[b] * cells_per_fec cells), cells_out = the same blocks de-interleaved,
+ * with the Q component moved back one cell inside each FEC block (unconditionally, like the reference). */
+int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cells_in, int n_ti_blocks,
+                           const int32_t* n_fec_per_block, float* cells_out);
+
+/* ---- K4: soft demapper + bit de-interleave / demux ------------------------------------------ */
+/* Replaces llr_demapper::execute -> qpsk/qam16/qam64/qam256 (llr_demapper.cpp:132-768) for
+ * n_ti_blocks TI blocks of one PLP:
+ *   ti_cells      complex<float>, de-interleaved TI blocks back to back; DEROTATED IN PLACE when
+ *                 rotation != 0, exactly like the reference (llr_demapper.cpp:555-557)
+ *   llr_out       int8[sum(n_fec_per_block)][64800 | 16200], codeword order, ready for t2b200_ldpc_decode
+ *   snr_out       float[n_ti_blocks] or NULL: the value the reference emits as signal_noise_ratio
+ *   precision_out float[n_ti_blocks] or NULL: 8*a*sum_s/sum_e actually used
+ *   precision_in  float[n_ti_blocks] or NULL: override (parity tests pin the one order-dependent
+ *                 float reduction of this stage with it)                                              */
+int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, const int32_t* n_fec_per_block,
+                 int mod, int rotation, int fec_type, int code_rate, int8_t* llr_out,
+                 float* snr_out, float* precision_out, const float* precision_in);
+
 #ifdef __cplusplus
 }
 #endif

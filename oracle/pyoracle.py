@@ -45,6 +45,11 @@ def port():
         L.port_ldpc_encode.argtypes = [C.c_int, _u8p, _u8p]
         L.port_bch_strip_descramble.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
         L.port_bb_prbs.argtypes = [_u8p, C.c_int]
+        L.port_cell_permutation.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.port_ti_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.port_demap_address_for.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.port_demap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_float]
+        L.port_demap.restype = C.c_float
         _port = L
     return _port
 
@@ -130,3 +135,206 @@ def make_llr(code, n_cw, ebn0_db, seed, scale=2.0, all_zero=False):
     y = x + sigma * rng.standard_normal(x.shape, dtype=np.float32)
     llr = 2.0 * y / (sigma * sigma)
     return np.clip(np.rint(scale * llr), -128, 127).astype(np.int8), info
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole reference receiver, stage by stage (oracle/ref_chain.cc -> oracle/_ref/libref_chain.so)
+_ref_chain = None
+FFT_MODE = {'16K': 4, '32K': 5}                      # dvbt2_definition.h:121-131
+GI = {'1/32': 0, '1/16': 1, '1/8': 2, '1/4': 3, '1/128': 4, '19/128': 5, '19/256': 6}
+PARAM_NAMES = ['fft_size', 'k_total', 'l_nulls', 'c_p2', 'c_data', 'n_fc', 'c_fc', 'n_data', 'len_frame', 'l_fc',
+               'n_p2', 'guard_interval_size', 'k_ext']
+_f32p = np.ctypeslib.ndpointer(np.float32, flags='C')
+_i32p = np.ctypeslib.ndpointer(np.int32, flags='C')
+
+
+def ref_chain():
+    """One receiver instance per process (the reference keeps static state)."""
+    global _ref_chain
+    if _ref_chain is None:
+        L = C.CDLL(os.path.join(_HERE, '_ref', 'libref_chain.so'))
+        L.ref_rx_init.argtypes = [C.c_int] * 6 + [_i32p]
+        L.ref_rx_tables_data.argtypes = [C.c_int, _i32p, _f32p]
+        L.ref_rx_tables_p2.argtypes = [_i32p, _f32p]
+        L.ref_rx_tables_fc.argtypes = [_i32p, _f32p]
+        L.ref_rx_tables_h.argtypes = [C.c_int, _i32p, _i32p]
+        L.ref_rx_amps.argtypes = [C.POINTER(C.c_float)] * 3
+        L.ref_fft.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_data_symbol.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ref_fc_symbol.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ref_p2_symbol.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ref_fec_start.argtypes = [C.c_int, _i32p, C.c_int, C.c_int]
+        L.ref_fec_chain.argtypes = [C.c_int] * 4
+        L.ref_fec_feed_p2.argtypes = [_i32p, _i32p, C.c_int, C.c_void_p]
+        L.ref_fec_feed.argtypes = [C.c_int, C.c_void_p]
+        L.ref_demap.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_ti_permutation.argtypes = [C.c_int, _i32p, C.c_int]
+        L.ref_demap_address.argtypes = [C.c_int, C.c_int, C.c_int, _i32p]
+        for n in ('ti_cells', 'ti_sizes', 'llr', 'ldpc_bits', 'bb_bits', 'bb_len', 'snr', 'ts', 'ts_datagrams'):
+            f = getattr(L, 'ref_tap_' + n)
+            f.argtypes = [C.c_void_p, C.c_longlong]
+            f.restype = C.c_longlong
+        L.ref_demod_new.argtypes = [C.c_float, C.c_int]
+        L.ref_demod_feed.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        _ref_chain = L
+    return _ref_chain
+
+
+class RefRx:
+    """Reference demodulator-side stages for one transmission mode."""
+
+    def __init__(self, fft='32K', carrier_ext=True, pp=7, gi='1/128', n_data=59, papr=0):
+        self.L = ref_chain()
+        out = np.zeros(13, np.int32)
+        self.L.ref_rx_init(FFT_MODE[fft], 1 if carrier_ext else 0, pp - 1, GI[gi], n_data, papr, out)
+        self.p = dict(zip(PARAM_NAMES, [int(x) for x in out]))
+
+    def tables(self):
+        """dict of the init-time tables the drop-in facade hands over to the GPU engine"""
+        p, L = self.p, self.L
+        k = p['k_total']
+        t = {}
+        nd = p['len_frame'] - p['l_fc'] - p['n_p2']
+        t['data_map'] = np.zeros((nd, k), np.int32)
+        t['data_ref'] = np.zeros((nd, k), np.float32)
+        for i in range(nd):
+            L.ref_rx_tables_data(i, t['data_map'][i], t['data_ref'][i])
+        t['p2_map'] = np.zeros(k, np.int32)
+        t['p2_ref'] = np.zeros(k, np.float32)
+        L.ref_rx_tables_p2(t['p2_map'], t['p2_ref'])
+        if p['l_fc']:
+            t['fc_map'] = np.zeros(k, np.int32)
+            t['fc_ref'] = np.zeros(k, np.float32)
+            L.ref_rx_tables_fc(t['fc_map'], t['fc_ref'])
+        for kind, name in enumerate(['p2', 'data', 'fc']):
+            e, o = np.zeros(32768, np.int32), np.zeros(32768, np.int32)
+            L.ref_rx_tables_h(kind, e, o)
+            t['h_even_' + name], t['h_odd_' + name] = e, o
+        a = [C.c_float() for _ in range(3)]
+        L.ref_rx_amps(*[C.byref(x) for x in a])
+        t['amp_p2'], t['amp_sp'], t['amp_cp'] = [x.value for x in a]
+        return t
+
+    def fft(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        out = np.empty_like(x)
+        self.L.ref_fft(x.ctypes.data, out.ctypes.data)
+        return out
+
+    def data_symbol(self, idx_symbol, freq):
+        freq = np.ascontiguousarray(freq, np.complex64)
+        out = np.empty(self.p['c_data'], np.complex64)
+        sro, ph = C.c_float(), C.c_float()
+        self.L.ref_data_symbol(idx_symbol, freq.ctypes.data, out.ctypes.data, C.byref(sro), C.byref(ph))
+        return out, sro.value, ph.value
+
+    def fc_symbol(self, freq):
+        freq = np.ascontiguousarray(freq, np.complex64)
+        out = np.empty(self.p['n_fc'], np.complex64)
+        sro, ph = C.c_float(), C.c_float()
+        self.L.ref_fc_symbol(freq.ctypes.data, out.ctypes.data, C.byref(sro), C.byref(ph))
+        return out, sro.value, ph.value
+
+    def p2_symbol(self, freq):
+        freq = np.ascontiguousarray(freq, np.complex64)
+        out = np.empty(self.p['c_p2'], np.complex64)
+        sro, ph = C.c_float(), C.c_float()
+        crc = self.L.ref_p2_symbol(freq.ctypes.data, out.ctypes.data, C.byref(sro), C.byref(ph))
+        return out, sro.value, ph.value, crc
+
+
+def _tap(L, name, dtype):
+    f = getattr(L, 'ref_tap_' + name)
+    n = f(None, 0)
+    a = np.empty(n, dtype)
+    if n:
+        f(a.ctypes.data, n)
+    return a
+
+
+class RefFec:
+    """Reference FEC chain (time_deinterleaver -> llr_demapper -> ldpc_decoder -> bch_decoder -> bb_de_header)
+    behind a RefRx (needs its dvbt2_parameters).  plps: list of dicts(id, cod, mod, rot, fec, blocks_max, ti_len, ti_type)."""
+
+    def __init__(self, rx, plps, l1_post_size, need_plp=0):
+        self.L = rx.L
+        self.rx = rx
+        d = np.array([[p['id'], p['cod'], p['mod'], p['rot'], p['fec'], p['blocks_max'], p['ti_len'], p['ti_type']]
+                      for p in plps], np.int32)
+        self.L.ref_fec_start(len(plps), np.ascontiguousarray(d.reshape(-1)), l1_post_size, need_plp)
+        self.n_plp = len(plps)
+
+    def chain(self, after_ti=True, after_demap=True, after_ldpc=True, after_bch=True):
+        self.L.ref_fec_chain(int(after_ti), int(after_demap), int(after_ldpc), int(after_bch))
+
+    def feed_p2(self, starts, num_blocks, cells):
+        cells = np.ascontiguousarray(cells, np.complex64).copy()
+        self.L.ref_fec_feed_p2(np.asarray(starts, np.int32), np.asarray(num_blocks, np.int32), len(cells), cells.ctypes.data)
+
+    def feed(self, cells):
+        cells = np.ascontiguousarray(cells, np.complex64).copy()
+        self.L.ref_fec_feed(len(cells), cells.ctypes.data)
+
+    def demap(self, cells, plp=0):
+        cells = np.ascontiguousarray(cells, np.complex64).copy()
+        self.L.ref_demap(len(cells), cells.ctypes.data, plp)
+
+    def permutation(self, plp=0):
+        out = np.zeros(1 << 22, np.int32)
+        n = self.L.ref_ti_permutation(plp, out, len(out))
+        return out[:n].copy()
+
+    def taps(self):
+        L = self.L
+        return {'ti_cells': _tap(L, 'ti_cells', np.complex64), 'ti_sizes': _tap(L, 'ti_sizes', np.int32),
+                'llr': _tap(L, 'llr', np.int8), 'ldpc_bits': _tap(L, 'ldpc_bits', np.uint8),
+                'bb_bits': _tap(L, 'bb_bits', np.uint8), 'bb_len': _tap(L, 'bb_len', np.int32),
+                'snr': _tap(L, 'snr', np.float32), 'ts': _tap(L, 'ts', np.uint8),
+                'ts_datagrams': _tap(L, 'ts_datagrams', np.int32)}
+
+    def clear(self):
+        self.L.ref_tap_clear()
+
+
+# ---- port oracle: FEC front half (oracle/port/fec_port.c) ----
+def port_cell_permutation(n_fec, cells_per_fec):
+    out = np.zeros(n_fec * cells_per_fec, np.int32)
+    port().port_cell_permutation(n_fec, cells_per_fec, out.ctypes.data)
+    return out
+
+
+def port_ti_blocks(cells, n_fec_per_block, cells_per_fec, perm, state=None):
+    """cells complex64 stream of consecutive TI blocks -> de-interleaved blocks.  state = [end_cell, q_first]
+    carried like the reference's members (zero for a fresh receiver)."""
+    cells = np.ascontiguousarray(cells, np.complex64)
+    out = np.zeros_like(cells)
+    end_cell, q_first = C.c_int(0 if state is None else state[0]), C.c_float(0.0 if state is None else state[1])
+    perm = np.ascontiguousarray(perm, np.int32)
+    off = 0
+    for nf in n_fec_per_block:
+        n = nf * cells_per_fec
+        src, dst = cells[off:off + n], out[off:off + n]
+        port().port_ti_block(src.ctypes.data, nf, cells_per_fec, perm.ctypes.data, dst.ctypes.data,
+                             C.byref(end_cell), C.byref(q_first))
+        off += n
+    if state is not None:
+        state[0], state[1] = end_cell.value, q_first.value
+    return out
+
+
+def port_demap_address(fec_normal, mod, code_rate):
+    out = np.zeros(64800 if fec_normal else 16200, np.int32)
+    port().port_demap_address_for(int(fec_normal), mod, code_rate, out.ctypes.data)
+    return out
+
+
+def port_demap(cells, mod, rotation, fec_normal, code_rate, precision_in=0.0):
+    """one TI block; returns (llr int8[n_fec][N], snr, precision, derotated cells)"""
+    cells = np.ascontiguousarray(cells, np.complex64).copy()
+    nb = 64800 if fec_normal else 16200
+    cpf = nb // (2 * (mod + 1))
+    llr = np.zeros((len(cells) // cpf, nb), np.int8)
+    snr = C.c_float()
+    p = port().port_demap(cells.ctypes.data, len(cells), mod, int(rotation), int(fec_normal), code_rate,
+                          llr.ctypes.data, C.byref(snr), float(precision_in))
+    return llr, snr.value, p, cells

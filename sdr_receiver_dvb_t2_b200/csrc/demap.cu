@@ -1,0 +1,401 @@
+// K3: time / cell de-interleaver + cyclic-Q-delay removal;  K4: rotated-QAM soft demapper with the bit
+// de-interleaver (column twist) and demux folded into its store addresses.
+//
+// Reference semantics reproduced (paths relative to the reference's src/DVB_T2):
+//   time_deinterleaver.cpp:316-374   cell k of a TI block (arrival order) -> d = (k mod cols)*rows + k div cols,
+//                                    a = perm[d]; out[a].re = in.re; out[a-1 cyclic inside the FEC block].im = in.im
+//                                    (the Q component is ALWAYS moved back one cell, rotated constellation or not)
+//   llr_demapper.cpp:160-776         optional derotation by e^{-j theta}; sum_s / sum_e over the whole TI block from
+//                                    hard slicing (incl. the 64-QAM outer-level quirk, :407,:427, and QPSK's first-2048
+//                                    -cells rule, :185); precision = 8*a*sum_s/sum_e; per axis
+//                                    L0 = x, L1 = |x| - 8a, L2 = |L1| - 4a, L3 = |L2| - 2a (256-QAM; fewer for 64/16);
+//                                    round-to-nearest-even(L * precision); (int8) cast that WRAPS (QPSK saturates);
+//                                    store through address[] (:110-130)
+// B200 design: both stages are HBM-streaming permutations.  K3 is a coalesced read / scattered 4-byte
+// write pass whose working set (one TI block, <= 4.4 MB) lives in L2.  K4 runs one CTA per FECFRAME:
+// LLRs are produced into a 64.8 KB shared-memory image of the de-interleaved frame and leave the SM as
+// coalesced 16-byte stores, so the column-twist scatter never reaches HBM as byte writes.
+#include "ctx.h"
+#include "fec_tables.h"
+#include <algorithm>
+#include <cmath>
+
+struct TiPlp {
+  int cells_per_fec = 0, n_fec_max = 0, rows = 0;
+  int32_t* d_perm = nullptr;
+};
+struct DemapTable { int32_t* d_addr = nullptr; };
+struct TiDemapState {
+  std::map<int, TiPlp> plp;
+  std::map<int, DemapTable> addr;        // key fec_type*100 + mod*10 + code_rate class
+  double* d_partials = nullptr; size_t partial_cap = 0;
+};
+
+namespace {
+
+constexpr float kRot[4] = {0.506145483f, 0.293215314f, 0.150098316f, 0.062418810f};      // dvbt2_definition.h:45-48
+constexpr float kNorm[4] = {0.707106781f, 0.316227766f, 0.15430335f, 0.076696499f};      // dvbt2_definition.h:49-52
+
+// ---- K3 ------------------------------------------------------------------------------------
+struct TiBlockDesc { long long in_off, out_off; int n_fec; };
+
+__global__ void ti_deinterleave_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                       const int32_t* __restrict__ perm, const TiBlockDesc* __restrict__ blocks,
+                                       int rows, int cpf)
+{
+  const TiBlockDesc b = blocks[blockIdx.y];
+  const int cols = 5 * b.n_fec;
+  const int n = cols * rows;
+  const float2* src = in + b.in_off;
+  float* dst = reinterpret_cast<float*>(out + b.out_off);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const float2 c = __ldg(src + k);
+    const int col = k % cols, row = k / cols;
+    const int a = __ldg(perm + col * rows + row);
+    const int r = a % cpf;
+    const int qa = r == 0 ? a + cpf - 1 : a - 1;
+    dst[2 * a] = c.x;
+    dst[2 * qa + 1] = c.y;
+  }
+}
+
+// ---- K4 pass 1: derotate (in place, like the reference) + hard-decision statistics ------------
+template <int MOD>
+__device__ __forceinline__ float slice_axis(float x, float a)
+{
+  // nearest constellation level the way the reference's if-ladders pick it (strict > / < tests)
+  if (MOD == 0) return x > 0 ? a : -a;
+  if (MOD == 1) {
+    if (x > 0) return x > 2 * a ? 3 * a : a;
+    return x < -(2 * a) ? -(3 * a) : -a;
+  }
+  if (MOD == 2) {
+    if (x > 0) {
+      if (x > 4 * a) return x > 6 * a ? 7 * a : 5 * a;
+      return x > 2 * a ? 3 * a : a;
+    }
+    if (x < -(4 * a)) return x > 6 * a ? -(7 * a) : -(5 * a);   // llr_demapper.cpp:407,427: never -7a
+    return x < -(2 * a) ? -(3 * a) : -a;
+  }
+  // 256-QAM
+  const float ax = fabsf(x);
+  float s;
+  if (x > 0) {
+    if (x > 8 * a) { if (x > 12 * a) s = x > 14 * a ? 15 * a : 13 * a; else s = x > 10 * a ? 11 * a : 9 * a; }
+    else { if (x > 4 * a) s = x > 6 * a ? 7 * a : 5 * a; else s = x > 2 * a ? 3 * a : a; }
+    return s;
+  }
+  (void)ax;
+  if (x < -(8 * a)) { if (x < -(12 * a)) s = x < -(14 * a) ? 15 * a : 13 * a; else s = x < -(10 * a) ? 11 * a : 9 * a; }
+  else { if (x < -(4 * a)) s = x < -(6 * a) ? 7 * a : 5 * a; else s = x < -(2 * a) ? 3 * a : a; }
+  return -s;
+}
+
+struct DemapBlockDesc { long long cell_off; int n_cells; int first_fec; };
+
+// levels k*a must be the same floats the reference holds (norm_x_k = NORM * k.0f): computed as a*k in float
+template <int MOD>
+__global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
+                                   double* __restrict__ partials, int rotate, float rc, float rs)
+{
+  const DemapBlockDesc b = blocks[blockIdx.y];
+  float2* c = cells + b.cell_off;
+  const float a = kNorm[MOD];
+  const int n_stat = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;      // llr_demapper.cpp:185
+  double ss = 0.0, se = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < b.n_cells; k += gridDim.x * blockDim.x) {
+    float2 v = c[k];
+    if (rotate) {                       // _in[i] *= derotate (llr_demapper.cpp:555-557), no FMA contraction
+      const float re = __fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs));
+      const float im = __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc));
+      v = make_float2(re, im);
+      c[k] = v;
+    }
+    if (k < n_stat) {
+      const float sx = slice_axis<MOD>(v.x, a), sy = slice_axis<MOD>(v.y, a);
+      const float ex = __fsub_rn(v.x, sx), ey = __fsub_rn(v.y, sy);
+      ss += (double)__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy));
+      se += (double)__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+    }
+  }
+  // deterministic block reduction
+  __shared__ double sh[2][32];
+  for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); se += __shfl_xor_sync(0xffffffffu, se, o); }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][w] = ss; sh[1][w] = se; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0, a1 = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a0 += sh[0][i]; a1 += sh[1][i]; }
+    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 0] = a0;
+    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 1] = a1;
+  }
+}
+
+// fixed-order sum of the per-CTA partials -> precision and SNR per TI block
+template <int MOD>
+__global__ void demap_precision_kernel(const double* __restrict__ partials, int n_partials, float* __restrict__ precision,
+                                       float* __restrict__ snr, const float* __restrict__ precision_in)
+{
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  double ss = 0, se = 0;
+  for (int i = 0; i < n_partials; ++i) { ss += partials[((size_t)b * n_partials + i) * 2]; se += partials[((size_t)b * n_partials + i) * 2 + 1]; }
+  const float fs = (float)ss, fe = (float)se;
+  const float a8 = __fmul_rn(8.0f, kNorm[MOD]);
+  float p = __fdiv_rn(__fmul_rn(a8, fs), fe);              // 8.0f * NORM * sum_s / sum_e, left to right
+  if (precision_in) p = precision_in[b];
+  precision[b] = p;
+  if (snr) snr[b] = (MOD == 0 ? 10.0f : 20.0f) * log10f(fs / fe);
+}
+
+// (int8_t)(float) as x86-64 gcc compiles it: cvttss2si to int32 (0x80000000 when out of range), low byte
+__device__ __forceinline__ int wrap_i8(float r)
+{
+  if (!(fabsf(r) < 2147483648.0f)) return 0;
+  return (int)(int8_t)(__float2int_rz(r) & 0xff);
+}
+
+// ---- K4 pass 2: one CTA per FECFRAME -----------------------------------------------------------
+template <int MOD>
+__global__ void demap_llr_kernel(const float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
+                                 const float* __restrict__ precision, const int32_t* __restrict__ address,
+                                 int8_t* __restrict__ llr, int cpf, int fec_bits)
+{
+  extern __shared__ __align__(16) int8_t frame[];
+  constexpr int BPC = 2 * (MOD + 1);
+  const DemapBlockDesc b = blocks[blockIdx.y];
+  const int n_fec = b.n_cells / cpf;
+  const float a = kNorm[MOD];
+  const float p = precision[blockIdx.y];
+  for (int f = blockIdx.x; f < n_fec; f += gridDim.x) {
+    const float2* c = cells + b.cell_off + (size_t)f * cpf;
+    for (int k = threadIdx.x; k < cpf; k += blockDim.x) {
+      const float2 v = __ldg(c + k);
+      float xi = v.x, xq = v.y;
+#pragma unroll
+      for (int l = 0; l < MOD + 1; ++l) {
+        float ri, rq;
+        if (MOD == 0) {                                  // quantize(): nearbyint, then saturate (llr_demapper.cpp:770-776)
+          ri = fminf(fmaxf(rintf(__fmul_rn(xi, p)), -128.0f), 127.0f);
+          rq = fminf(fmaxf(rintf(__fmul_rn(xq, p)), -128.0f), 127.0f);
+        } else {
+          ri = rintf(__fmul_rn(xi, p));                  // _mm256_round_ps(x * precision, NEAREST)
+          rq = rintf(__fmul_rn(xq, p));
+        }
+        const int bi = BPC * k + 2 * l;
+        const int ai = MOD == 0 ? bi : __ldg(address + bi), aq = MOD == 0 ? bi + 1 : __ldg(address + bi + 1);
+        frame[ai] = (int8_t)wrap_i8(ri);
+        frame[aq] = (int8_t)wrap_i8(rq);
+        if (l < MOD) {                                   // next level: |x| - (2^(MOD-l)) * a
+          const float t = a * (float)(1 << (MOD - l));
+          xi = __fsub_rn(fabsf(xi), t);
+          xq = __fsub_rn(fabsf(xq), t);
+        }
+      }
+    }
+    __syncthreads();
+    int4* dst = reinterpret_cast<int4*>(llr + ((size_t)b.first_fec + f) * fec_bits);
+    const int4* src = reinterpret_cast<const int4*>(frame);
+    if ((((size_t)b.first_fec + f) * fec_bits) % 16 == 0) {
+      for (int k = threadIdx.x; k < fec_bits / 16; k += blockDim.x) dst[k] = src[k];
+      for (int k = (fec_bits / 16) * 16 + threadIdx.x; k < fec_bits; k += blockDim.x)
+        llr[((size_t)b.first_fec + f) * fec_bits + k] = frame[k];
+    } else {                                             // 16200-bit frames: odd frames start 8-byte aligned
+      int2* d2 = reinterpret_cast<int2*>(llr + ((size_t)b.first_fec + f) * fec_bits);
+      const int2* s2 = reinterpret_cast<const int2*>(frame);
+      for (int k = threadIdx.x; k < fec_bits / 8; k += blockDim.x) d2[k] = s2[k];
+    }
+    __syncthreads();
+  }
+}
+
+TiDemapState* state(t2b200_ctx* ctx)
+{
+  if (!ctx->ti) ctx->ti = new TiDemapState();
+  return ctx->ti;
+}
+
+}  // namespace
+
+void t2_ti_free(t2b200_ctx* ctx)
+{
+  if (!ctx->ti) return;
+  for (auto& kv : ctx->ti->plp) cudaFree(kv.second.d_perm);
+  for (auto& kv : ctx->ti->addr) cudaFree(kv.second.d_addr);
+  if (ctx->ti->d_partials) cudaFree(ctx->ti->d_partials);
+  delete ctx->ti;
+  ctx->ti = nullptr;
+}
+
+extern "C" int t2b200_cell_permutation(int n_fec_blocks, int cells_per_fec, int32_t* perm_out)
+{
+  if (n_fec_blocks <= 0 || cells_per_fec <= 0 || !perm_out) return T2B200_ERR_ARG;
+  std::vector<int32_t> p;
+  t2_cell_deinterleaver_permutation(n_fec_blocks, cells_per_fec, p);
+  std::copy(p.begin(), p.end(), perm_out);
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_demap_address_table(int fec_type, int mod, int code_rate, int32_t* address_out)
+{
+  std::vector<int32_t> a;
+  if (!address_out || !t2_demap_address_table(fec_type, mod, code_rate, a)) return T2B200_ERR_ARG;
+  if (a.empty()) { const int n = fec_type ? 64800 : 16200; for (int i = 0; i < n; ++i) address_out[i] = i; return T2B200_OK; }
+  std::copy(a.begin(), a.end(), address_out);
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_ti_configure(t2b200_ctx* ctx, int plp, int fec_type, int mod, int n_fec_blocks_max,
+                                   const int32_t* permutation)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (plp < 0 || plp > 255 || mod < 0 || mod > 3 || (fec_type != 0 && fec_type != 1) || n_fec_blocks_max <= 0) {
+    ctx->err = "t2b200_ti_configure: bad argument"; return T2B200_ERR_ARG;
+  }
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  TiDemapState* st = state(ctx);
+  TiPlp& p = st->plp[plp];
+  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p.d_perm) { cudaFree(p.d_perm); p.d_perm = nullptr; }
+  p.cells_per_fec = t2_cells_per_fec(fec_type, mod);
+  p.rows = p.cells_per_fec / 5;
+  p.n_fec_max = n_fec_blocks_max;
+  std::vector<int32_t> own;
+  const size_t n = (size_t)n_fec_blocks_max * p.cells_per_fec;
+  if (!permutation) { t2_cell_deinterleaver_permutation(n_fec_blocks_max, p.cells_per_fec, own); permutation = own.data(); }
+  T2_CUDA(ctx, cudaMalloc(&p.d_perm, n * sizeof(int32_t)));
+  T2_CUDA(ctx, cudaMemcpy(p.d_perm, permutation, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return T2B200_OK;
+}
+
+static int upload_descs(t2b200_ctx* ctx, int slot, const void* h, size_t bytes, void** d)
+{
+  int rc;
+  if ((rc = t2_dev_scratch(ctx, slot, bytes, d))) return rc;
+  T2_CUDA(ctx, cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cells_in, int n_ti_blocks,
+                                      const int32_t* n_fec_per_block, float* cells_out)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (!cells_in || !cells_out || n_ti_blocks < 0 || !n_fec_per_block) { ctx->err = "t2b200_ti_deinterleave: bad argument"; return T2B200_ERR_ARG; }
+  if (!ctx->ti || !ctx->ti->plp.count(plp)) { ctx->err = "t2b200_ti_deinterleave: PLP not configured"; return T2B200_ERR_STATE; }
+  if (n_ti_blocks == 0) return T2B200_OK;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  const TiPlp& p = ctx->ti->plp[plp];
+  std::vector<TiBlockDesc> d(n_ti_blocks);
+  long long off = 0; int max_cells = 0;
+  for (int i = 0; i < n_ti_blocks; ++i) {
+    if (n_fec_per_block[i] <= 0 || n_fec_per_block[i] > p.n_fec_max) { ctx->err = "TI block larger than configured"; return T2B200_ERR_ARG; }
+    d[i] = {off, off, n_fec_per_block[i]};
+    off += (long long)n_fec_per_block[i] * p.cells_per_fec;
+    max_cells = std::max(max_cells, n_fec_per_block[i] * p.cells_per_fec);
+  }
+  int rc; const void* din; void *dout, *ddesc;
+  if ((rc = t2_to_device(ctx, 0, cells_in, (size_t)off * 8, &din))) return rc;
+  if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)off * 8, &dout))) return rc;
+  if ((rc = upload_descs(ctx, 5, d.data(), d.size() * sizeof(TiBlockDesc), &ddesc))) return rc;
+  dim3 grid(std::min((max_cells + 255) / 256, ctx->sm_count * 8), n_ti_blocks);
+  ti_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>((const float2*)din, (float2*)dout, p.d_perm,
+                                                         (const TiBlockDesc*)ddesc, p.rows, p.cells_per_fec);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the host descriptor vector goes out of scope
+  return t2_finish_out(ctx, cells_out, dout, (size_t)off * 8);
+}
+
+template <int MOD>
+static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_blocks, int max_cells,
+                        int rotation, const int32_t* d_addr, int8_t* d_llr, int cpf, int fec_bits, int max_fec,
+                        float* d_prec, float* d_snr, const float* d_prec_in)
+{
+  TiDemapState* st = ctx->ti;
+  const int gx = std::max(1, std::min((max_cells + 255) / 256, 256));
+  const size_t need = (size_t)n_blocks * gx * 2 * sizeof(double);
+  if (st->partial_cap < need) {
+    T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (st->d_partials) cudaFree(st->d_partials);
+    st->d_partials = nullptr; st->partial_cap = 0;
+    T2_CUDA(ctx, cudaMalloc(&st->d_partials, need * 2));
+    st->partial_cap = need * 2;
+  }
+  const float th = -kRot[MOD];
+  const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
+  demap_stats_kernel<MOD><<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, st->d_partials, rotation != 0, rc, rs);
+  T2_CUDA(ctx, cudaGetLastError());
+  demap_precision_kernel<MOD><<<n_blocks, 32, 0, ctx->stream>>>(st->d_partials, gx, d_prec, d_snr, d_prec_in);
+  T2_CUDA(ctx, cudaGetLastError());
+  auto k = demap_llr_kernel<MOD>;
+  const size_t smem = (size_t)((fec_bits + 15) & ~15);
+  T2_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<dim3(std::min(max_fec, ctx->sm_count * 3), n_blocks), 512, smem, ctx->stream>>>(d_cells, d_desc, d_prec, d_addr, d_llr, cpf, fec_bits);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 3;
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, const int32_t* n_fec_per_block,
+                            int mod, int rotation, int fec_type, int code_rate, int8_t* llr_out,
+                            float* snr_out, float* precision_out, const float* precision_in)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (!ti_cells || !llr_out || n_ti_blocks < 0 || !n_fec_per_block || mod < 0 || mod > 3 ||
+      (fec_type != 0 && fec_type != 1) || code_rate < 0 || code_rate > 5) { ctx->err = "t2b200_demap: bad argument"; return T2B200_ERR_ARG; }
+  if (n_ti_blocks == 0) return T2B200_OK;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  TiDemapState* st = state(ctx);
+  const int cpf = t2_cells_per_fec(fec_type, mod), fec_bits = fec_type ? 64800 : 16200;
+  const int cr_class = (fec_type && code_rate == 1) ? 1 : (fec_type && mod == 3 && code_rate == 2) ? 2 : 0;
+  const int key = fec_type * 100 + mod * 10 + cr_class;
+  if (mod != 0 && !st->addr.count(key)) {
+    std::vector<int32_t> a;
+    t2_demap_address_table(fec_type, mod, code_rate, a);
+    DemapTable t;
+    T2_CUDA(ctx, cudaMalloc(&t.d_addr, a.size() * 4));
+    T2_CUDA(ctx, cudaMemcpy(t.d_addr, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+    st->addr[key] = t;
+  }
+  std::vector<DemapBlockDesc> d(n_ti_blocks);
+  long long off = 0; int fec = 0, max_cells = 0, max_fec = 0;
+  for (int i = 0; i < n_ti_blocks; ++i) {
+    if (n_fec_per_block[i] <= 0) { ctx->err = "t2b200_demap: empty TI block"; return T2B200_ERR_ARG; }
+    d[i] = {off, n_fec_per_block[i] * cpf, fec};
+    off += (long long)n_fec_per_block[i] * cpf; fec += n_fec_per_block[i];
+    max_cells = std::max(max_cells, n_fec_per_block[i] * cpf); max_fec = std::max(max_fec, n_fec_per_block[i]);
+  }
+  int rc; const void* dcells; void *dllr, *ddesc, *dprec, *dsnr; const void* dpin = nullptr;
+  const bool cells_on_dev = t2_is_device_ptr(ti_cells);
+  if ((rc = t2_to_device(ctx, 0, ti_cells, (size_t)off * 8, &dcells))) return rc;
+  if ((rc = t2_out_device(ctx, 1, llr_out, (size_t)fec * fec_bits, &dllr))) return rc;
+  if ((rc = upload_descs(ctx, 5, d.data(), d.size() * sizeof(DemapBlockDesc), &ddesc))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 6, 8 * (size_t)n_ti_blocks + 16, &dprec))) return rc;
+  dsnr = (float*)dprec + n_ti_blocks;
+  if (precision_in) {
+    void* tmp;
+    if ((rc = t2_dev_scratch(ctx, 7, 4 * (size_t)n_ti_blocks, &tmp))) return rc;
+    T2_CUDA(ctx, cudaMemcpyAsync(tmp, precision_in, 4 * (size_t)n_ti_blocks,
+                                 t2_is_device_ptr(precision_in) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    dpin = tmp;
+  }
+  const int32_t* daddr = mod ? st->addr[key].d_addr : nullptr;
+#define DM(M) demap_launch<M>(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, rotation, daddr, \
+                              (int8_t*)dllr, cpf, fec_bits, max_fec, (float*)dprec, (float*)dsnr, (const float*)dpin)
+  switch (mod) { case 0: rc = DM(0); break; case 1: rc = DM(1); break; case 2: rc = DM(2); break; default: rc = DM(3); break; }
+  if (rc) return rc;
+  auto copy_small = [&](float* dst, const void* src) -> int {
+    if (!dst) return T2B200_OK;
+    T2_CUDA(ctx, cudaMemcpyAsync(dst, src, 4 * (size_t)n_ti_blocks,
+                                 t2_is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    return T2B200_OK;
+  };
+  if ((rc = copy_small(precision_out, dprec))) return rc;
+  if ((rc = copy_small(snr_out, dsnr))) return rc;
+  // the reference derotates its input in place (llr_demapper.cpp:555-557): mirror that for host buffers too
+  if (!cells_on_dev && rotation)
+    T2_CUDA(ctx, cudaMemcpyAsync(ti_cells, dcells, (size_t)off * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return t2_finish_out(ctx, llr_out, dllr, (size_t)fec * fec_bits);
+}

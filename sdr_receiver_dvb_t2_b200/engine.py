@@ -25,6 +25,8 @@ SYMBOLS = [
     't2b200_version', 't2b200_launch_count',
     't2b200_ldpc_code_id', 't2b200_ldpc_n', 't2b200_ldpc_k', 't2b200_ldpc_k_bch',
     't2b200_ldpc_decode', 't2b200_bch_descramble',
+    't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
+    't2b200_demap',
 ]
 
 
@@ -60,6 +62,11 @@ def lib():
     L.t2b200_launch_count.restype = C.c_longlong
     L.t2b200_ldpc_decode.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, u32]
     L.t2b200_bch_descramble.argtypes = [vp, i32, vp, i32, vp]
+    L.t2b200_cell_permutation.argtypes = [i32, i32, vp]
+    L.t2b200_demap_address_table.argtypes = [i32, i32, i32, vp]
+    L.t2b200_ti_configure.argtypes = [vp, i32, i32, i32, i32, vp]
+    L.t2b200_ti_deinterleave.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.t2b200_demap.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -171,3 +178,46 @@ class Engine:
         out = _like(bits, (n, KB), np.uint8)
         self._chk(self.L.t2b200_bch_descramble(self.h, code, _ptr(bits), n, _ptr(out)))
         return out
+
+    # ---- K3 / K4 ----
+    def ti_configure(self, plp, fec_type, mod, n_fec_blocks_max, permutation=None):
+        if permutation is not None:
+            permutation = np.ascontiguousarray(permutation, np.int32)
+        self._chk(self.L.t2b200_ti_configure(self.h, plp, fec_type, mod, n_fec_blocks_max, _ptr(permutation)))
+
+    def ti_deinterleave(self, plp, cells, n_fec_per_block):
+        """cells complex64[total cells] (numpy or torch cuda) -> de-interleaved TI blocks, same type"""
+        nf = np.ascontiguousarray(n_fec_per_block, np.int32)
+        out = _like(cells, tuple(cells.shape), np.complex64)
+        self._chk(self.L.t2b200_ti_deinterleave(self.h, plp, _ptr(cells), len(nf), _ptr(nf), _ptr(out)))
+        return out
+
+    def demap(self, ti_cells, n_fec_per_block, mod, rotation, fec_type, code_rate, precision_in=None):
+        """ti_cells is derotated IN PLACE when rotation != 0 (as the reference does).
+        -> dict(llr int8[n_fec][N], snr, precision)"""
+        nf = np.ascontiguousarray(n_fec_per_block, np.int32)
+        n_fec, nbits = int(nf.sum()), (64800 if fec_type else 16200)
+        llr = _like(ti_cells, (n_fec, nbits), np.int8)
+        snr = np.zeros(len(nf), np.float32)
+        prec = np.zeros(len(nf), np.float32)
+        if precision_in is not None:
+            precision_in = np.ascontiguousarray(precision_in, np.float32)
+        self._chk(self.L.t2b200_demap(self.h, _ptr(ti_cells), len(nf), _ptr(nf), mod, rotation, fec_type, code_rate,
+                                      _ptr(llr), _ptr(snr), _ptr(prec), _ptr(precision_in)))
+        return {'llr': llr, 'snr': snr, 'precision': prec}
+
+
+def cell_permutation(n_fec_blocks, cells_per_fec):
+    out = np.zeros(n_fec_blocks * cells_per_fec, np.int32)
+    rc = lib().t2b200_cell_permutation(n_fec_blocks, cells_per_fec, out.ctypes.data)
+    if rc != OK:
+        raise T2Error('t2b200_cell_permutation rc=%d' % rc)
+    return out
+
+
+def demap_address_table(fec_type, mod, code_rate):
+    out = np.zeros(64800 if fec_type else 16200, np.int32)
+    rc = lib().t2b200_demap_address_table(fec_type, mod, code_rate, out.ctypes.data)
+    if rc != OK:
+        raise T2Error('t2b200_demap_address_table rc=%d' % rc)
+    return out
