@@ -28,7 +28,6 @@ struct DemapTable { int32_t* d_addr = nullptr; };
 struct TiDemapState {
   std::map<int, TiPlp> plp;
   std::map<int, DemapTable> addr;        // key fec_type*100 + mod*10 + code_rate class
-  double* d_partials = nullptr; size_t partial_cap = 0;
 };
 
 namespace {
@@ -93,16 +92,17 @@ __device__ __forceinline__ float slice_axis(float x, float a)
 
 struct DemapBlockDesc { long long cell_off; int n_cells; int first_fec; };
 
-// levels k*a must be the same floats the reference holds (norm_x_k = NORM * k.0f): computed as a*k in float
+// levels k*a must be the same floats the reference holds (norm_x_k = NORM * k.0f): computed as a*k in float.
+// Pass 1a: derotate in place + per-cell |s|^2 and |e|^2 of the hard decision, stored for the ordered sum.
 template <int MOD>
 __global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
-                                   double* __restrict__ partials, int rotate, float rc, float rs)
+                                   float2* __restrict__ terms, int rotate, float rc, float rs)
 {
   const DemapBlockDesc b = blocks[blockIdx.y];
   float2* c = cells + b.cell_off;
+  float2* t = terms + b.cell_off;
   const float a = kNorm[MOD];
   const int n_stat = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;      // llr_demapper.cpp:185
-  double ss = 0.0, se = 0.0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < b.n_cells; k += gridDim.x * blockDim.x) {
     float2 v = c[k];
     if (rotate) {                       // _in[i] *= derotate (llr_demapper.cpp:555-557), no FMA contraction
@@ -114,39 +114,61 @@ __global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockD
     if (k < n_stat) {
       const float sx = slice_axis<MOD>(v.x, a), sy = slice_axis<MOD>(v.y, a);
       const float ex = __fsub_rn(v.x, sx), ey = __fsub_rn(v.y, sy);
-      ss += (double)__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy));
-      se += (double)__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+      t[k] = make_float2(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
     }
-  }
-  // deterministic block reduction
-  __shared__ double sh[2][32];
-  for (int o = 16; o; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); se += __shfl_xor_sync(0xffffffffu, se, o); }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][w] = ss; sh[1][w] = se; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a0 = 0, a1 = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a0 += sh[0][i]; a1 += sh[1][i]; }
-    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 0] = a0;
-    partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 1] = a1;
   }
 }
 
-// fixed-order sum of the per-CTA partials -> precision and SNR per TI block
+// Pass 1b: sum_s / sum_e exactly as the reference accumulates them -- float, in cell order (the one
+// order-dependent reduction of the receiver; every LLR of the TI block is scaled by its result, so a
+// tree sum would flip ~0.1 % of the LLRs by one LSB).  One warp per TI block: the lanes stream the
+// terms through shared memory, lane 0 owns the two dependent FADD chains (~4 cycles per cell, ~1 ms
+// for the largest TI block, a few per cent of one SM at full LDPC throughput).
 template <int MOD>
-__global__ void demap_precision_kernel(const double* __restrict__ partials, int n_partials, float* __restrict__ precision,
-                                       float* __restrict__ snr, const float* __restrict__ precision_in)
+__global__ void demap_ordered_sum_kernel(const float2* __restrict__ terms, const DemapBlockDesc* __restrict__ blocks,
+                                         float* __restrict__ precision, float* __restrict__ snr,
+                                         const float* __restrict__ precision_in)
 {
-  const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
-  double ss = 0, se = 0;
-  for (int i = 0; i < n_partials; ++i) { ss += partials[((size_t)b * n_partials + i) * 2]; se += partials[((size_t)b * n_partials + i) * 2 + 1]; }
-  const float fs = (float)ss, fe = (float)se;
-  const float a8 = __fmul_rn(8.0f, kNorm[MOD]);
-  float p = __fdiv_rn(__fmul_rn(a8, fs), fe);              // 8.0f * NORM * sum_s / sum_e, left to right
-  if (precision_in) p = precision_in[b];
-  precision[b] = p;
-  if (snr) snr[b] = (MOD == 0 ? 10.0f : 20.0f) * log10f(fs / fe);
+  constexpr int CH = 256;
+  __shared__ float2 buf[2][CH];
+  const DemapBlockDesc b = blocks[blockIdx.x];
+  const float2* t = terms + b.cell_off;
+  const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;
+  const int lane = threadIdx.x;
+  float ss = 0.0f, se = 0.0f;
+  float2 r[CH / 32];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int j = 0; j < CH / 32; ++j) {
+      const int k = c0 + lane + 32 * j;
+      r[j] = k < n ? __ldg(t + k) : make_float2(0.0f, 0.0f);
+    }
+  };
+  fetch(0);
+  int pb = 0;
+  for (int c0 = 0; c0 < n; c0 += CH, pb ^= 1) {
+#pragma unroll
+    for (int j = 0; j < CH / 32; ++j) buf[pb][lane + 32 * j] = r[j];
+    __syncwarp();
+    if (c0 + CH < n) fetch(c0 + CH);                      // in flight while lane 0 adds
+    if (lane == 0) {
+      const int m = min(CH, n - c0);
+      if (m == CH) {
+#pragma unroll 16
+        for (int i = 0; i < CH; ++i) { ss = __fadd_rn(ss, buf[pb][i].x); se = __fadd_rn(se, buf[pb][i].y); }
+      } else {
+        for (int i = 0; i < m; ++i) { ss = __fadd_rn(ss, buf[pb][i].x); se = __fadd_rn(se, buf[pb][i].y); }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const float a8 = __fmul_rn(8.0f, kNorm[MOD]);
+    float p = __fdiv_rn(__fmul_rn(a8, ss), se);            // 8.0f * NORM * sum_s / sum_e, left to right
+    if (precision_in) p = precision_in[blockIdx.x];
+    precision[blockIdx.x] = p;
+    if (snr) snr[blockIdx.x] = (MOD == 0 ? 10.0f : 20.0f) * log10f(ss / se);
+  }
 }
 
 // (int8_t)(float) as x86-64 gcc compiles it: cvttss2si to int32 (0x80000000 when out of range), low byte
@@ -223,7 +245,6 @@ void t2_ti_free(t2b200_ctx* ctx)
   if (!ctx->ti) return;
   for (auto& kv : ctx->ti->plp) cudaFree(kv.second.d_perm);
   for (auto& kv : ctx->ti->addr) cudaFree(kv.second.d_addr);
-  if (ctx->ti->d_partials) cudaFree(ctx->ti->d_partials);
   delete ctx->ti;
   ctx->ti = nullptr;
 }
@@ -308,25 +329,19 @@ extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cel
 }
 
 template <int MOD>
-static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_blocks, int max_cells,
+static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_blocks, int max_cells, long long total_cells,
                         int rotation, const int32_t* d_addr, int8_t* d_llr, int cpf, int fec_bits, int max_fec,
                         float* d_prec, float* d_snr, const float* d_prec_in)
 {
-  TiDemapState* st = ctx->ti;
-  const int gx = std::max(1, std::min((max_cells + 255) / 256, 256));
-  const size_t need = (size_t)n_blocks * gx * 2 * sizeof(double);
-  if (st->partial_cap < need) {
-    T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (st->d_partials) cudaFree(st->d_partials);
-    st->d_partials = nullptr; st->partial_cap = 0;
-    T2_CUDA(ctx, cudaMalloc(&st->d_partials, need * 2));
-    st->partial_cap = need * 2;
-  }
+  const int gx = std::max(1, std::min((max_cells + 255) / 256, ctx->sm_count * 8));
+  void* d_terms;
+  int rc0;
+  if ((rc0 = t2_dev_scratch(ctx, 4, (size_t)total_cells * sizeof(float2), &d_terms))) return rc0;
   const float th = -kRot[MOD];
   const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
-  demap_stats_kernel<MOD><<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, st->d_partials, rotation != 0, rc, rs);
+  demap_stats_kernel<MOD><<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, (float2*)d_terms, rotation != 0, rc, rs);
   T2_CUDA(ctx, cudaGetLastError());
-  demap_precision_kernel<MOD><<<n_blocks, 32, 0, ctx->stream>>>(st->d_partials, gx, d_prec, d_snr, d_prec_in);
+  demap_ordered_sum_kernel<MOD><<<n_blocks, 32, 0, ctx->stream>>>((const float2*)d_terms, d_desc, d_prec, d_snr, d_prec_in);
   T2_CUDA(ctx, cudaGetLastError());
   auto k = demap_llr_kernel<MOD>;
   const size_t smem = (size_t)((fec_bits + 15) & ~15);
@@ -381,7 +396,7 @@ extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, c
     dpin = tmp;
   }
   const int32_t* daddr = mod ? st->addr[key].d_addr : nullptr;
-#define DM(M) demap_launch<M>(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, rotation, daddr, \
+#define DM(M) demap_launch<M>(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, off, rotation, daddr, \
                               (int8_t*)dllr, cpf, fec_bits, max_fec, (float*)dprec, (float*)dsnr, (const float*)dpin)
   switch (mod) { case 0: rc = DM(0); break; case 1: rc = DM(1); break; case 2: rc = DM(2); break; default: rc = DM(3); break; }
   if (rc) return rc;

@@ -1,7 +1,7 @@
 """K3 / K4 parity through the C-ABI: time de-interleaver + Q-delay removal (exact: a permutation) and the
-soft demapper.  The demapper has ONE order-dependent float reduction (sum_s / sum_e -> precision); the tests
-pin it: with the oracle's precision handed in, every int8 LLR must be identical; with the GPU's own
-(double-accumulated) precision it must agree to 2e-6 relative and LLRs may differ by 1 LSB on < 0.1 %."""
+soft demapper.  The demapper has ONE order-dependent float reduction (sum_s / sum_e -> precision); the CUDA path
+accumulates it in the reference's order (float, cell by cell), so precision and every int8 LLR must be identical
+to the oracle -- both with the oracle's precision handed in and with the GPU's own."""
 import os
 
 import numpy as np
@@ -30,11 +30,9 @@ def test_ti_and_demap_match_oracle(engine, name):
     # (2) own precision
     cells2 = ti.copy()
     r2 = engine.demap(cells2, blocks, cfg['mod'], cfg['rot'], cfg['fec'], cfg['cod'])
-    assert np.allclose(r2['precision'], prec_ref, rtol=2e-6, atol=0)
-    assert np.allclose(r2['snr'], snr_ref, rtol=0, atol=1e-3)
-    d = np.abs(r2['llr'].astype(np.int16) - llr_ref.astype(np.int16))
-    d = np.minimum(d, 256 - d)                       # the int8 cast wraps
-    assert d.max() <= 1 and (d != 0).mean() < 1e-3
+    assert np.array_equal(r2['precision'], prec_ref)
+    assert np.allclose(r2['snr'], snr_ref, rtol=0, atol=1e-4)        # log10f: library ulp
+    assert np.array_equal(r2['llr'], llr_ref)
     if cfg['rot']:
         # the reference derotates its input buffer in place (llr_demapper.cpp:555-557)
         off = 0
