@@ -136,6 +136,35 @@ int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, const int32_
                  int mod, int rotation, int fec_type, int code_rate, int8_t* llr_out,
                  float* snr_out, float* precision_out, const float* precision_in);
 
+/* ---- K2: channel estimation + equalisation + frequency de-interleaving ---------------------- */
+/* kind: 0 = P2 symbol, 1 = data symbols, 2 = frame-closing symbol */
+enum { T2B200_SYM_P2 = 0, T2B200_SYM_DATA = 1, T2B200_SYM_FC = 2 };
+
+/* Replaces p2_symbol::init / data_symbol::init / fc_symbol::init (p2_symbol.cpp:43-76,
+ * data_symbol.cpp:39-106, fc_symbol.cpp:37-80): hands the engine the init-time tables that the
+ * reference's pilot_generator and address_freq_deinterleaver objects hold (pilot_generator.h:28-33,
+ * address_freq_deinterleaver.h:33-38), which the drop-in classes receive as arguments.
+ *   n_symbols     symbols of this kind per T2 frame (n_data for DATA, 1 for P2 / FC)
+ *   first_symbol  frame index of the first one (0 for P2, n_p2 for DATA, len_frame-1 for FC)
+ *   carrier_map   int32[n_symbols][k_total]  carrier types (dvbt2_definition.h:103-113)
+ *   pilot_refer   float[n_symbols][k_total]  +-amplitude for pilots, 0 elsewhere
+ *   h_even/h_odd  int32[>= n_out]            de-interleaver tables; the symbol's parity picks one
+ *   amp_main      amp_p2 (P2) or amp_sp (DATA, FC); amp_cp for continual pilots (DATA only)          */
+int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int first_symbol, int fft_size,
+                        int k_total, int l_nulls, int n_out, const int32_t* carrier_map,
+                        const float* pilot_refer, const int32_t* h_even, const int32_t* h_odd,
+                        float amp_main, float amp_cp);
+
+/* Replaces the equaliser of p2_symbol::execute (p2_symbol.cpp:89-259), data_symbol::execute
+ * (data_symbol.cpp:108-335) and fc_symbol::execute (fc_symbol.cpp:82-271) for a batch of symbols:
+ *   idx_symbol int32[n]  frame index of each symbol (parity selects h_odd / h_even, index selects the map)
+ *   freq       complex<float>[n][fft_size]  FFT output, halves swapped (fast_fourier_transform::execute)
+ *   cells_out  complex<float>[n][n_out]     equalised, frequency-de-interleaved cells
+ *   sro, phase float[n] or NULL             the two feedback estimates the reference returns by reference
+ * n = 1 is the synchronous per-symbol call of live reception.                                        */
+int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx_symbol,
+                    const float* freq, float* cells_out, float* sro, float* phase);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,12 @@ def port():
         L.port_demap_address_for.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.port_demap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_float]
         L.port_demap.restype = C.c_float
+        L.port_equalize.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_float, C.c_float, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.port_fft_shift.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.port_atan2_approx.argtypes = [C.c_float, C.c_float]
+        L.port_atan2_approx.restype = C.c_float
+        L.port_sincos_lut.argtypes = [C.c_void_p, C.c_void_p]
         _port = L
     return _port
 
@@ -338,3 +344,24 @@ def port_demap(cells, mod, rotation, fec_normal, code_rate, precision_in=0.0):
     p = port().port_demap(cells.ctypes.data, len(cells), mod, int(rotation), int(fec_normal), code_rate,
                           llr.ctypes.data, C.byref(snr), float(precision_in))
     return llr, snr.value, p, cells
+
+
+# ---- port oracle: FFT + equaliser (oracle/port/eq_port.c) ----
+def port_equalize(kind, freq, l_nulls, k_total, cmap, refer, h, n_out, amp_main, amp_cp=0.0):
+    """one symbol; kind 0 P2 / 1 data / 2 FC -> (cells complex64[n_out], sro, phase)"""
+    freq = np.ascontiguousarray(freq, np.complex64)
+    cmap = np.ascontiguousarray(cmap, np.int32)
+    refer = np.ascontiguousarray(refer, np.float32)
+    h = np.ascontiguousarray(h, np.int32)
+    out = np.zeros(n_out, np.complex64)
+    sro, ph = C.c_float(), C.c_float()
+    port().port_equalize(kind, freq.ctypes.data, l_nulls, k_total, cmap.ctypes.data, refer.ctypes.data, h.ctypes.data,
+                         float(amp_main), float(amp_cp), out.ctypes.data, C.byref(sro), C.byref(ph))
+    return out, sro.value, ph.value
+
+
+def port_fft(x):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty_like(x)
+    port().port_fft_shift(x.ctypes.data, len(x), out.ctypes.data)
+    return out

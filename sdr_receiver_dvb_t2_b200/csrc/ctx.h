@@ -27,6 +27,7 @@ struct t2b200_ctx {
   std::string err;
   long long launches = 0;
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id
+  float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes
   unsigned* d_group_sync = nullptr; size_t group_sync_cap = 0;
   std::map<int, FftPlan*> fft;                // by log2 n

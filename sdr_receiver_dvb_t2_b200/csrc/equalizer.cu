@@ -1,0 +1,291 @@
+// K2: pilot-based channel estimation, per-carrier equalisation and frequency de-interleaving for P2,
+// data and frame-closing symbols.
+//
+// Reference semantics reproduced (paths relative to the reference's src/):
+//   DVB_T2/data_symbol.cpp:108-335, fc_symbol.cpp:82-271, p2_symbol.cpp:94-259
+//     every estimating pilot gives angle = atan2_approx(cell * ref) and amp = |cell| / amp_pilot; the data
+//     cells between two consecutive pilots get angle / amp interpolated linearly BY REPEATED ADDITION of the
+//     step (so the n-th cell carries n rounded float adds), with the asymmetric +-pi unwrap of
+//     data_symbol.cpp:190-191; derotation through the 65 536-entry sin/cos table (DSP/fast_math.h:25-42);
+//     out[h[d]] = cell * conj(e^{j angle} / amp); the centre carrier never estimates; continual pilots use
+//     amp_cp, scattered / edge ones amp_sp; phase = atan2(sum pilots left) + atan2(sum pilots right),
+//     sro = sum angle right - sum angle left, both accumulated in carrier order.
+// B200 design: the serial scan of the reference is turned inside out.  At table-upload time the host
+// compiles each symbol's carrier map into a PLAN: the list of estimating pilots and, per data cell, its
+// carrier, its left pilot, its position inside the interval and its de-interleaved address (8 bytes per
+// cell, identical plans shared between symbols).  One CTA then handles one symbol: pilots are estimated
+// in parallel into shared memory, one thread forms the ordered pilot sums while all others equalise the
+// data cells independently (each re-running its interval's additions, <= 191 FADDs), and results leave
+// through the de-interleaver as 8-byte scattered stores that merge in L2.  Arithmetic is written with
+// explicit round-to-nearest intrinsics so no FMA contraction changes a bit relative to the CPU oracle.
+#include "ctx.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+enum { DATA_CARRIER = 1, P2CARRIER, P2PAPR_CARRIER, TRPAPR_CARRIER, SCATTERED_CARRIER, CONTINUAL_CARRIER,
+       P2CARRIER_INVERTED, SCATTERED_CARRIER_INVERTED, CONTINUAL_CARRIER_INVERTED };     // dvbt2_definition.h:103-113
+
+struct PlanPilot { uint16_t k; uint8_t second_half; uint8_t pad; float ref; float amp; };
+struct PlanHost {
+  std::vector<PlanPilot> pilots;
+  std::vector<uint2> cells;          // x = k | left_pilot << 16 ; y = j | n << 8 | h << 16
+};
+struct PlanDev { PlanPilot* pilots = nullptr; uint2* cells = nullptr; int n_pilots = 0, n_cells = 0, n_first = 0, pad = 0; };
+
+}  // namespace
+
+struct SymbolTables {
+  int kind = 0, k_total = 0, l_nulls = 0, fft_size = 0, n_out = 0, first_symbol = 0, n_symbols = 0;
+  std::vector<PlanDev> plans;            // unique plans
+  std::vector<int> plan_even, plan_odd;  // per symbol of the kind: plan when idx_symbol is even / odd
+  int* d_plan_even = nullptr; int* d_plan_odd = nullptr;
+  PlanDev* d_plans = nullptr;
+  int max_pilots = 0;
+};
+
+namespace {
+
+float* g_unused = nullptr;
+
+__device__ __forceinline__ float atan2_approx_dev(float y, float x)      // DSP/fast_math.h:61-81
+{
+  const float PI = 3.14159265358979323846f, PI_2 = 1.57079632679489661923f;
+  if (x == 0.0f) return y > 0.0f ? PI_2 : -PI_2;
+  if (y == 0.0f) return x > 0.0f ? 0.0f : -PI;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool min_x = ax < ay;
+  const float a = min_x ? __fdiv_rn(ax, ay) : __fdiv_rn(ay, ax);
+  const float s = __fmul_rn(a, a);
+  float r = __fadd_rn(__fmul_rn(-4.6496475e-2f, s), 1.5931422e-1f);
+  r = __fsub_rn(__fmul_rn(r, s), 3.2762276e-1f);
+  r = __fadd_rn(__fmul_rn(__fmul_rn(r, s), a), a);
+  if (min_x) r = __fsub_rn(PI_2, r);
+  if (x < 0.0f) r = __fsub_rn(PI, r);
+  if (y < 0.0f) r = -r;
+  return r;
+}
+
+struct EqParams {
+  const float2* freq; float2* out; float* sro; float* phase; const int* idx_symbol;
+  const PlanDev* plans; const int* plan_even; const int* plan_odd;
+  const float* lut_sin; const float* lut_cos;
+  int fft_size, l_nulls, n_out, first_symbol, n_symbols_kind;
+};
+
+__global__ void __launch_bounds__(512) equalize_kernel(const EqParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int s = blockIdx.x;
+  const int idx = p.idx_symbol[s];
+  int rel = idx - p.first_symbol;
+  rel = min(max(rel, 0), p.n_symbols_kind - 1);
+  const PlanDev pl = p.plans[(idx & 1) ? p.plan_odd[rel] : p.plan_even[rel]];
+  float* ang = reinterpret_cast<float*>(smem_raw);
+  float* amp = ang + pl.n_pilots;
+  float2* est = reinterpret_cast<float2*>(amp + pl.n_pilots + (pl.n_pilots & 1));
+  const float2* cell = p.freq + (size_t)s * p.fft_size + p.l_nulls;
+  float2* out = p.out + (size_t)s * p.n_out;
+
+  for (int i = threadIdx.x; i < pl.n_pilots; i += blockDim.x) {
+    const PlanPilot pp = pl.pilots[i];
+    const float2 c = __ldg(cell + pp.k);
+    const float er = __fmul_rn(c.x, pp.ref), ei = __fmul_rn(c.y, pp.ref);        // cell * pilot_refer
+    est[i] = make_float2(er, ei);
+    ang[i] = atan2_approx_dev(ei, er);
+    amp[i] = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y))), pp.amp);
+  }
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    // ordered sums (data_symbol.cpp:162-163,183-193,319-324): the first pilot feeds sum_pilot_1 only
+    float s1r = est[0].x, s1i = est[0].y, s2r = 0.f, s2i = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = 1; i < pl.n_first; ++i) {                         // pilots left of the centre carrier
+      const float2 e = est[i];
+      s1r = __fadd_rn(s1r, e.x); s1i = __fadd_rn(s1i, e.y); a1 = __fadd_rn(a1, ang[i]);
+    }
+    for (int i = pl.n_first; i < pl.n_pilots; ++i) {               // right of it
+      const float2 e = est[i];
+      s2r = __fadd_rn(s2r, e.x); s2i = __fadd_rn(s2i, e.y); a2 = __fadd_rn(a2, ang[i]);
+    }
+    if (p.phase) p.phase[s] = __fadd_rn(atan2_approx_dev(s2i, s2r), atan2_approx_dev(s1i, s1r));
+    if (p.sro) p.sro[s] = __fsub_rn(a2, a1);
+  }
+
+  const float PI = 3.14159265358979323846f;
+  const float k_table = 32767.0f / (2.0f * PI);
+  for (int d = threadIdx.x; d < pl.n_cells; d += blockDim.x) {
+    const uint2 w = pl.cells[d];
+    const int k = w.x & 0xffff, ip = w.x >> 16, j = w.y & 0xff, n = (w.y >> 8) & 0xff, h = w.y >> 16;
+    const float ang_l = ang[ip], ang_r = ang[ip + 1], amp_l = amp[ip], amp_r = amp[ip + 1];
+    float dif = __fsub_rn(ang_r, ang_l);
+    if (dif > PI) dif = __fsub_rn(__fmul_rn(PI, 2.0f), dif);                      // data_symbol.cpp:190-191
+    else if (dif < -PI) dif = __fadd_rn(__fmul_rn(PI, 2.0f), dif);
+    const float fn = (float)(n + 1);
+    const float da = __fdiv_rn(dif, fn), dm = __fdiv_rn(__fsub_rn(amp_r, amp_l), fn);
+    float a = ang_l, m = amp_l;
+    for (int t = 0; t < j; ++t) { a = __fadd_rn(a, da); m = __fadd_rn(m, dm); }
+    const int li = __float2int_rz(__fadd_rn(__fmul_rn(a, k_table), 32767.0f)) & 65535;
+    const float dr = __fdiv_rn(__ldg(p.lut_cos + li), m), di = __fdiv_rn(__ldg(p.lut_sin + li), m);
+    const float2 c = __ldg(cell + k);
+    out[h] = make_float2(__fadd_rn(__fmul_rn(c.x, dr), __fmul_rn(c.y, di)),
+                         __fsub_rn(__fmul_rn(c.y, dr), __fmul_rn(c.x, di)));
+  }
+}
+
+// carrier map + pilot references of ONE symbol -> plan (the reference's scan, run once on the host)
+bool build_plan(int kind, int k_total, const int32_t* map, const float* refer, const int32_t* h, float amp_main,
+                float amp_cp, PlanHost& out, std::string& err)
+{
+  const int half_total = k_total / 2;
+  out.pilots.clear(); out.cells.clear();
+  out.pilots.push_back({0, 0, 0, refer[0], amp_main});            // carrier 0: always the first (edge) pilot
+  std::vector<int> pending;                                        // carriers of buffered data cells
+  int d = 0;
+  for (int i = 1; i < k_total; ++i) {
+    const int t = map[i];
+    bool pilot;
+    if (kind == 0) pilot = (t == P2CARRIER || t == P2CARRIER_INVERTED);
+    else if (kind == 1) pilot = (t == SCATTERED_CARRIER || t == SCATTERED_CARRIER_INVERTED || t == CONTINUAL_CARRIER ||
+                                 t == CONTINUAL_CARRIER_INVERTED);
+    else pilot = (t == SCATTERED_CARRIER || t == SCATTERED_CARRIER_INVERTED);
+    if (i == half_total) {                                         // centre carrier never estimates
+      if (kind != 0 && t == DATA_CARRIER) pending.push_back(i);
+      continue;
+    }
+    if (t == DATA_CARRIER) { pending.push_back(i); continue; }
+    if (!pilot) continue;
+    const bool cp = kind == 1 && (t == CONTINUAL_CARRIER || t == CONTINUAL_CARRIER_INVERTED);
+    const int left = (int)out.pilots.size() - 1;
+    out.pilots.push_back({(uint16_t)i, (uint8_t)(i > half_total), 0, refer[i], cp ? amp_cp : amp_main});
+    const int n = (int)pending.size();
+    if (n > 255) { err = "more than 255 data cells between two pilots"; return false; }
+    for (int j = 0; j < n; ++j, ++d) {
+      if (h[d] < 0 || h[d] > 65535) { err = "de-interleaver address out of range"; return false; }
+      out.cells.push_back(make_uint2((uint32_t)pending[j] | ((uint32_t)left << 16),
+                                     (uint32_t)(j + 1) | ((uint32_t)n << 8) | ((uint32_t)h[d] << 16)));
+    }
+    pending.clear();
+  }
+  if (out.pilots.size() > 65535) { err = "too many pilots"; return false; }
+  return true;
+}
+
+void free_tables(SymbolTables* t)
+{
+  if (!t) return;
+  for (auto& p : t->plans) { cudaFree(p.pilots); cudaFree(p.cells); }
+  cudaFree(t->d_plan_even); cudaFree(t->d_plan_odd); cudaFree(t->d_plans);
+  delete t;
+}
+
+}  // namespace
+
+void t2_eq_free(t2b200_ctx* ctx)
+{
+  for (auto& s : ctx->sym) { free_tables(s); s = nullptr; }
+  if (ctx->d_lut) { cudaFree(ctx->d_lut); ctx->d_lut = nullptr; }
+  (void)g_unused;
+}
+
+static int ensure_lut(t2b200_ctx* ctx)
+{
+  if (ctx->d_lut) return T2B200_OK;
+  std::vector<float> h(2 * 65536, 0.0f);                          // DSP/fast_math.h:25-40: entry 65535 stays 0
+  const float k_table = 32767.0f / (2.0f * 3.14159265358979323846f);
+  for (int i = -32767; i < 32768; i++) { h[i + 32767] = sinf(i / k_table); h[65536 + i + 32767] = cosf(i / k_table); }
+  T2_CUDA(ctx, cudaMalloc(&ctx->d_lut, h.size() * sizeof(float)));
+  T2_CUDA(ctx, cudaMemcpy(ctx->d_lut, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int first_symbol, int fft_size, int k_total,
+                                   int l_nulls, int n_out, const int32_t* carrier_map, const float* pilot_refer,
+                                   const int32_t* h_even, const int32_t* h_odd, float amp_main, float amp_cp)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (kind < 0 || kind > 2 || n_symbols <= 0 || !carrier_map || !pilot_refer || !h_even || !h_odd || k_total <= 0 ||
+      k_total > 32768 || l_nulls < 0 || l_nulls + k_total > fft_size || n_out <= 0) {
+    ctx->err = "t2b200_eq_configure: bad argument"; return T2B200_ERR_ARG;
+  }
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure_lut(ctx))) return rc;
+  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  free_tables(ctx->sym[kind]); ctx->sym[kind] = nullptr;
+  SymbolTables* t = new SymbolTables();
+  t->kind = kind; t->k_total = k_total; t->l_nulls = l_nulls; t->fft_size = fft_size; t->n_out = n_out;
+  t->first_symbol = first_symbol; t->n_symbols = n_symbols;
+  std::vector<PlanHost> uniq;
+  auto intern = [&](PlanHost& ph) -> int {
+    for (size_t u = 0; u < uniq.size(); ++u)
+      if (uniq[u].pilots.size() == ph.pilots.size() && uniq[u].cells.size() == ph.cells.size() &&
+          !memcmp(uniq[u].pilots.data(), ph.pilots.data(), ph.pilots.size() * sizeof(PlanPilot)) &&
+          !memcmp(uniq[u].cells.data(), ph.cells.data(), ph.cells.size() * sizeof(uint2))) return (int)u;
+    uniq.push_back(ph);
+    return (int)uniq.size() - 1;
+  };
+  for (int s = 0; s < n_symbols; ++s) {
+    for (int parity = 0; parity < 2; ++parity) {
+      PlanHost ph;
+      // idx_symbol even -> h_odd, odd -> h_even (data_symbol.cpp:148-149)
+      if (!build_plan(kind, k_total, carrier_map + (size_t)s * k_total, pilot_refer + (size_t)s * k_total,
+                      parity ? h_even : h_odd, amp_main, amp_cp, ph, ctx->err)) { delete t; return T2B200_ERR_ARG; }
+      if ((int)ph.cells.size() > n_out) { ctx->err = "carrier map holds more data cells than n_out"; delete t; return T2B200_ERR_ARG; }
+      (parity ? t->plan_odd : t->plan_even).push_back(intern(ph));
+    }
+  }
+  for (auto& ph : uniq) {
+    PlanDev d;
+    d.n_pilots = (int)ph.pilots.size(); d.n_cells = (int)ph.cells.size();
+    d.n_first = 0;
+    for (auto& pp : ph.pilots) d.n_first += pp.second_half ? 0 : 1;
+    T2_CUDA(ctx, cudaMalloc(&d.pilots, ph.pilots.size() * sizeof(PlanPilot)));
+    T2_CUDA(ctx, cudaMalloc(&d.cells, std::max<size_t>(1, ph.cells.size()) * sizeof(uint2)));
+    T2_CUDA(ctx, cudaMemcpy(d.pilots, ph.pilots.data(), ph.pilots.size() * sizeof(PlanPilot), cudaMemcpyHostToDevice));
+    T2_CUDA(ctx, cudaMemcpy(d.cells, ph.cells.data(), ph.cells.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    t->plans.push_back(d);
+    t->max_pilots = std::max(t->max_pilots, d.n_pilots);
+  }
+  T2_CUDA(ctx, cudaMalloc(&t->d_plans, t->plans.size() * sizeof(PlanDev)));
+  T2_CUDA(ctx, cudaMemcpy(t->d_plans, t->plans.data(), t->plans.size() * sizeof(PlanDev), cudaMemcpyHostToDevice));
+  T2_CUDA(ctx, cudaMalloc(&t->d_plan_even, n_symbols * sizeof(int)));
+  T2_CUDA(ctx, cudaMalloc(&t->d_plan_odd, n_symbols * sizeof(int)));
+  T2_CUDA(ctx, cudaMemcpy(t->d_plan_even, t->plan_even.data(), n_symbols * sizeof(int), cudaMemcpyHostToDevice));
+  T2_CUDA(ctx, cudaMemcpy(t->d_plan_odd, t->plan_odd.data(), n_symbols * sizeof(int), cudaMemcpyHostToDevice));
+  ctx->sym[kind] = t;
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx_symbol, const float* freq,
+                               float* cells_out, float* sro, float* phase)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (kind < 0 || kind > 2 || n_symbols < 0 || !idx_symbol || !freq || !cells_out) { ctx->err = "t2b200_equalize: bad argument"; return T2B200_ERR_ARG; }
+  SymbolTables* t = ctx->sym[kind];
+  if (!t) { ctx->err = "t2b200_equalize: symbol tables not configured"; return T2B200_ERR_STATE; }
+  if (n_symbols == 0) return T2B200_OK;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc; const void *dfreq, *didx; void *dout, *dsro = nullptr, *dph = nullptr;
+  if ((rc = t2_to_device(ctx, 0, freq, (size_t)n_symbols * t->fft_size * 8, &dfreq))) return rc;
+  if ((rc = t2_to_device(ctx, 5, idx_symbol, (size_t)n_symbols * 4, &didx))) return rc;
+  if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)n_symbols * t->n_out * 8, &dout))) return rc;
+  if (sro && (rc = t2_out_device(ctx, 2, sro, (size_t)n_symbols * 4, &dsro))) return rc;
+  if (phase && (rc = t2_out_device(ctx, 3, phase, (size_t)n_symbols * 4, &dph))) return rc;
+  EqParams p;
+  p.freq = (const float2*)dfreq; p.out = (float2*)dout; p.sro = (float*)dsro; p.phase = (float*)dph; p.idx_symbol = (const int*)didx;
+  p.plans = t->d_plans; p.plan_even = t->d_plan_even; p.plan_odd = t->d_plan_odd;
+  p.lut_sin = ctx->d_lut; p.lut_cos = ctx->d_lut + 65536;
+  p.fft_size = t->fft_size; p.l_nulls = t->l_nulls; p.n_out = t->n_out; p.first_symbol = t->first_symbol; p.n_symbols_kind = t->n_symbols;
+  const size_t smem = (size_t)(t->max_pilots + 2) * 16;
+  T2_CUDA(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  equalize_kernel<<<n_symbols, 512, smem, ctx->stream>>>(p);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  if ((rc = t2_finish_out(ctx, cells_out, dout, (size_t)n_symbols * t->n_out * 8))) return rc;
+  if (sro && (rc = t2_finish_out(ctx, sro, dsro, (size_t)n_symbols * 4))) return rc;
+  if (phase && (rc = t2_finish_out(ctx, phase, dph, (size_t)n_symbols * 4))) return rc;
+  return T2B200_OK;
+}

@@ -26,7 +26,7 @@ SYMBOLS = [
     't2b200_ldpc_code_id', 't2b200_ldpc_n', 't2b200_ldpc_k', 't2b200_ldpc_k_bch',
     't2b200_ldpc_decode', 't2b200_bch_descramble',
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
-    't2b200_demap',
+    't2b200_demap', 't2b200_eq_configure', 't2b200_equalize',
 ]
 
 
@@ -67,6 +67,8 @@ def lib():
     L.t2b200_ti_configure.argtypes = [vp, i32, i32, i32, i32, vp]
     L.t2b200_ti_deinterleave.argtypes = [vp, i32, vp, i32, vp, vp]
     L.t2b200_demap.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.t2b200_eq_configure.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float]
+    L.t2b200_equalize.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -205,6 +207,27 @@ class Engine:
         self._chk(self.L.t2b200_demap(self.h, _ptr(ti_cells), len(nf), _ptr(nf), mod, rotation, fec_type, code_rate,
                                       _ptr(llr), _ptr(snr), _ptr(prec), _ptr(precision_in)))
         return {'llr': llr, 'snr': snr, 'precision': prec}
+
+    # ---- K2 ----
+    def eq_configure(self, kind, first_symbol, fft_size, k_total, l_nulls, n_out, carrier_map, pilot_refer,
+                     h_even, h_odd, amp_main, amp_cp=0.0):
+        cm = np.ascontiguousarray(carrier_map, np.int32).reshape(-1, k_total)
+        pr = np.ascontiguousarray(pilot_refer, np.float32).reshape(-1, k_total)
+        he, ho = np.ascontiguousarray(h_even, np.int32), np.ascontiguousarray(h_odd, np.int32)
+        self._eq_nout = getattr(self, '_eq_nout', {})
+        self._eq_nout[kind] = (n_out, fft_size)
+        self._chk(self.L.t2b200_eq_configure(self.h, kind, cm.shape[0], first_symbol, fft_size, k_total, l_nulls, n_out,
+                                             _ptr(cm), _ptr(pr), _ptr(he), _ptr(ho), amp_main, amp_cp))
+
+    def equalize(self, kind, idx_symbol, freq, out=None):
+        """freq complex64[n][fft_size] (numpy / torch cuda) -> (cells complex64[n][n_out], sro[n], phase[n])"""
+        n_out, fft_size = self._eq_nout[kind]
+        idx = np.ascontiguousarray(idx_symbol, np.int32)
+        n = len(idx)
+        cells = out if out is not None else _like(freq, (n, n_out), np.complex64)
+        sro, ph = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._chk(self.L.t2b200_equalize(self.h, kind, n, _ptr(idx), _ptr(freq), _ptr(cells), _ptr(sro), _ptr(ph)))
+        return cells, sro, ph
 
 
 def cell_permutation(n_fec_blocks, cells_per_fec):
