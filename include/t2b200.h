@@ -165,6 +165,15 @@ int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int first_symb
 int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx_symbol,
                     const float* freq, float* cells_out, float* sro, float* phase);
 
+/* ---- K1: OFDM FFT --------------------------------------------------------------------------- */
+/* Replaces fast_fourier_transform::init + execute (DSP/fast_fourier_transform.h:54-70) for a batch of
+ * symbols: out[b] = halves-swapped, unnormalised forward DFT (FFTW_FORWARD sign) of in[b].
+ *   n      4096, 8192, 16384 or 32768 (the reference runs 16K and 32K)
+ *   in     complex<float>[batch][n]  the n samples after the guard interval (dvbt2_demodulator.cpp:332)
+ *   out    complex<float>[batch][n]  carrier k of the active band sits at index l_nulls + k
+ * FFTW is a binary-only dependency of the reference: agreement is to <= 1e-5 * max|X| (float64 DFT). */
+int t2b200_fft(t2b200_ctx* ctx, int n, const float* in, int batch, float* out);
+
 #ifdef __cplusplus
 }
 #endif

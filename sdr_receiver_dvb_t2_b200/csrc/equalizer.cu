@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(512) equalize_kernel(const EqParams p)
   const PlanDev pl = p.plans[(idx & 1) ? p.plan_odd[rel] : p.plan_even[rel]];
   float* ang = reinterpret_cast<float*>(smem_raw);
   float* amp = ang + pl.n_pilots;
-  float2* est = reinterpret_cast<float2*>(amp + pl.n_pilots + (pl.n_pilots & 1));
+  float2* est = reinterpret_cast<float2*>(amp + pl.n_pilots);          // 2 * n_pilots floats in: 8-byte aligned
   const float2* cell = p.freq + (size_t)s * p.fft_size + p.l_nulls;
   float2* out = p.out + (size_t)s * p.n_out;
 

@@ -26,7 +26,7 @@ SYMBOLS = [
     't2b200_ldpc_code_id', 't2b200_ldpc_n', 't2b200_ldpc_k', 't2b200_ldpc_k_bch',
     't2b200_ldpc_decode', 't2b200_bch_descramble',
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
-    't2b200_demap', 't2b200_eq_configure', 't2b200_equalize',
+    't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
     L.t2b200_demap.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.t2b200_eq_configure.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float]
     L.t2b200_equalize.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.t2b200_fft.argtypes = [vp, i32, vp, i32, vp]
     _lib = L
     return L
 
@@ -207,6 +208,14 @@ class Engine:
         self._chk(self.L.t2b200_demap(self.h, _ptr(ti_cells), len(nf), _ptr(nf), mod, rotation, fec_type, code_rate,
                                       _ptr(llr), _ptr(snr), _ptr(prec), _ptr(precision_in)))
         return {'llr': llr, 'snr': snr, 'precision': prec}
+
+    # ---- K1 ----
+    def fft(self, x, out=None):
+        """x complex64[batch][n] (numpy / torch cuda) -> shifted unnormalised forward DFT, same type"""
+        batch, n = x.shape
+        o = out if out is not None else _like(x, (batch, n), np.complex64)
+        self._chk(self.L.t2b200_fft(self.h, n, _ptr(x), batch, _ptr(o)))
+        return o
 
     # ---- K2 ----
     def eq_configure(self, kind, first_symbol, fft_size, k_total, l_nulls, n_out, carrier_map, pilot_refer,
