@@ -66,6 +66,14 @@ int  t2b200_set_stream(t2b200_ctx* ctx, void* cuda_stream);
 int  t2b200_sync(t2b200_ctx* ctx);
 const char* t2b200_last_error(const t2b200_ctx* ctx);
 const char* t2b200_version(void);
+/* Options.  Everything defaults to the reference's behaviour.
+ * T2B200_OPT_DEMAP_SATURATE (default 0): the reference converts LLRs with a C cast that WRAPS modulo 256
+ * (llr_demapper.cpp:722-737; 193.f -> -63).  For 256-QAM its decision-directed precision is never below
+ * ~116, so the outer constellation levels always wrap and the reference's own LDPC stage cannot converge on
+ * a clean AWGN signal (DESIGN.md "reference quirks").  1 = clamp to [-128,127] instead -- NOT bit-compatible
+ * with the reference, provided so the engine is usable; parity tests run with 0.                         */
+enum { T2B200_OPT_DEMAP_SATURATE = 1 };
+int t2b200_set_option(t2b200_ctx* ctx, int option, int value);
 /* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
 long long t2b200_launch_count(const t2b200_ctx* ctx);
 

@@ -139,6 +139,14 @@ int t2b200_sync(t2b200_ctx* ctx)
   return T2B200_OK;
 }
 
+int t2b200_set_option(t2b200_ctx* ctx, int option, int value)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (option == T2B200_OPT_DEMAP_SATURATE) { ctx->opt_demap_saturate = value != 0; return T2B200_OK; }
+  ctx->err = "t2b200_set_option: unknown option";
+  return T2B200_ERR_ARG;
+}
+
 const char* t2b200_last_error(const t2b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 long long t2b200_launch_count(const t2b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

@@ -26,6 +26,7 @@ struct t2b200_ctx {
   cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
   std::string err;
   long long launches = 0;
+  int opt_demap_saturate = 0;                 // T2B200_OPT_DEMAP_SATURATE
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id
   float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes

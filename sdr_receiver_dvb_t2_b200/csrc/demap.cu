@@ -171,15 +171,18 @@ __global__ void demap_ordered_sum_kernel(const float2* __restrict__ terms, const
   }
 }
 
-// (int8_t)(float) as x86-64 gcc compiles it: cvttss2si to int32 (0x80000000 when out of range), low byte
+// (int8_t)(float) as x86-64 gcc compiles it: cvttss2si to int32 (0x80000000 when out of range), low byte.
+// SAT (non-reference option T2B200_OPT_DEMAP_SATURATE) clamps to [-128, 127] instead of wrapping.
+template <bool SAT>
 __device__ __forceinline__ int wrap_i8(float r)
 {
+  if (SAT) return (int)fminf(fmaxf(r, -128.0f), 127.0f);
   if (!(fabsf(r) < 2147483648.0f)) return 0;
   return (int)(int8_t)(__float2int_rz(r) & 0xff);
 }
 
 // ---- K4 pass 2: one CTA per FECFRAME -----------------------------------------------------------
-template <int MOD>
+template <int MOD, bool SAT>
 __global__ void demap_llr_kernel(const float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
                                  const float* __restrict__ precision, const int32_t* __restrict__ address,
                                  int8_t* __restrict__ llr, int cpf, int fec_bits)
@@ -207,8 +210,8 @@ __global__ void demap_llr_kernel(const float2* __restrict__ cells, const DemapBl
         }
         const int bi = BPC * k + 2 * l;
         const int ai = MOD == 0 ? bi : __ldg(address + bi), aq = MOD == 0 ? bi + 1 : __ldg(address + bi + 1);
-        frame[ai] = (int8_t)wrap_i8(ri);
-        frame[aq] = (int8_t)wrap_i8(rq);
+        frame[ai] = (int8_t)wrap_i8<SAT>(ri);
+        frame[aq] = (int8_t)wrap_i8<SAT>(rq);
         if (l < MOD) {                                   // next level: |x| - (2^(MOD-l)) * a
           const float t = a * (float)(1 << (MOD - l));
           xi = __fsub_rn(fabsf(xi), t);
@@ -343,7 +346,7 @@ static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* 
   T2_CUDA(ctx, cudaGetLastError());
   demap_ordered_sum_kernel<MOD><<<n_blocks, 32, 0, ctx->stream>>>((const float2*)d_terms, d_desc, d_prec, d_snr, d_prec_in);
   T2_CUDA(ctx, cudaGetLastError());
-  auto k = demap_llr_kernel<MOD>;
+  auto k = ctx->opt_demap_saturate ? demap_llr_kernel<MOD, true> : demap_llr_kernel<MOD, false>;
   const size_t smem = (size_t)((fec_bits + 15) & ~15);
   T2_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<dim3(std::min(max_fec, ctx->sm_count * 3), n_blocks), 512, smem, ctx->stream>>>(d_cells, d_desc, d_prec, d_addr, d_llr, cpf, fec_bits);

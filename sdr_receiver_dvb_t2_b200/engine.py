@@ -18,11 +18,12 @@ LDPC_GROUP32, LDPC_BCH_DESCRAMBLE, LDPC_PACK_BITS, LDPC_WANT_POST = 1, 2, 4, 8
 C1_2, C3_5, C2_3, C3_4, C4_5, C5_6 = range(6)
 MOD_QPSK, MOD_16QAM, MOD_64QAM, MOD_256QAM = range(4)
 FEC_SHORT, FEC_NORMAL = 0, 1
+OPT_DEMAP_SATURATE = 1
 
 # every symbol include/t2b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     't2b200_create', 't2b200_destroy', 't2b200_set_stream', 't2b200_sync', 't2b200_last_error',
-    't2b200_version', 't2b200_launch_count',
+    't2b200_version', 't2b200_launch_count', 't2b200_set_option',
     't2b200_ldpc_code_id', 't2b200_ldpc_n', 't2b200_ldpc_k', 't2b200_ldpc_k_bch',
     't2b200_ldpc_decode', 't2b200_bch_descramble',
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
@@ -59,6 +60,7 @@ def lib():
     L.t2b200_last_error.restype = C.c_char_p
     L.t2b200_version.restype = C.c_char_p
     L.t2b200_launch_count.argtypes = [vp]
+    L.t2b200_set_option.argtypes = [vp, i32, i32]
     L.t2b200_launch_count.restype = C.c_longlong
     L.t2b200_ldpc_decode.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, u32]
     L.t2b200_bch_descramble.argtypes = [vp, i32, vp, i32, vp]
@@ -144,6 +146,9 @@ class Engine:
         else:
             h = stream
         self._chk(self.L.t2b200_set_stream(self.h, C.c_void_p(h)))
+
+    def set_option(self, option, value):
+        self._chk(self.L.t2b200_set_option(self.h, option, int(value)))
 
     @property
     def launches(self):
