@@ -22,7 +22,7 @@ class FrameChain:
         self.torch = torch
         self.eng, self.t, self.p = eng, tables, tables['p']
         p = self.p
-        self.mod, self.cod, self.fec, self.rot, self.plp = mod, cod, fec_type, rotation, plp
+        self.mod, self.cod, self.fec_type, self.rot, self.plp = mod, cod, fec_type, rotation, plp
         self.nbits = 64800 if fec_type else 16200
         self.cpf = self.nbits // (2 * (mod + 1))
         base = n_blocks // ti_len
@@ -90,7 +90,7 @@ class FrameChain:
         F = stream.shape[0]
         blocks = self.blocks * F
         ti = self.eng.ti_deinterleave(self.plp, stream.reshape(-1), blocks)
-        d = self.eng.demap(ti, blocks, self.mod, self.rot, self.fec, self.cod, precision_in=precision_in)
+        d = self.eng.demap(ti, blocks, self.mod, self.rot, self.fec_type, self.cod, precision_in=precision_in)
         r = self.eng.ldpc_decode(self.code, d['llr'], flags=flags, max_trials=max_trials)
         r['snr'], r['precision'] = d['snr'], d['precision']
         if want_llr:

@@ -79,9 +79,11 @@ def test_post_fft_chain_bit_exact_c32_256qam(engine):
     assert np.array_equal(stream.cpu().numpy()[0].view(np.float32), stream_o.view(np.float32))
     perm = O.port_cell_permutation(68, 8100)
     ti_o = O.port_ti_blocks(stream_o, m.blocks, 8100, perm, [0, 0.0])
+    ti = engine.ti_deinterleave(0, stream.reshape(-1), m.blocks)                 # before the demapper derotates it in place
+    engine.sync()
+    assert np.array_equal(ti.cpu().numpy().view(np.float32), ti_o.view(np.float32))
     r = ch.fec(stream, want_llr=True)
     engine.sync()
-    assert np.array_equal(r['ti'].cpu().numpy().view(np.float32), ti_o.view(np.float32))
     off, llr_o, prec_o = 0, [], []
     for nf in m.blocks:
         l, s, pr, _ = O.port_demap(ti_o[off:off + nf * 8100], 3, 1, 1, 2)
