@@ -3,14 +3,16 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl t2b200|reference]
 
-Workload (BASELINE.json configs[1]): 8 MHz 32K 256-QAM r2/3, 64 800-bit FECFRAMEs.  One "step" is one
-pass of the FEC hot path (layered min-sum LDPC with the reference's 32-codeword lock-step batch
-semantics + BCH-parity strip + BB descramble, one fused kernel) over a batch of 4096 codewords
-(= 20.3 T2 frames of 202 FEC blocks, 265 MB of int8 LLRs: larger than the 126 MB L2, and three such
-batches are rotated).  `value` = LDPC codewords/s with inputs resident in HBM; `e2e` = the same through
-the C-ABI with HOST (pinned) buffers, H2D + D2H inside the timed region; `ts_mbit_s` is the TS payload
-rate those codewords carry (HEM BBFRAMEs).  N > 1: one process per GPU (torchrun), codewords are
-independent so ranks decode disjoint shards with no data-path collective (weak scaling).
+Workload (BASELINE.json configs[1]): 8 MHz 32K extended PP7 GI 1/128 SISO, one PLP 256-QAM rotated r2/3 with
+64 800-bit FECFRAMEs (202 FEC blocks per T2 frame, TI blocks 67/67/68).  One "step" is one pass of the WHOLE hot
+path -- FFT, equalise + frequency de-interleave, time/cell de-interleave + Q-delay removal, soft demap, layered
+min-sum LDPC with the reference's 32-codeword lock-step semantics, BCH-parity strip + BB descramble -- over 20
+synthetic T2 frames (tools/modulator.py + AWGN; 1 200 OFDM symbols, 4 040 codewords, 315 MB of IQ: larger than the
+126 MB L2, three such batches are rotated).  `value` = LDPC codewords/s with the IQ resident in HBM; `e2e` = the
+same with pinned HOST IQ in and HOST BBFRAME bits out, copies inside the timed region; `ts_mbit_s` is the TS
+payload those codewords carry.  `stages` gives every stage's device time and HBM fraction, `roofline` the
+dominant kernel.  N > 1: one process per GPU (torchrun); T2 frames / FEC blocks are independent, ranks take
+disjoint shards with no data-path collective (weak scaling).
 
 --impl reference times the reference's own CPU decoder (oracle/_ref, compiled from the unmodified
 sources; else the C port) on all host threads on a bounded sample of the same workload.
@@ -29,6 +31,8 @@ sys.path.insert(0, ROOT)
 CODE_N, CODE_K, CODE_KBCH = 64800, 43200, 43040      # normal FECFRAME, rate 2/3
 CODE_ID = 2
 BATCH = 4096
+FRAMES_PER_STEP = 20      # 20 x 202 = 4040 codewords, 315 MB of IQ per step
+CN_DB = 20.5
 EBN0_DB = 2.9            # BPSK-equivalent operating point: ~5.5 mean / 6.5 group-max iterations
 FEC_PER_FRAME = 202      # C32 frame, 256-QAM r2/3
 
@@ -97,7 +101,7 @@ def synth_llr(torch, n, device, seed):
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_rate(seconds_budget=12.0):
+def cpu_reference_rate(seconds_budget=12.0, sample=None):
     """Reference CPU LDPC decoder (oracle/_ref when built, else the C port) on all host threads.
     Returns (codewords/s, info dict)."""
     import numpy as np
@@ -133,14 +137,19 @@ def cpu_reference_rate(seconds_budget=12.0):
             res[idx] = n
 
     # calibrate on one group, then size the sample to the budget
-    g0 = make_group()
+    g0 = make_group() if sample is None else np.ascontiguousarray(sample[:32])
     t = time.perf_counter()
     res = [0]
     worker([g0], res, 0)
     t1 = time.perf_counter() - t
     # threads share the cores' SIMD units / caches: assume no better than t1 per group per thread
     per_thread = max(1, min(1024, int(seconds_budget / max(t1, 1e-3))))
-    distinct = [make_group() for _ in range(4)]
+    if sample is not None and len(sample) >= 32:          # LLRs of the GPU run's own demapper: same iteration statistics
+        distinct = [np.ascontiguousarray(sample[32 * i:32 * i + 32]) for i in range(min(4, len(sample) // 32))]
+        while len(distinct) < 4:
+            distinct.append(distinct[0])
+    else:
+        distinct = [make_group() for _ in range(4)]
     groups = [[distinct[(i + k) % 4] for k in range(per_thread)] for i in range(ncpu)]
     res = [0] * ncpu
     th = [threading.Thread(target=worker, args=(groups[i], res, i)) for i in range(ncpu)]
@@ -188,6 +197,9 @@ def run_t2b200(args):
     import torch
     import sdr_receiver_dvb_t2_b200 as t2
     from sdr_receiver_dvb_t2_b200 import engine as E
+    from sdr_receiver_dvb_t2_b200.chain import FrameChain
+    from tools.make_golden_tables import load as load_tables
+    from tools.modulator import Modulator
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -208,50 +220,100 @@ def run_t2b200(args):
 
     stream = torch.cuda.Stream(device=dev)
     eng = t2.Engine(local, stream=stream.cuda_stream)
-    flags = E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE
-
-    # three distinct resident batches (3 x 265 MB): successive steps never find their input in L2
-    nbuf = 3
-    llr = [synth_llr(torch, BATCH, dev, 1000 * rank + i) for i in range(nbuf)]
-    out = torch.empty((BATCH, CODE_KBCH), dtype=torch.uint8, device=dev)
-
+    # The reference's LLR cast wraps modulo 256 and its decision-directed precision is never below ~116 for
+    # 256-QAM, so on AWGN its own LDPC stage never converges (tests/test_chain_gpu.py reproduces that bit for bit).
+    # The throughput workload therefore runs with the documented saturating-cast option; every other operation is
+    # the reference's.  The reference-exact (never converging, 25 trials) timing is reported next to it.
+    eng.set_option(E.OPT_DEMAP_SATURATE, 1)
+    tables = load_tables(os.path.join(ROOT, 'tests', 'golden', 'tables_c32.npz'))
+    p = tables['p']
+    L, N = p['len_frame'], p['fft_size']
+    F = FRAMES_PER_STEP
+    mod = Modulator(tables, mod=3, cod=2, fec_normal=True, n_blocks=FEC_PER_FRAME, ti_len=3, seed=100 + rank)
+    clean = np.stack([mod.frame(noise_cn_db=None)['time'] for _ in range(4)])            # 4 distinct frames of payload
+    sigma = 200.0 * 10 ** (-CN_DB / 20) / np.sqrt(2) / np.sqrt(N)                         # tools/modulator.py: scale 200
     with torch.cuda.stream(stream):
-        r = eng.ldpc_decode(CODE_ID, llr[0], flags=flags, out=out)
+        d_clean = torch.from_numpy(clean).to(dev)
+        nbuf = 3
+        bufs = []
+        g = torch.Generator(device=dev)
+        g.manual_seed(7 + rank)
+        for i in range(nbuf):                                # 3 x 315 MB of distinct noisy IQ: never L2-resident
+            x = d_clean[torch.arange(F, device=dev) % 4].clone()
+            x += torch.view_as_complex(sigma * torch.randn((F, L, N, 2), generator=g, device=dev))
+            bufs.append(x)
+        chain = FrameChain(eng, tables, mod=3, cod=2, fec_type=1, n_blocks=FEC_PER_FRAME, ti_len=3)
+        r = chain.decode_frames(bufs[0])
         stream.synchronize()
         mean_iters = float(r['iterations'].float().mean().item())
         frac_ok = float((r['trials_left'] >= 0).float().mean().item())
-        bit_err = int(out.sum().item()) if False else None  # descrambled output is not all-zero; parity is tests' job
+        sample_llr = None
 
         for i in range(args.warmup):
-            eng.ldpc_decode(CODE_ID, llr[i % nbuf], flags=flags, out=out, want_status=False)
+            chain.decode_frames(bufs[i % nbuf], want_status=False)
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
+        chain.events = {}
         launches0 = eng.launches
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        ev[0].record(stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
         for i in range(args.steps):
-            eng.ldpc_decode(CODE_ID, llr[(args.warmup + i) % nbuf], flags=flags, out=out, want_status=False)
-            ev[i + 1].record(stream)
+            chain.decode_frames(bufs[(args.warmup + i) % nbuf], want_status=False)
+        e1.record(stream)
         barrier()
         launches = eng.launches - launches0
-        total_ms = ev[0].elapsed_time(ev[-1])
-        step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        total_ms = e0.elapsed_time(e1)
+        stage_ms = chain.stage_ms()
+        chain.events = None
 
-        # ---- end to end through the C-ABI with host buffers (pinned), H2D + D2H in the timed region ----
-        h_llr = [torch.empty((BATCH, CODE_N), dtype=torch.int8).pin_memory() for _ in range(2)]
+        # ---- LDPC stage alone on the LLRs of one batch (explains the chain number; roofline of the dominant kernel) ----
+        stream_cells, _, _ = chain.demodulate(bufs[0])
+        rr = chain.fec(stream_cells, want_llr=True)
+        llr = rr['llr']
+        out_bits = torch.empty((llr.shape[0], CODE_KBCH), dtype=torch.uint8, device=dev)
+        flags = E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE
+        for _ in range(2):
+            eng.ldpc_decode(CODE_ID, llr, flags=flags, out=out_bits, want_status=False)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(5):
+            eng.ldpc_decode(CODE_ID, llr, flags=flags, out=out_bits, want_status=False)
+        k1.record(stream)
+        stream.synchronize()
+        ldpc_ms = k0.elapsed_time(k1) / 5
+        sample_llr = llr[:256].cpu().numpy()
+
+        # ---- reference-exact cast (wrapping): nothing converges, as in the reference ----
+        eng.set_option(E.OPT_DEMAP_SATURATE, 0)
+        chain.decode_frames(bufs[0], want_status=False)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        rx = chain.decode_frames(bufs[1])
+        x1.record(stream)
+        stream.synchronize()
+        exact_ms = x0.elapsed_time(x1)
+        exact_conv = float((rx['trials_left'] >= 0).float().mean().item())
+        eng.set_option(E.OPT_DEMAP_SATURATE, 1)
+
+        # ---- end to end: host (pinned) IQ in, host bits out, copies inside the timed region ----
+        h_in = [torch.empty((F, L, N), dtype=torch.complex64).pin_memory() for _ in range(2)]
         for i in range(2):
-            h_llr[i].copy_(llr[i])
-        h_out = torch.empty((BATCH, CODE_KBCH), dtype=torch.uint8).pin_memory()
-        np_llr = [h.numpy() for h in h_llr]
-        np_out = h_out.numpy()
-        e2e_steps = max(2, min(args.steps, 5))
-        eng.ldpc_decode(CODE_ID, np_llr[0], flags=flags, out=np_out, want_status=False)
+            h_in[i].copy_(bufs[i])
+        h_out = torch.empty((F * FEC_PER_FRAME, CODE_KBCH), dtype=torch.uint8).pin_memory()
+        d_in = torch.empty((F, L, N), dtype=torch.complex64, device=dev)
+        e2e_steps = max(2, min(args.steps, 4))
+
+        def e2e_step(i):
+            d_in.copy_(h_in[i % 2], non_blocking=True)
+            rr = chain.decode_frames(d_in, want_status=False)
+            h_out.copy_(rr['bits'], non_blocking=True)
+            stream.synchronize()
+        e2e_step(0)
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            eng.ldpc_decode(CODE_ID, np_llr[i % 2], flags=flags, out=np_out, want_status=False)  # returns with np_out filled
-        torch.cuda.synchronize()
+            e2e_step(i)
         e2e_s = time.perf_counter() - t0
         barrier()
         sampler.stop_flag = True
@@ -263,45 +325,61 @@ def run_t2b200(args):
     total_ms, e2e_s = float(t[0].item()), float(t[1].item())
 
     if rank == 0:
-        value = world * BATCH * args.steps / (total_ms * 1e-3)
-        e2e_value = world * BATCH * e2e_steps / e2e_s
+        cw_step = F * FEC_PER_FRAME
+        value = world * cw_step * args.steps / (total_ms * 1e-3)
+        e2e_value = world * cw_step * e2e_steps / e2e_s
         peak, peak_src = hbm_peak()
-        kern_ms = sorted(step_ms)[len(step_ms) // 2]          # one kernel launch per step
-        alg_bytes = (CODE_N + CODE_KBCH) * BATCH              # int8 LLRs in, one byte per bit out (K6 fused)
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        alg_bytes = (CODE_N + CODE_KBCH) * cw_step            # int8 LLRs in, one byte per bit out (K6 fused)
+        achieved = alg_bytes / (ldpc_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get('ldpc_decode_kernel_bytes_per_codeword')
-                traffic = traffic * BATCH if traffic else None
+                traffic = json.load(open(tp)).get('ldpc_decode_kernel_dram_bytes_per_codeword')
+                traffic = traffic * cw_step if traffic else None
             except Exception:
                 traffic = None
-        cpu = None
-        if world == 1 or rank == 0:
-            try:
-                v, info = cpu_reference_rate(seconds_budget=12.0)
-                cpu = dict(info, value=v, unit='codewords/s')
-            except Exception as e:  # the baseline is reported, never required for the GPU number
-                cpu = {'value': None, 'unit': 'codewords/s', 'cores': 0, 'kind': 'port', 'sample': 'failed: %s' % e}
+        try:
+            v, info = cpu_reference_rate(seconds_budget=12.0, sample=sample_llr)
+            cpu = dict(info, value=v, unit='codewords/s')
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            cpu = {'value': None, 'unit': 'codewords/s', 'cores': 0, 'kind': 'port', 'sample': 'failed: %s' % e}
+        # algorithmic bytes per frame of every stage and the HBM fraction each reaches
+        per_frame = {
+            'fft': L * 16 * N,
+            'equalize_p2': 8 * p['k_total'] + 8 * p['c_p2'],
+            'equalize_data': (L - 1) * (8 * p['k_total'] + 8 * p['c_data']),
+            'ti_deinterleave': 16 * FEC_PER_FRAME * 8100,
+            'demap': 16 * FEC_PER_FRAME * 8100,
+            'ldpc_bch': FEC_PER_FRAME * (CODE_N + CODE_KBCH),
+        }
+        stages = {k: {'ms': round(ms, 4), 'gb_s': round(per_frame[k] * F / (ms * 1e-3) / 1e9, 1),
+                      'hbm_frac': round(per_frame[k] * F / (ms * 1e-3) / 1e9 / peak, 4)} for k, ms in stage_ms.items() if k in per_frame}
         line = {
             'metric': 'ldpc_codewords_per_s', 'value': value, 'unit': 'codewords/s', 'ts_mbit_s': ts_mbit(value),
-            'realtime_multiple': value / 931.0,
+            't2_frames_per_s': value / FEC_PER_FRAME, 'realtime_multiple': value / 931.0,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
-            'config': {'workload': '8MHz 32K 256-QAM r2/3 FEC path: LDPC 64800 r2/3 (reference group-of-32 lock-step, '
-                                   '<=25 trials) + BCH strip + BB descramble, fused',
-                       'batch_codewords_per_gpu': BATCH, 't2_frames_per_step': BATCH / FEC_PER_FRAME,
-                       'ebn0_db': EBN0_DB, 'mean_iterations': mean_iters, 'converged_fraction': frac_ok,
-                       'l2': 'inputs 265 MB per step > 126 MB L2, 3 batches rotated', 'parallelism': 'shard%d' % world},
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 demod + int8 FEC', 'data': 'synthetic',
+            'config': {'workload': '8MHz 32K ext PP7 GI1/128 SISO, 1 PLP 256-QAM rotated r2/3 64800, TI 67/67/68: whole hot path '
+                                   'FFT -> equalise/freq-deint -> time/cell-deint -> demap -> LDPC(group-of-32, <=25 trials) -> '
+                                   'BCH strip + BB descramble, replay mode',
+                       'frames_per_step_per_gpu': F, 'codewords_per_step_per_gpu': cw_step, 'cn_db': CN_DB,
+                       'demap_cast': 'saturate (T2B200_OPT_DEMAP_SATURATE; the reference wraps and never converges on 256-QAM)',
+                       'mean_ldpc_iterations': mean_iters, 'converged_fraction': frac_ok,
+                       'l2': 'input IQ 315 MB per step > 126 MB L2, 3 batches rotated', 'parallelism': 'shard%d' % world},
             'e2e': {'value': e2e_value, 'unit': 'codewords/s', 'ts_mbit_s': ts_mbit(e2e_value),
-                    'h2d_bytes_per_step': BATCH * CODE_N, 'd2h_bytes_per_step': BATCH * CODE_KBCH,
-                    'steps': e2e_steps, 'api': 't2b200_ldpc_decode(host llr, host bits), pinned, chunk-pipelined'},
+                    'h2d_bytes_per_step': F * L * N * 8, 'd2h_bytes_per_step': cw_step * CODE_KBCH,
+                    'steps': e2e_steps, 'api': 'pinned host IQ -> FrameChain.decode_frames (t2b200_* C-ABI) -> host BBFRAME bits'},
             'gpu_launches': int(launches),
+            'stages': stages,
+            'ldpc_only': {'value': cw_step / (ldpc_ms * 1e-3), 'unit': 'codewords/s', 'ms': ldpc_ms},
+            'reference_exact_cast': {'ms_per_step': exact_ms, 'codewords_per_s': cw_step / (exact_ms * 1e-3),
+                                     'converged_fraction': exact_conv,
+                                     'note': 'wrapping cast: every group runs 25 trials and is dropped, as in the reference'},
             'roofline': {'bound': 'hbm', 'kernel': 'ldpc_decode_kernel', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'note': 'decoder state lives in shared memory: compute-bound by construction, '
-                                 'algorithmic bytes = N + K_bch per codeword'},
+                         'note': 'decoder state lives in shared memory: compute-bound by construction (SURVEY 8d); '
+                                 'algorithmic bytes = N + K_bch per codeword; streaming stages: see "stages"'},
             'cpu_baseline': cpu,
             'clocks': sampler.summary(),
         }

@@ -42,6 +42,7 @@ class FrameChain:
         eng.ti_configure(plp, fec_type, mod, max(self.blocks))
         self.need = n_blocks * self.cpf
         self._bufs = {}
+        self.events = None          # set to {} to collect per-stage CUDA events: name -> [(start, stop), ...]
 
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape), dtype)
@@ -51,6 +52,27 @@ class FrameChain:
             self._bufs[key] = b
         return b
 
+    def _timed(self, name):
+        chain = self
+
+        class _T:
+            def __enter__(self_inner):
+                if chain.events is not None:
+                    st = chain.torch.cuda.current_stream()
+                    self_inner.a = chain.torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record(st)
+
+            def __exit__(self_inner, *exc):
+                if chain.events is not None:
+                    b = chain.torch.cuda.Event(enable_timing=True)
+                    b.record(chain.torch.cuda.current_stream())
+                    chain.events.setdefault(name, []).append((self_inner.a, b))
+        return _T()
+
+    def stage_ms(self):
+        """mean device milliseconds per stage from the collected events"""
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.events or {}).items()}
+
     def demodulate(self, time):
         """time: torch complex64 cuda [F][len_frame][fft_size] -> PLP cell stream [F][n_blocks*cpf] (arrival order),
         sro / phase feedback [F][len_frame]"""
@@ -58,7 +80,8 @@ class FrameChain:
         F = time.shape[0]
         L, N = p['len_frame'], p['fft_size']
         freq = self._buf('freq', (F * L, N), torch.complex64)
-        eng.fft(time.reshape(F * L, N), out=freq)
+        with self._timed('fft'):
+            eng.fft(time.reshape(F * L, N), out=freq)
         freq3 = freq.reshape(F, L, N)
         # frame cell stream: P2 cells | data symbols | FC
         per_frame = p['c_p2'] + self.n_data_sym * p['c_data'] + (p['n_fc'] if p['l_fc'] else 0)
@@ -68,13 +91,16 @@ class FrameChain:
         # P2 symbols of all frames in one launch, data symbols of all frames in one launch (strided views are
         # materialised once: the equaliser wants [n][fft_size] / writes [n][n_out] contiguous)
         p2f = freq3[:, 0, :].contiguous()
-        c, s, h = eng.equalize(E_SYM_P2, np.zeros(F, np.int32), p2f)
+        with self._timed('equalize_p2'):
+            c, s, h = eng.equalize(E_SYM_P2, np.zeros(F, np.int32), p2f)
         cells[:, :p['c_p2']] = c
         sro[:, 0], ph[:, 0] = s, h
         nd = self.n_data_sym
         dfreq = freq3[:, p['n_p2']:p['n_p2'] + nd, :].reshape(F * nd, N)
         idx = np.tile(np.arange(p['n_p2'], p['n_p2'] + nd, dtype=np.int32), F)
-        c, s, h = eng.equalize(E_SYM_DATA, idx, dfreq.contiguous() if not dfreq.is_contiguous() else dfreq)
+        dfreq = dfreq.contiguous() if not dfreq.is_contiguous() else dfreq
+        with self._timed('equalize_data'):
+            c, s, h = eng.equalize(E_SYM_DATA, idx, dfreq)
         cells[:, p['c_p2']:p['c_p2'] + nd * p['c_data']] = c.reshape(F, nd * p['c_data'])
         sro[:, p['n_p2']:p['n_p2'] + nd], ph[:, p['n_p2']:p['n_p2'] + nd] = s.reshape(F, nd), h.reshape(F, nd)
         if p['l_fc']:
@@ -85,13 +111,17 @@ class FrameChain:
         stream = cells[:, self.p2_start:self.p2_start + self.need].contiguous()
         return stream, sro, ph
 
-    def fec(self, stream, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE, precision_in=None, want_llr=False, max_trials=25):
+    def fec(self, stream, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE, precision_in=None, want_llr=False, max_trials=25,
+            want_status=True):
         """stream [F][n_blocks*cpf] complex64 cuda -> dict(bits [F*n_blocks][K_bch|K], trials_left, iterations, snr, llr?)"""
         F = stream.shape[0]
         blocks = self.blocks * F
-        ti = self.eng.ti_deinterleave(self.plp, stream.reshape(-1), blocks)
-        d = self.eng.demap(ti, blocks, self.mod, self.rot, self.fec_type, self.cod, precision_in=precision_in)
-        r = self.eng.ldpc_decode(self.code, d['llr'], flags=flags, max_trials=max_trials)
+        with self._timed('ti_deinterleave'):
+            ti = self.eng.ti_deinterleave(self.plp, stream.reshape(-1), blocks)
+        with self._timed('demap'):
+            d = self.eng.demap(ti, blocks, self.mod, self.rot, self.fec_type, self.cod, precision_in=precision_in)
+        with self._timed('ldpc_bch'):
+            r = self.eng.ldpc_decode(self.code, d['llr'], flags=flags, max_trials=max_trials, want_status=want_status)
         r['snr'], r['precision'] = d['snr'], d['precision']
         if want_llr:
             r['llr'], r['ti'] = d['llr'], ti
