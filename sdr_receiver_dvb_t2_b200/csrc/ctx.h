@@ -35,7 +35,7 @@ struct t2b200_ctx {
   SymbolTables* sym[3] = {nullptr, nullptr, nullptr};
   TiDemapState* ti = nullptr;
   // staging scratch, grown on demand
-  Scratch dev[8];
+  Scratch dev[16];
   Scratch pin[8];
 };
 

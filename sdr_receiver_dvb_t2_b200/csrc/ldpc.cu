@@ -28,6 +28,7 @@
 #include "ctx.h"
 #include "ldpc_schedule.h"
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace {
@@ -42,6 +43,7 @@ constexpr int kMaxEdgeWords = 648;     // max q * CNL over all codes (rate 3/5 n
 struct LdpcParams {
   const int8_t* llr; uint8_t* bits; int32_t* trials_left; int32_t* iters; int8_t* post_out;
   const uint8_t* level; const uint8_t* prbs; unsigned* gsync;
+  void* cn_state;                     // [grid][R] packed check-node words (L2-resident scratch, thread-private)
   int n_cw, group_lanes, max_trials; unsigned flags;
   int N, K, q, k_out;
   // CN (i,j) data edge c reads posterior 360*g + (j + shift) mod 360 = j + ea - (j >= et ? 360 : 0)
@@ -253,14 +255,19 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
   return bad;
 }
 
-template <int CNL, typename ST>
-__global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
+// co-resident CTAs per SM the register budget is cut for (65536 / (384 * MINB) registers per thread)
+
+template <int CNL, typename ST, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   int8_t* post = reinterpret_cast<int8_t*>(smem);
-  ST* state = reinterpret_cast<ST*>(smem + ((p.N + 15) & ~15));
+  uint32_t* hb = reinterpret_cast<uint32_t*>(smem + ((p.N + 15) & ~15));
   const int R = p.N - p.K;
-  uint32_t* hb = reinterpret_cast<uint32_t*>(state + R);
+  // Check-node words are private to the thread that owns check node (i, tid): they live in an L2-resident
+  // global scratch (ld/st.cg, next layer's word prefetched a layer ahead) so that shared memory only holds the
+  // posteriors and two or three codewords fit on one SM.
+  ST* state = reinterpret_cast<ST*>(p.cn_state) + (size_t)blockIdx.x * R;
   __shared__ int s_flag;
 
   const int tid = threadIdx.x;
@@ -278,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
       const int2* src = reinterpret_cast<const int2*>(p.llr + (size_t)cw * p.N);
       int2* dst = reinterpret_cast<int2*>(post);
       for (int k = tid; k < p.N / 8; k += kThreads) dst[k] = __ldg(src + k);
-      for (int k = tid; k < R; k += kThreads) state[k] = 0;
+      if (tid < 360)
+        for (int i = 0; i < p.q; ++i) __stcg(state + i * 360 + tid, (ST)0);
     }
     __syncthreads();
 
@@ -299,7 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
       }
       if (!(group_bad && --trials >= 0)) break;
       // ---- one update() ----
+      ST w_next = tid < 360 ? __ldcg(state + tid) : (ST)0;
       for (int i = 0; i < p.q; ++i) {
+        const ST w_cur = w_next;
+        if (tid < 360 && i + 1 < p.q) w_next = __ldcg(state + (i + 1) * 360 + tid);
         const int cnt = p.cnt[i];
         const int nl = p.nlev[i];
         const uint16_t* ea = p.ea + i * CNL;
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
         CheckNode<CNL, ST> cn;
         if (nl == 1) {
           if (tid < 360) {
-            cn.begin(post, state[i * 360 + tid]);
+            cn.begin(post, w_cur);
             if (cnt == CNL) {
               cn.template load<ALL_SLOTS>(ea, et, cnt, ~0u, true, i, tid, p.K, p.q);
               cn.template store<ALL_SLOTS>(cnt, ~0u, true, i, tid);
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
               cn.template load<PREDICATED>(ea, et, cnt, ~0u, true, i, tid, p.K, p.q);
               cn.template store<PREDICATED>(cnt, ~0u, true, i, tid);
             }
-            state[i * 360 + tid] = cn.finish();
+            __stcg(state + i * 360 + tid, cn.finish());
           }
           __syncthreads();
         } else {
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
           int mylev = 0;
           if (tid < 360) {
             mylev = __ldg(p.level + (int)p.cidx[i] * 360 + tid);
-            cn.begin(post, state[i * 360 + tid]);
+            cn.begin(post, w_cur);
             cn.template load<PREDICATED>(ea, et, cnt, ~sh, true, i, tid, p.K, p.q);
           }
           if (__popc(sh) == 2) {
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
           }
           if (tid < 360) {
             cn.template store<PREDICATED>(cnt, ~sh, true, i, tid);
-            state[i * 360 + tid] = cn.finish();
+            __stcg(state + i * 360 + tid, cn.finish());
           }
           __syncthreads();
         }
@@ -406,10 +417,10 @@ __global__ void __launch_bounds__(kThreads, 1) ldpc_decode_kernel(const __grid_c
   }
 }
 
-template <int CNL, typename ST>
+template <int CNL, typename ST, int MINB>
 cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
 {
-  auto k = ldpc_decode_kernel<CNL, ST>;
+  auto k = ldpc_decode_kernel<CNL, ST, MINB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (p.group_lanes > 1) {     // lock-step lanes spin on each other: they must be co-resident
@@ -420,10 +431,10 @@ cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
   return cudaGetLastError();
 }
 
-template <int CNL, typename ST>
+template <int CNL, typename ST, int MINB>
 cudaError_t occupancy(size_t smem, int* blocks_per_sm)
 {
-  auto k = ldpc_decode_kernel<CNL, ST>;
+  auto k = ldpc_decode_kernel<CNL, ST, MINB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreads, smem);
@@ -432,25 +443,31 @@ cudaError_t occupancy(size_t smem, int* blocks_per_sm)
 // smallest instantiated CNL >= cnl_max
 const int kCnlBuckets[] = {4, 5, 7, 8, 9, 11, 12, 13, 16, 17, 20};
 
-#define DISPATCH(CALL)                                                             \
-  switch (cnl) {                                                                   \
-    case 4:  return CALL(4, uint32_t);   case 5:  return CALL(5, uint32_t);        \
-    case 7:  return CALL(7, uint32_t);   case 8:  return CALL(8, uint32_t);        \
-    case 9:  return CALL(9, uint32_t);   case 11: return CALL(11, uint32_t);       \
-    case 12: return CALL(12, uint32_t);  case 13: return CALL(13, uint32_t);       \
-    case 16: return CALL(16, uint64_t);  case 17: return CALL(17, uint64_t);       \
-    case 20: return CALL(20, uint64_t);                                            \
-    default: return cudaErrorInvalidValue;                                         \
+// (CNL bucket, register budget) instantiations: minb = co-resident CTAs per SM the register allocation is cut for
+#define DISPATCH(CALL)                                                                    \
+  switch (cnl * 4 + minb) {                                                               \
+    case 4 * 4 + 2:  return CALL(4, uint32_t, 2);   case 4 * 4 + 3:  return CALL(4, uint32_t, 3);   \
+    case 5 * 4 + 2:  return CALL(5, uint32_t, 2);   case 5 * 4 + 3:  return CALL(5, uint32_t, 3);   \
+    case 7 * 4 + 2:  return CALL(7, uint32_t, 2);   case 7 * 4 + 3:  return CALL(7, uint32_t, 3);   \
+    case 8 * 4 + 2:  return CALL(8, uint32_t, 2);   case 8 * 4 + 3:  return CALL(8, uint32_t, 3);   \
+    case 9 * 4 + 2:  return CALL(9, uint32_t, 2);   case 9 * 4 + 3:  return CALL(9, uint32_t, 3);   \
+    case 11 * 4 + 2: return CALL(11, uint32_t, 2);  case 11 * 4 + 3: return CALL(11, uint32_t, 3);  \
+    case 12 * 4 + 2: return CALL(12, uint32_t, 2);  case 12 * 4 + 3: return CALL(12, uint32_t, 3);  \
+    case 13 * 4 + 2: return CALL(13, uint32_t, 2);  case 13 * 4 + 3: return CALL(13, uint32_t, 3);  \
+    case 16 * 4 + 1: return CALL(16, uint64_t, 1);  case 16 * 4 + 2: return CALL(16, uint64_t, 2);  \
+    case 17 * 4 + 1: return CALL(17, uint64_t, 1);  case 17 * 4 + 2: return CALL(17, uint64_t, 2);  \
+    case 20 * 4 + 1: return CALL(20, uint64_t, 1);  case 20 * 4 + 2: return CALL(20, uint64_t, 2);  \
+    default: return cudaErrorInvalidValue;                                                \
   }
 
-cudaError_t launch_dispatch(int cnl, const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_dispatch(int cnl, int minb, const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
 {
-#define CALL_L(C, T) launch<C, T>(p, grid, smem, st)
+#define CALL_L(C, T, B) launch<C, T, B>(p, grid, smem, st)
   DISPATCH(CALL_L)
 }
-cudaError_t occupancy_dispatch(int cnl, size_t smem, int* bps)
+cudaError_t occupancy_dispatch(int cnl, int minb, size_t smem, int* bps)
 {
-#define CALL_O(C, T) occupancy<C, T>(smem, bps)
+#define CALL_O(C, T, B) occupancy<C, T, B>(smem, bps)
   DISPATCH(CALL_O)
 }
 
@@ -459,6 +476,7 @@ cudaError_t occupancy_dispatch(int cnl, size_t smem, int* bps)
 struct LdpcDeviceCode {
   LdpcSchedule s;
   int cnl = 0;              // instantiated bucket
+  int minb = 1;             // register-budget variant (CTAs per SM)
   size_t state_bytes = 4, smem = 0;
   int blocks_per_sm = 0;
   uint8_t* d_level = nullptr;
@@ -478,8 +496,8 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
     delete d; ctx->err = "LDPC code geometry not instantiated"; return T2B200_ERR_ARG;
   }
   d->state_bytes = d->cnl + 2 <= 15 ? 4 : 8;
-  // posteriors | check-node state | packed sign plane (+ 2 padding words, rounded)
-  d->smem = (size_t)((s.N + 15) & ~15) + (size_t)s.R * d->state_bytes + (size_t)(((s.N + 31) / 32 + 3) & ~1) * 4;
+  // shared memory: posteriors | packed sign plane (+ 2 padding words, rounded); check-node words are in global scratch
+  d->smem = (size_t)((s.N + 15) & ~15) + (size_t)(((s.N + 31) / 32 + 3) & ~1) * 4;
   LdpcParams& p = d->proto;
   memset(&p, 0, sizeof(p));
   p.N = s.N; p.K = s.K; p.q = s.q;
@@ -494,7 +512,12 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
   T2_CUDA(ctx, cudaMalloc(&d->d_level, level.size()));
   T2_CUDA(ctx, cudaMemcpy(d->d_level, level.data(), level.size(), cudaMemcpyHostToDevice));
   p.level = d->d_level;
-  T2_CUDA(ctx, occupancy_dispatch(d->cnl, d->smem, &d->blocks_per_sm));
+  d->minb = 2;
+  if (const char* e = getenv("T2B200_LDPC_MINB")) {          // development aid: pick the register-budget variant
+    const int v = atoi(e);
+    if (d->cnl <= 13 ? (v == 2 || v == 3) : (v == 1 || v == 2)) d->minb = v;
+  }
+  T2_CUDA(ctx, occupancy_dispatch(d->cnl, d->minb, d->smem, &d->blocks_per_sm));
   if (d->blocks_per_sm < 1) { ctx->err = "LDPC kernel does not fit on an SM"; return T2B200_ERR_CUDA; }
   ctx->ldpc[code] = d;
   *out = d;
@@ -556,7 +579,13 @@ static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, 
   } else {
     grid = std::min(capacity, n_cw);
   }
-  T2_CUDA(ctx, launch_dispatch(d->cnl, p, grid, d->smem, st));
+  {
+    // one row of check-node words per resident CTA; the kernel clears its row per codeword
+    void* cs; int rc;
+    if ((rc = t2_dev_scratch(ctx, 8, (size_t)capacity * d->s.R * d->state_bytes, &cs))) return rc;
+    p.cn_state = cs;
+  }
+  T2_CUDA(ctx, launch_dispatch(d->cnl, d->minb, p, grid, d->smem, st));
   ctx->launches++;
   return T2B200_OK;
 }
