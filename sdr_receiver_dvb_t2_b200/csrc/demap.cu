@@ -19,6 +19,7 @@
 #include "fec_tables.h"
 #include <algorithm>
 #include <cmath>
+#include <climits>
 
 struct TiPlp {
   int cells_per_fec = 0, n_fec_max = 0, rows = 0;
@@ -121,48 +122,142 @@ __global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockD
 
 // Pass 1b: sum_s / sum_e exactly as the reference accumulates them -- float, in cell order (the one
 // order-dependent reduction of the receiver; every LLR of the TI block is scaled by its result, so a
-// tree sum would flip ~0.1 % of the LLRs by one LSB).  One warp per TI block: the lanes stream the
-// terms through shared memory, lane 0 owns the two dependent FADD chains (~4 cycles per cell, ~1 ms
-// for the largest TI block, a few per cent of one SM at full LDPC throughput).
-template <int MOD>
-__global__ void demap_ordered_sum_kernel(const float2* __restrict__ terms, const DemapBlockDesc* __restrict__ blocks,
-                                         float* __restrict__ precision, float* __restrict__ snr,
-                                         const float* __restrict__ precision_in)
+// tree sum would flip ~0.1 % of the LLRs by one LSB).  The serial recurrence s <- fl(s + t_k) is evaluated
+// EXACTLY by a parallel scan: while s stays inside one binade [2^e, 2^(e+1)) it is an integer S (units of
+// ulp = 2^(e-23)) and round-to-nearest-even addition of t >= 0 is S += q + [f > 1/2] + [f == 1/2 and S + q odd]
+// with q = floor(t / ulp), f = frac(t / ulp): an integer recurrence whose only state besides S is its parity.
+// So every run of elements is a pair (delta if S starts even, delta if S starts odd), pairs compose
+// associatively, and one CTA scans 8192 elements per pass.  The (rare: ~40 per TI block) additions that carry
+// s into the next binade are found by the scan, executed as one real float addition, and the scan resumes
+// behind them.  tools/ordered_sum_model.py is the bit-level model this kernel follows.
+constexpr int kSumThreads = 512, kSumE = 16, kSumChunk = kSumThreads * kSumE;
+constexpr int kSumSat = 1 << 26;           // deltas saturate far above 2^24 (= "left the binade")
+
+struct SumPair { int a0, a1; };            // S + a0 if S is even on entry, S + a1 if odd
+__device__ __forceinline__ int sum_sat(int a, int b) { return min(a + b, kSumSat); }
+__device__ __forceinline__ SumPair sum_compose(SumPair x, SumPair y)     // x first, then y
 {
-  constexpr int CH = 256;
-  __shared__ float2 buf[2][CH];
+  SumPair r;
+  r.a0 = sum_sat(x.a0, (x.a0 & 1) ? y.a1 : y.a0);
+  r.a1 = sum_sat(x.a1, (x.a1 & 1) ? y.a0 : y.a1);
+  return r;
+}
+// q | [f > 1/2] << 30 | [f == 1/2] << 31 of term bits tb against the binade with exponent field es
+__device__ __forceinline__ uint32_t sum_elem(int es, uint32_t tb)
+{
+  if (tb == 0) return 0;
+  int et = (tb >> 23) & 0xff;
+  uint32_t mt = tb & 0x7fffffu;
+  if (et) mt |= 0x800000u; else et = 1;
+  const int sh = es - et;
+  if (sh < 0) return 1u << 24;              // t >= 2^(e+1): certainly leaves the binade
+  if (sh == 0) return mt;
+  if (sh > 24) return 0;                    // t < ulp / 2
+  const uint32_t q = mt >> sh, rem = mt & ((1u << sh) - 1u), half = 1u << (sh - 1);
+  return q | (rem > half ? 1u << 30 : 0u) | (rem == half ? 1u << 31 : 0u);
+}
+__device__ __forceinline__ int sum_apply(int S, uint32_t w)
+{
+  const int q = (int)(w & 0x1ffffffu);
+  return min(S + q + (int)((w >> 30) & 1u) + (int)((w >> 31) & (uint32_t)(S + q) & 1u), kSumSat);
+}
+
+template <int MOD>
+__global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const float2* __restrict__ terms,
+                                                                         const DemapBlockDesc* __restrict__ blocks,
+                                                                         float* __restrict__ precision, float* __restrict__ snr,
+                                                                         const float* __restrict__ precision_in)
+{
+  __shared__ SumPair wt[2][kSumThreads / 32];
+  __shared__ float sh_s[2];
+  __shared__ int sh_cross;
   const DemapBlockDesc b = blocks[blockIdx.x];
   const float2* t = terms + b.cell_off;
   const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;
-  const int lane = threadIdx.x;
-  float ss = 0.0f, se = 0.0f;
-  float2 r[CH / 32];
-  auto fetch = [&](int c0) {
-#pragma unroll
-    for (int j = 0; j < CH / 32; ++j) {
-      const int k = c0 + lane + 32 * j;
-      r[j] = k < n ? __ldg(t + k) : make_float2(0.0f, 0.0f);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { sh_s[0] = 0.0f; sh_s[1] = 0.0f; sh_cross = INT_MAX; }
+  __syncthreads();
+  int base = 0;
+  while (base < n) {
+    const float s0 = sh_s[0], s1 = sh_s[1];
+    const uint32_t b0 = __float_as_uint(s0), b1 = __float_as_uint(s1);
+    const int es0 = (b0 >> 23) & 0xff, es1 = (b1 >> 23) & 0xff;
+    if (es0 == 0 || es0 == 255 || es1 == 0 || es1 == 255) {       // zero / denormal / non-finite sum: one plain addition
+      __syncthreads();
+      if (tid == 0) { const float2 v = __ldg(t + base); sh_s[0] = __fadd_rn(s0, v.x); sh_s[1] = __fadd_rn(s1, v.y); }
+      __syncthreads();
+      ++base;
+      continue;
     }
-  };
-  fetch(0);
-  int pb = 0;
-  for (int c0 = 0; c0 < n; c0 += CH, pb ^= 1) {
+    const int S0 = (int)((b0 & 0x7fffffu) | 0x800000u), S1 = (int)((b1 & 0x7fffffu) | 0x800000u);
+    const int m = min(kSumChunk, n - base);
+    uint32_t w0[kSumE], w1[kSumE];
+    int x00 = 0, x01 = 1, x10 = 0, x11 = 1;                       // pseudo-S started even / odd, per sum
 #pragma unroll
-    for (int j = 0; j < CH / 32; ++j) buf[pb][lane + 32 * j] = r[j];
-    __syncwarp();
-    if (c0 + CH < n) fetch(c0 + CH);                      // in flight while lane 0 adds
-    if (lane == 0) {
-      const int m = min(CH, n - c0);
-      if (m == CH) {
-#pragma unroll 16
-        for (int i = 0; i < CH; ++i) { ss = __fadd_rn(ss, buf[pb][i].x); se = __fadd_rn(se, buf[pb][i].y); }
-      } else {
-        for (int i = 0; i < m; ++i) { ss = __fadd_rn(ss, buf[pb][i].x); se = __fadd_rn(se, buf[pb][i].y); }
+    for (int i = 0; i < kSumE; ++i) {
+      const int k = tid * kSumE + i;
+      float2 v = make_float2(0.0f, 0.0f);
+      if (k < m) v = __ldg(t + base + k);
+      w0[i] = sum_elem(es0, __float_as_uint(v.x));
+      w1[i] = sum_elem(es1, __float_as_uint(v.y));
+      x00 = sum_apply(x00, w0[i]); x01 = sum_apply(x01, w0[i]);
+      x10 = sum_apply(x10, w1[i]); x11 = sum_apply(x11, w1[i]);
+    }
+    SumPair p0 = {x00, x01 - 1}, p1 = {x10, x11 - 1};
+    // inclusive scan inside the warp, warp totals through shared memory
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      SumPair o0, o1;
+      o0.a0 = __shfl_up_sync(0xffffffffu, p0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, p0.a1, off);
+      o1.a0 = __shfl_up_sync(0xffffffffu, p1.a0, off); o1.a1 = __shfl_up_sync(0xffffffffu, p1.a1, off);
+      if (lane >= off) { p0 = sum_compose(o0, p0); p1 = sum_compose(o1, p1); }
+    }
+    if (lane == 31) { wt[0][warp] = p0; wt[1][warp] = p1; }
+    SumPair e0, e1;                                              // exclusive inside the warp
+    e0.a0 = __shfl_up_sync(0xffffffffu, p0.a0, 1); e0.a1 = __shfl_up_sync(0xffffffffu, p0.a1, 1);
+    e1.a0 = __shfl_up_sync(0xffffffffu, p1.a0, 1); e1.a1 = __shfl_up_sync(0xffffffffu, p1.a1, 1);
+    if (lane == 0) { e0.a0 = e0.a1 = 0; e1.a0 = e1.a1 = 0; }
+    __syncthreads();
+    SumPair q0 = {0, 0}, q1 = {0, 0};
+    for (int wi = 0; wi < warp; ++wi) { q0 = sum_compose(q0, wt[0][wi]); q1 = sum_compose(q1, wt[1][wi]); }
+    q0 = sum_compose(q0, e0); q1 = sum_compose(q1, e1);
+    int Sa = sum_sat(S0, (S0 & 1) ? q0.a1 : q0.a0), Sb = sum_sat(S1, (S1 & 1) ? q1.a1 : q1.a0);
+    // walk the thread's elements with the true S: find the first addition that leaves a binade
+    int my_cross = INT_MAX, Sa_before = Sa, Sb_before = Sb;
+    if (Sa >= (1 << 24) || Sb >= (1 << 24)) my_cross = tid * kSumE;   // happened in an earlier thread (never the minimum)
+    else {
+#pragma unroll
+      for (int i = 0; i < kSumE; ++i) {
+        if (my_cross == INT_MAX && tid * kSumE + i < m) {
+          const int na = sum_apply(Sa, w0[i]), nb = sum_apply(Sb, w1[i]);
+          if (na >= (1 << 24) || nb >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; Sb_before = Sb; }
+          else { Sa = na; Sb = nb; }
+        }
       }
     }
-    __syncwarp();
+    if (my_cross != INT_MAX) atomicMin(&sh_cross, my_cross);
+    __syncthreads();
+    const int cross = sh_cross;
+    if (cross == INT_MAX) {
+      if (tid == (m - 1) / kSumE) {                              // owner of the last element holds the totals
+        sh_s[0] = __uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa & 0x7fffffu));
+        sh_s[1] = __uint_as_float(((uint32_t)es1 << 23) | ((uint32_t)Sb & 0x7fffffu));
+      }
+      base += m;
+    } else {
+      if (my_cross == cross && tid == cross / kSumE) {           // the crossing addition itself, in real float arithmetic
+        const float2 v = __ldg(t + base + cross);
+        sh_s[0] = __fadd_rn(__uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa_before & 0x7fffffu)), v.x);
+        sh_s[1] = __fadd_rn(__uint_as_float(((uint32_t)es1 << 23) | ((uint32_t)Sb_before & 0x7fffffu)), v.y);
+      }
+      base += cross + 1;
+    }
+    __syncthreads();
+    if (tid == 0) sh_cross = INT_MAX;
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (tid == 0) {
+    const float ss = sh_s[0], se = sh_s[1];
     const float a8 = __fmul_rn(8.0f, kNorm[MOD]);
     float p = __fdiv_rn(__fmul_rn(a8, ss), se);            // 8.0f * NORM * sum_s / sum_e, left to right
     if (precision_in) p = precision_in[blockIdx.x];
@@ -344,7 +439,7 @@ static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* 
   const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
   demap_stats_kernel<MOD><<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, (float2*)d_terms, rotation != 0, rc, rs);
   T2_CUDA(ctx, cudaGetLastError());
-  demap_ordered_sum_kernel<MOD><<<n_blocks, 32, 0, ctx->stream>>>((const float2*)d_terms, d_desc, d_prec, d_snr, d_prec_in);
+  demap_ordered_sum_kernel<MOD><<<n_blocks, kSumThreads, 0, ctx->stream>>>((const float2*)d_terms, d_desc, d_prec, d_snr, d_prec_in);
   T2_CUDA(ctx, cudaGetLastError());
   auto k = ctx->opt_demap_saturate ? demap_llr_kernel<MOD, true> : demap_llr_kernel<MOD, false>;
   const size_t smem = (size_t)((fec_bits + 15) & ~15);

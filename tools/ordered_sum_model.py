@@ -1,0 +1,79 @@
+"""Bit-level model of the exact parallel evaluation of the float recurrence s <- fl(s + t_k), t_k >= 0, used by
+demap_ordered_sum_kernel (sdr_receiver_dvb_t2_b200/csrc/demap.cu): run it to check the algorithm against a serial sum."""
+import numpy as np
+BIG=1<<26
+def elem(Es, tb):
+    if tb==0: return 0,0,0
+    Et=(tb>>23)&0xff; mt=(tb&0x7fffff)|(0x800000 if Et else 0)
+    if Et==0: Et=1
+    sh=Es-Et
+    if sh<0: return 1<<24,0,0
+    if sh==0: return mt,0,0
+    if sh<=24:
+        q=mt>>sh; rem=mt&((1<<sh)-1); half=1<<(sh-1)
+        return q,int(rem>half),int(rem==half)
+    return 0,0,0
+def sat(x): return min(x,BIG)
+def compose(A,B):  # A first
+    return [sat(A[p]+B[p^(A[p]&1)]) for p in (0,1)]
+def fbits(x): return int(np.float32(x).view(np.uint32))
+def frombits(b): return np.uint32(b).view(np.float32)
+def ordered_sum(t, CH=64, E=4):
+    n=len(t); s=np.float32(0); base=0; passes=0
+    while base<n:
+        sb=fbits(s); Es=(sb>>23)&0xff
+        if Es==0:   # zero/denormal: serial step
+            s=np.float32(s+t[base]); base+=1; continue
+        S0=(sb&0x7fffff)|0x800000
+        m=min(CH,n-base); passes+=1
+        nt=(m+E-1)//E
+        el=[elem(Es,fbits(t[base+k])) for k in range(m)]
+        loc=[]
+        for th in range(nt):
+            A=[0,0]
+            for k in range(th*E,min(m,th*E+E)):
+                q,gt,tie=el[k]
+                for v in (0,1):
+                    cp=v^(A[v]&1)
+                    A[v]=sat(A[v]+q+gt+(tie&((cp+q)&1)))
+            loc.append(A)
+        # exclusive scan
+        pref=[[0,0]]
+        for th in range(nt-1): pref.append(compose(pref[-1],loc[th]))
+        cross=None; Send=None
+        for th in range(nt):
+            S=S0+pref[th][S0&1]
+            if S>=1<<24:
+                cross=th*E if cross is None else cross; break
+            done=False
+            for k in range(th*E,min(m,th*E+E)):
+                q,gt,tie=el[k]
+                Sn=S+q+gt+(tie&((S+q)&1))
+                if Sn>=1<<24:
+                    cross=(k,S); done=True; break
+                S=Sn
+            if done: break
+            Send=S
+        if cross is None:
+            s=frombits((Es<<23)|(Send&0x7fffff)); base+=m
+        else:
+            k,Sb=cross
+            sbf=frombits((Es<<23)|(Sb&0x7fffff))
+            s=np.float32(sbf+t[base+k]); base+=k+1
+    return s,passes
+rng=np.random.default_rng(1)
+def serial(t):
+    s=np.float32(0)
+    for x in t: s=np.float32(s+x)
+    return s
+for trial in range(300):
+    n=int(rng.integers(1,3000))
+    kind=trial%5
+    if kind==0: t=(rng.standard_normal(n)**2).astype(np.float32)
+    elif kind==1: t=(rng.integers(0,64,n)/np.float32(8)).astype(np.float32)      # many ties
+    elif kind==2: t=(rng.integers(0,4,n)*np.float32(2.0**-int(rng.integers(0,30)))).astype(np.float32)
+    elif kind==3: t=(10.0**rng.uniform(-12,6,n)).astype(np.float32)
+    else: t=np.where(rng.random(n)<0.3,0,rng.integers(1,5,n)*np.float32(0.5)).astype(np.float32); t[rng.integers(0,n)]=np.float32(3e7)
+    a=serial(t); b,p=ordered_sum(t)
+    assert fbits(a)==fbits(b),(trial,kind,n,a,b)
+print('model ok')
