@@ -130,7 +130,8 @@ __global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockD
 // associatively, and one CTA scans 8192 elements per pass.  The (rare: ~40 per TI block) additions that carry
 // s into the next binade are found by the scan, executed as one real float addition, and the scan resumes
 // behind them.  tools/ordered_sum_model.py is the bit-level model this kernel follows.
-constexpr int kSumThreads = 512, kSumE = 16, kSumChunk = kSumThreads * kSumE;
+constexpr int kSumThreads = 1024, kSumE = 8, kSumChunk = kSumThreads * kSumE;
+constexpr int kSumSerialHead = 768;        // the sums double every few cells at first: no point scanning there
 constexpr int kSumSat = 1 << 26;           // deltas saturate far above 2^24 (= "left the binade")
 
 struct SumPair { int a0, a1; };            // S + a0 if S is even on entry, S + a1 if odd
@@ -168,16 +169,20 @@ __global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const fl
                                                                          float* __restrict__ precision, float* __restrict__ snr,
                                                                          const float* __restrict__ precision_in)
 {
-  __shared__ SumPair wt[2][kSumThreads / 32];
+  __shared__ SumPair wt[2][kSumThreads / 32];      // warp totals, then their exclusive scan
   __shared__ float sh_s[2];
   __shared__ int sh_cross;
   const DemapBlockDesc b = blocks[blockIdx.x];
   const float2* t = terms + b.cell_off;
   const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { sh_s[0] = 0.0f; sh_s[1] = 0.0f; sh_cross = INT_MAX; }
+  int base = min(n, kSumSerialHead);
+  if (tid == 0) {
+    float a = 0.0f, c = 0.0f;
+    for (int k = 0; k < base; ++k) { const float2 v = __ldg(t + k); a = __fadd_rn(a, v.x); c = __fadd_rn(c, v.y); }
+    sh_s[0] = a; sh_s[1] = c; sh_cross = INT_MAX;
+  }
   __syncthreads();
-  int base = 0;
   while (base < n) {
     const float s0 = sh_s[0], s1 = sh_s[1];
     const uint32_t b0 = __float_as_uint(s0), b1 = __float_as_uint(s1);
@@ -218,9 +223,23 @@ __global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const fl
     e1.a0 = __shfl_up_sync(0xffffffffu, p1.a0, 1); e1.a1 = __shfl_up_sync(0xffffffffu, p1.a1, 1);
     if (lane == 0) { e0.a0 = e0.a1 = 0; e1.a0 = e1.a1 = 0; }
     __syncthreads();
-    SumPair q0 = {0, 0}, q1 = {0, 0};
-    for (int wi = 0; wi < warp; ++wi) { q0 = sum_compose(q0, wt[0][wi]); q1 = sum_compose(q1, wt[1][wi]); }
-    q0 = sum_compose(q0, e0); q1 = sum_compose(q1, e1);
+    if (warp == 0) {                                             // exclusive scan of the warp totals
+      SumPair t0 = wt[0][lane], t1 = wt[1][lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        SumPair o0, o1;
+        o0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, off);
+        o1.a0 = __shfl_up_sync(0xffffffffu, t1.a0, off); o1.a1 = __shfl_up_sync(0xffffffffu, t1.a1, off);
+        if (lane >= off) { t0 = sum_compose(o0, t0); t1 = sum_compose(o1, t1); }
+      }
+      SumPair x0, x1;
+      x0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, 1); x0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, 1);
+      x1.a0 = __shfl_up_sync(0xffffffffu, t1.a0, 1); x1.a1 = __shfl_up_sync(0xffffffffu, t1.a1, 1);
+      if (lane == 0) { x0.a0 = x0.a1 = 0; x1.a0 = x1.a1 = 0; }
+      wt[0][lane] = x0; wt[1][lane] = x1;
+    }
+    __syncthreads();
+    const SumPair q0 = sum_compose(wt[0][warp], e0), q1 = sum_compose(wt[1][warp], e1);
     int Sa = sum_sat(S0, (S0 & 1) ? q0.a1 : q0.a0), Sb = sum_sat(S1, (S1 & 1) ? q1.a1 : q1.a0);
     // walk the thread's elements with the true S: find the first addition that leaves a binade
     int my_cross = INT_MAX, Sa_before = Sa, Sb_before = Sb;

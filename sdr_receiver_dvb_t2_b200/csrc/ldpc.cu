@@ -39,149 +39,222 @@ constexpr int kMaxLayers = 90;         // q of the rate-1/2 normal code
 constexpr int kMaxEdgeWords = 648;     // max q * CNL over all codes (rate 3/5 normal: 72 * 9)
 
 // Passed by value: the whole schedule lives in the kernel-parameter constant bank, so the per-layer
-// (base, shift) pairs are fetched through the uniform datapath, not through the LSU.
+// (group base, shift) pairs are fetched through the constant path, not through the LSU.
 struct LdpcParams {
   const int8_t* llr; uint8_t* bits; int32_t* trials_left; int32_t* iters; int8_t* post_out;
   const uint8_t* level; const uint8_t* prbs; unsigned* gsync;
-  void* cn_state;                     // [grid][R] packed check-node words (L2-resident scratch, thread-private)
+  uint32_t* cn_state;                 // [grid][NS][R] packed check-node words (L2-resident scratch, thread-private)
   int n_cw, group_lanes, max_trials; unsigned flags;
   int N, K, q, k_out;
-  // CN (i,j) data edge c reads posterior 360*g + (j + shift) mod 360 = j + ea - (j >= et ? 360 : 0)
-  uint16_t ea[kMaxEdgeWords];         // [q][CNL]: 360*g + shift
-  uint16_t et[kMaxEdgeWords];         // [q][CNL]: 360 - shift
+  // CN (i,j) data edge c reads posterior eb + (j + es) mod 360
+  uint16_t eb[kMaxEdgeWords];         // [q][CNL]: 360 * bit-group
+  uint16_t es[kMaxEdgeWords];         // [q][CNL]: cyclic shift
   uint32_t shared[kMaxLayers];        // per layer: data-edge slots whose bit another CN of the layer also uses
   int16_t cidx[kMaxLayers];           // row of level[] for layers with shared bits
   uint8_t cnt[kMaxLayers], nlev[kMaxLayers];
 };
 static_assert(sizeof(LdpcParams) <= 4000, "kernel parameter block");
 
-template <typename ST> struct StateCodec;
-template <> struct StateCodec<uint32_t> {       // <= 15 slots: signs[0,15) idx[15,20) m0[20,26) m1[26,32)
-  static __device__ __forceinline__ void unpack(uint32_t w, uint32_t& sg, int& idx, int& m0, int& m1) {
-    sg = w & 0x7fffu; idx = (w >> 15) & 31; m0 = (w >> 20) & 63; m1 = w >> 26;
-  }
-  static __device__ __forceinline__ uint32_t pack(uint32_t sg, int idx, int m0, int m1) {
-    return sg | ((uint32_t)idx << 15) | ((uint32_t)m0 << 20) | ((uint32_t)m1 << 26);
-  }
-};
-template <> struct StateCodec<uint64_t> {       // <= 32 slots: signs in the low word
-  static __device__ __forceinline__ void unpack(uint64_t w, uint32_t& sg, int& idx, int& m0, int& m1) {
-    sg = (uint32_t)w; uint32_t h = (uint32_t)(w >> 32); idx = h & 31; m0 = (h >> 8) & 63; m1 = (h >> 16) & 63;
-  }
-  static __device__ __forceinline__ uint64_t pack(uint32_t sg, int idx, int m0, int m1) {
-    return (uint64_t)sg | ((uint64_t)((uint32_t)idx | ((uint32_t)m0 << 8) | ((uint32_t)m1 << 16)) << 32);
-  }
+// Check-node word layout.  The min-sum messages of a check node are fully determined by (m0, m1, arg-min slot,
+// output signs): message of slot c = sign_c * (c == arg-min ? m1 : m0).  They are kept as one 2-bit code per slot
+// (bit 0: sign negative, bit 1: slot is the arg-min), one code per NIBBLE, so that a single PRMT (byte permute)
+// looks the messages of four slots up in a 4-entry byte table {+m0, -m0, +m1, -m1} and a second PRMT extracts one
+// of them sign-extended: 1.25 ALU instructions per edge instead of a compare/select ladder.
+template <int CNL> struct CnLayout {
+  static constexpr int SLOTS = CNL + 2;
+  static constexpr int NW = (SLOTS + 7) / 8;                 // code words, 8 nibbles each
+  static constexpr int TAIL = SLOTS - 8 * (NW - 1);          // nibbles in use in the last code word
+  static constexpr bool MPACK = TAIL <= 5;                   // m0 | m1 (6 + 6 bits) share the last code word
+  static constexpr int NS = NW + (MPACK ? 0 : 1);            // 32-bit words per check node
 };
 
 // min/max through PTX so that the optimiser cannot range-narrow the int8-valued data into packed
 // 16-bit lanes (it then spends more PRMT pack/unpack instructions than it saves)
 __device__ __forceinline__ int smin(int a, int b) { int r; asm("min.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ int smax(int a, int b) { int r; asm("max.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// byte i of x, sign-extended (PRMT with the sign-replicate selector mode)
+template <int I> __device__ __forceinline__ int sext_byte(uint32_t x)
+{
+  return (int)__byte_perm(x, 0u, (uint32_t)(I | ((8 | I) << 4) | ((8 | I) << 8) | ((8 | I) << 12)));
+}
+__device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
+{
+  return ((uint32_t)b0 & 0xffu) | (((uint32_t)b1 & 0xffu) << 8) | (((uint32_t)b2 & 0xffu) << 16) | ((uint32_t)b3 << 24);
+}
 
 enum SlotMode { ALL_SLOTS, PREDICATED, BRANCHED };
+constexpr int kKeyIdle = 1 << 20;
 
 // One check node (LDPC/layered_decoder.hh:87-107 + algorithms.hh:250-291), split so that the edges
 // of a layer that are private to the check node and the edges it shares with another check node of
 // the same layer can be read / written at different times.
-template <int CNL, typename ST>
+template <int CNL>
 struct CheckNode {
-  static constexpr int SLOTS = CNL + 2;
+  using LY = CnLayout<CNL>;
+  static constexpr int SLOTS = LY::SLOTS, NW = LY::NW, NG = (SLOTS + 3) / 4;
   int inp[SLOTS], adr[SLOTS];
   int key0, key1, sx;
-  // minus the stored message of the previous iteration (clamp(out,-32,31)), by sign and by "is arg-min"
-  int nb_neg0, nb_pos0, nb_neg1, nb_pos1, idx;
-  uint32_t sg, nsg;
+  uint32_t tin;             // bytes {-clamp(+m0), -clamp(-m0), -clamp(+m1), -clamp(-m1)} of the PREVIOUS iteration:
+                            // minus the stored message (clamped to [-32, 31]) by code
+  uint32_t cw[NW];          // previous iteration's codes
+  uint32_t nin[NG];         // minus stored message of slots 4g .. 4g+3, one byte each
+  uint32_t ncw[NW];         // codes being built for this iteration
   int8_t* post;
 
-  __device__ __forceinline__ void begin(int8_t* post_, ST w) {
+  __device__ __forceinline__ void begin(int8_t* post_, const uint32_t (&w)[LY::NS]) {
     post = post_;
-    int m0c, m1c;
-    StateCodec<ST>::unpack(w, sg, idx, m0c, m1c);
-    nb_neg0 = m0c; nb_pos0 = -smin(m0c, 31); nb_neg1 = m1c; nb_pos1 = -smin(m1c, 31);
-    key0 = 1 << 20; key1 = 1 << 20; sx = 0; nsg = 0;
+    const uint32_t mw = w[LY::NS - 1];
+    const int m0c = LY::MPACK ? (int)((mw >> 20) & 63u) : (int)(mw & 63u);
+    const int m1c = LY::MPACK ? (int)(mw >> 26) : (int)((mw >> 6) & 63u);
+    tin = pack4(-smin(m0c, 31), m0c, -smin(m1c, 31), m1c);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { cw[k] = w[k]; ncw[k] = 0; }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) nin[g] = __byte_perm(tin, 0u, (g & 1) ? (cw[g >> 1] >> 16) : cw[g >> 1]);
+    key0 = kKeyIdle; key1 = kKeyIdle; sx = 0;
   }
-  __device__ __forceinline__ void edge_in(int slot, int a, bool active) {
+  template <int SLOT> __device__ __forceinline__ int stored_neg() const { return sext_byte<SLOT & 3>(nin[SLOT >> 2]); }
+  // the same for a run-time slot number (shared-edge fast path)
+  __device__ __forceinline__ int stored_neg_rt(int slot) const {
+    uint32_t w = cw[0];
+#pragma unroll
+    for (int k = 1; k < NW; ++k) if ((slot >> 3) == k) w = cw[k];
+    const uint32_t code = (w >> (4 * (slot & 7))) & 3u;
+    return (int)(int8_t)(tin >> (8 * code));
+  }
+  template <int SLOT> __device__ __forceinline__ void edge_in(int a, bool active) {
     const int pv = post[a];
-    const bool neg = (sg >> slot) & 1u;
-    int nbl = neg ? nb_neg0 : nb_pos0;
-    if (slot == idx) nbl = neg ? nb_neg1 : nb_pos1;
-    const int v = smax(__viaddmin_s32(pv, nbl, 127), -128);   // vqsub(posterior, stored message)
-    const int mag = __viaddmin_s32_relu(abs(v), -1, 126);     // vqabs, then unsigned vqsub of beta = 1
-    int key = mag * 32 + slot;
-    if (!active) key = 1 << 20;
-    if (active) { inp[slot] = v; adr[slot] = a; }
+    const int v = smax(__viaddmin_s32(pv, stored_neg<SLOT>(), 127), -128);   // vqsub(posterior, stored message)
+    // vqabs + unsigned vqsub of beta = 1 are monotone, so they are applied to the two minima only (store());
+    // key = (|v| - 1) * 32 + slot orders the edges the same way
+    int key = abs(v) * 32 + (SLOT - 32);
+    if (!active) key = kKeyIdle;
+    if (active) { inp[SLOT] = v; adr[SLOT] = a; }
     key1 = smin(key1, smax(key0, key));
     key0 = smin(key0, key);
     sx ^= active ? v : 0;
   }
-  __device__ __forceinline__ void edge_out(int slot, int m0, int m1, int idn, bool active) {
-    const int v = inp[slot];
-    const bool neg = ((sx ^ v) < 0);                          // sign of the product of the other links
-    int o = neg ? -m0 : m0;                                   // other(mags[i], mins[0], mins[1]) with that sign
-    if (slot == idn) o = neg ? -m1 : m1;
-    if (active) post[adr[slot]] = (int8_t)smax(__viaddmin_s32(v, o, 127), -128);   // vqadd
-    if (neg && active) nsg |= 1u << slot;
+  // m0 / m1 / arg-min of everything seen so far
+  __device__ __forceinline__ void minima(int& m0, int& m1, int& idn) const {
+    m0 = smin(smax(key0 >> 5, 0), 126); m1 = smin(smax(key1 >> 5, 0), 126); idn = key0 & 31;
+  }
+  template <int SLOT> __device__ __forceinline__ void mark_sign(bool active) {
+    if (active && ((sx ^ inp[SLOT]) < 0)) ncw[SLOT >> 3] |= 1u << (4 * (SLOT & 7));   // sign of the product of the other links
   }
   // Data slots: ALL_SLOTS  - every c < CNL is an edge (regular layer, nothing shared);
   //             PREDICATED - slot c takes part iff c < cnt and bit c of mask; inactive slots are
   //                          computed and discarded so the loads still issue back to back;
   //             BRANCHED   - same condition by (warp-uniform) branches: few active slots.
-  template <SlotMode MODE>
-  __device__ __forceinline__ void load(const uint16_t* ea, const uint16_t* et, int cnt, uint32_t mask,
-                                       bool with_parity, int i, int j, int K, int q) {
-#pragma unroll
-    for (int c = 0; c < CNL; ++c) {
-      const bool on = MODE == ALL_SLOTS ? true : (c < cnt && ((mask >> c) & 1u));
-      if (MODE == BRANCHED && !on) continue;
-      int a = j + (int)ea[c];
-      if (j >= (int)et[c]) a -= 360;
-      edge_in(c, a, on);
-    }
-    if (with_parity) {
-      edge_in(CNL, K + 360 * i + j, true);
-      const bool hasB = (i | j) != 0;
-      edge_in(CNL + 1, i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + (hasB ? j - 1 : 0), hasB);
+  template <SlotMode MODE, int C>
+  __device__ __forceinline__ void load_from(const uint16_t* eb, const uint16_t* es, int cnt, uint32_t mask, int j) {
+    if constexpr (C < CNL) {
+      const bool on = MODE == ALL_SLOTS ? true : (C < cnt && ((mask >> C) & 1u));
+      if (!(MODE == BRANCHED && !on)) {
+        const unsigned t = (unsigned)j + (unsigned)es[C];
+        const int a = (int)__viaddmin_u32(t, 0xfffffe98u, t) + (int)eb[C];      // eb + (j + es) mod 360
+        edge_in<C>(a, on);
+      }
+      load_from<MODE, C + 1>(eb, es, cnt, mask, j);
     }
   }
   template <SlotMode MODE>
-  __device__ __forceinline__ void store(int cnt, uint32_t mask, bool with_parity, int i, int j) {
-    const int m0 = key0 >> 5, idn = key0 & 31, m1 = key1 >> 5;
-#pragma unroll
-    for (int c = 0; c < CNL; ++c) {
-      const bool on = MODE == ALL_SLOTS ? true : (c < cnt && ((mask >> c) & 1u));
-      if (MODE == BRANCHED && !on) continue;
-      edge_out(c, m0, m1, idn, on);
-    }
+  __device__ __forceinline__ void load(const uint16_t* eb, const uint16_t* es, int cnt, uint32_t mask,
+                                       bool with_parity, int i, int j, int K, int q) {
+    load_from<MODE, 0>(eb, es, cnt, mask, j);
     if (with_parity) {
-      edge_out(CNL, m0, m1, idn, true);
-      edge_out(CNL + 1, m0, m1, idn, (i | j) != 0);
+      edge_in<CNL>(K + 360 * i + j, true);
+      const bool hasB = (i | j) != 0;
+      edge_in<CNL + 1>(i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + (hasB ? j - 1 : 0), hasB);
     }
+  }
+  template <SlotMode MODE, int C>
+  __device__ __forceinline__ void sign_from(int cnt, uint32_t mask) {
+    if constexpr (C < CNL) {
+      const bool on = MODE == ALL_SLOTS ? true : (C < cnt && ((mask >> C) & 1u));
+      if (!(MODE == BRANCHED && !on)) mark_sign<C>(on);
+      sign_from<MODE, C + 1>(cnt, mask);
+    }
+  }
+  template <int SLOT> __device__ __forceinline__ void edge_out(const uint32_t (&nout)[NG], bool active) {
+    const int o = sext_byte<SLOT & 3>(nout[SLOT >> 2]);       // other(mags[i], mins[0], mins[1]) with the sign
+    if (active) post[adr[SLOT]] = (int8_t)smax(__viaddmin_s32(inp[SLOT], o, 127), -128);   // vqadd
+  }
+  template <SlotMode MODE, int C>
+  __device__ __forceinline__ void out_from(const uint32_t (&nout)[NG], int cnt, uint32_t mask) {
+    if constexpr (C < CNL) {
+      const bool on = MODE == ALL_SLOTS ? true : (C < cnt && ((mask >> C) & 1u));
+      if (!(MODE == BRANCHED && !on)) edge_out<C>(nout, on);
+      out_from<MODE, C + 1>(nout, cnt, mask);
+    }
+  }
+  // sign codes of the shared slots resolved earlier (run-time slot numbers), merged with compile-time shifts
+  template <int C> __device__ __forceinline__ void merge_shared(uint32_t shared_neg) {
+    if constexpr (C < CNL) {
+      if ((shared_neg >> C) & 1u) ncw[C >> 3] |= 1u << (4 * (C & 7));
+      merge_shared<C + 1>(shared_neg);
+    }
+  }
+  // Write the private edges back and finish the check-node word.  shared_neg: bit c set when shared slot c
+  // (already written by shared_out) carried a negative output sign.
+  template <SlotMode MODE>
+  __device__ __forceinline__ void store(int cnt, uint32_t mask, int i, int j, uint32_t shared_neg, uint32_t (&w)[LY::NS]) {
+    int m0, m1, idn;
+    minima(m0, m1, idn);
+    sign_from<MODE, 0>(cnt, mask);
+    mark_sign<CNL>(true);
+    mark_sign<CNL + 1>((i | j) != 0);
+    if (MODE != ALL_SLOTS) merge_shared<0>(shared_neg);
+    {
+      const uint32_t bit = 2u << (4 * (idn & 7));
+#pragma unroll
+      for (int k = 0; k < NW; ++k) if ((idn >> 3) == k) ncw[k] |= bit;
+    }
+    const uint32_t tout = pack4(m0, -m0, m1, -m1);
+    uint32_t nout[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) nout[g] = __byte_perm(tout, 0u, (g & 1) ? (ncw[g >> 1] >> 16) : ncw[g >> 1]);
+    out_from<MODE, 0>(nout, cnt, mask);
+    edge_out<CNL>(nout, true);
+    edge_out<CNL + 1>(nout, (i | j) != 0);
+    const uint32_t mm = (uint32_t)smin(m0, 32) | ((uint32_t)smin(m1, 32) << 6);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) w[k] = ncw[k];
+    if (LY::MPACK) w[NW - 1] |= mm << 20; else w[LY::NS - 1] = mm;
   }
   // ---- shared-edge fast path: the slot number is a run-time (warp-uniform) value ----
-  // minus the stored message for `slot`: everything that does not depend on the posterior
-  __device__ __forceinline__ int stored_neg(int slot) const {
-    const bool neg = (sg >> slot) & 1u;
-    int nbl = neg ? nb_neg0 : nb_pos0;
-    if (slot == idx) nbl = neg ? nb_neg1 : nb_pos1;
-    return nbl;
-  }
   __device__ __forceinline__ int shared_in(int slot, int a, int nbl) {
     const int v = smax(__viaddmin_s32((int)post[a], nbl, 127), -128);
-    const int key = __viaddmin_s32_relu(abs(v), -1, 126) * 32 + slot;
+    const int key = abs(v) * 32 + (slot - 32);
     key1 = smin(key1, smax(key0, key));
     key0 = smin(key0, key);
     sx ^= v;
     return v;
   }
-  __device__ __forceinline__ void shared_out(int slot, int a, int v, int m0, int m1, int idn) {
+  // returns 1 when the output sign is negative
+  __device__ __forceinline__ uint32_t shared_out(int slot, int a, int v, int m0, int m1, int idn) {
     const bool neg = ((sx ^ v) < 0);
     int o = neg ? -m0 : m0;
     if (slot == idn) o = neg ? -m1 : m1;
     post[a] = (int8_t)smax(__viaddmin_s32(v, o, 127), -128);
-    if (neg) nsg |= 1u << slot;
+    return neg ? 1u : 0u;
   }
-  __device__ __forceinline__ ST finish() const {
-    return StateCodec<ST>::pack(nsg, key0 & 31, smin(key0 >> 5, 32), smin(key1 >> 5, 32));
+  // generic (BRANCHED) shared slots: load / write slot C if it is in `mask`
+  template <int C> __device__ __forceinline__ void shared_load_generic(const uint16_t* eb, const uint16_t* es, uint32_t mask, int j) {
+    if constexpr (C < CNL) {
+      if ((mask >> C) & 1u) {
+        const unsigned t = (unsigned)j + (unsigned)es[C];
+        const int a = (int)__viaddmin_u32(t, 0xfffffe98u, t) + (int)eb[C];
+        edge_in<C>(a, true);
+      }
+      shared_load_generic<C + 1>(eb, es, mask, j);
+    }
+  }
+  template <int C> __device__ __forceinline__ uint32_t shared_store_generic(uint32_t mask, int m0, int m1, int idn) {
+    if constexpr (C < CNL) {
+      uint32_t r = 0;
+      if ((mask >> C) & 1u) r = shared_out(C, adr[C], inp[C], m0, m1, idn) << C;
+      return r | shared_store_generic<C + 1>(mask, m0, m1, idn);
+    } else return 0u;
   }
 };
 
