@@ -75,7 +75,10 @@ __device__ __forceinline__ int smax(int a, int b) { int r; asm("max.s32 %0, %1, 
 // byte i of x, sign-extended (PRMT with the sign-replicate selector mode)
 template <int I> __device__ __forceinline__ int sext_byte(uint32_t x)
 {
-  return (int)__byte_perm(x, 0u, (uint32_t)(I | ((8 | I) << 4) | ((8 | I) << 8) | ((8 | I) << 12)));
+  // (__byte_perm masks bit 3 of the selector nibbles; the PTX instruction has the sign-replicate mode)
+  int r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "n"(I | ((8 | I) << 4) | ((8 | I) << 8) | ((8 | I) << 12)));
+  return r;
 }
 __device__ __forceinline__ uint32_t pack4(int b0, int b1, int b2, int b3)
 {
@@ -116,10 +119,11 @@ struct CheckNode {
   template <int SLOT> __device__ __forceinline__ int stored_neg() const { return sext_byte<SLOT & 3>(nin[SLOT >> 2]); }
   // the same for a run-time slot number (shared-edge fast path)
   __device__ __forceinline__ int stored_neg_rt(int slot) const {
-    uint32_t w = cw[0];
+    // (selects between computed values, not between array elements: keeps cw[] in registers)
+    const int sh4 = 4 * (slot & 7);
+    uint32_t code = (cw[0] >> sh4) & 3u;
 #pragma unroll
-    for (int k = 1; k < NW; ++k) if ((slot >> 3) == k) w = cw[k];
-    const uint32_t code = (w >> (4 * (slot & 7))) & 3u;
+    for (int k = 1; k < NW; ++k) { const uint32_t ck = (cw[k] >> sh4) & 3u; code = (slot >> 3) == k ? ck : code; }
     return (int)(int8_t)(tin >> (8 * code));
   }
   template <int SLOT> __device__ __forceinline__ void edge_in(int a, bool active) {
@@ -207,7 +211,7 @@ struct CheckNode {
     {
       const uint32_t bit = 2u << (4 * (idn & 7));
 #pragma unroll
-      for (int k = 0; k < NW; ++k) if ((idn >> 3) == k) ncw[k] |= bit;
+      for (int k = 0; k < NW; ++k) ncw[k] |= (idn >> 3) == k ? bit : 0u;
     }
     const uint32_t tout = pack4(m0, -m0, m1, -m1);
     uint32_t nout[NG];
@@ -305,7 +309,7 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
 #pragma unroll
     for (int c = 0; c < CNL; ++c)
       if (c < cnt) {
-        const int sh = 360 - (int)p.et[i * CNL + c], base = (int)p.ea[i * CNL + c] - sh;
+        const int sh = (int)p.es[i * CNL + c], base = (int)p.eb[i * CNL + c];
         int o = 32 * w + sh;
         if (o >= 360) o -= 360;
         uint32_t r = bits32(hb, base + o);
@@ -330,17 +334,19 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
 
 // co-resident CTAs per SM the register budget is cut for (65536 / (384 * MINB) registers per thread)
 
-template <int CNL, typename ST, int MINB>
+template <int CNL, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
 {
+  using LY = CnLayout<CNL>;
+  constexpr int NS = LY::NS;
   extern __shared__ __align__(16) unsigned char smem[];
   int8_t* post = reinterpret_cast<int8_t*>(smem);
   uint32_t* hb = reinterpret_cast<uint32_t*>(smem + ((p.N + 15) & ~15));
   const int R = p.N - p.K;
   // Check-node words are private to the thread that owns check node (i, tid): they live in an L2-resident
-  // global scratch (ld/st.cg, next layer's word prefetched a layer ahead) so that shared memory only holds the
-  // posteriors and two or three codewords fit on one SM.
-  ST* state = reinterpret_cast<ST*>(p.cn_state) + (size_t)blockIdx.x * R;
+  // global scratch (ld/st.cg, next layer's words prefetched a layer ahead) so that shared memory only holds the
+  // posteriors and two codewords fit on one SM.  NS planes of R words per resident CTA.
+  uint32_t* state = p.cn_state + (size_t)blockIdx.x * NS * R;
   __shared__ int s_flag;
 
   const int tid = threadIdx.x;
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __gri
       int2* dst = reinterpret_cast<int2*>(post);
       for (int k = tid; k < p.N / 8; k += kThreads) dst[k] = __ldg(src + k);
       if (tid < 360)
-        for (int i = 0; i < p.q; ++i) __stcg(state + i * 360 + tid, (ST)0);
+        for (int k = 0; k < NS * p.q; ++k) __stcg(state + k * 360 + tid, 0u);
     }
     __syncthreads();
 
@@ -380,26 +386,34 @@ __global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __gri
       }
       if (!(group_bad && --trials >= 0)) break;
       // ---- one update() ----
-      ST w_next = tid < 360 ? __ldcg(state + tid) : (ST)0;
+      uint32_t w_next[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) w_next[k] = tid < 360 ? __ldcg(state + k * R + tid) : 0u;
       for (int i = 0; i < p.q; ++i) {
-        const ST w_cur = w_next;
-        if (tid < 360 && i + 1 < p.q) w_next = __ldcg(state + (i + 1) * 360 + tid);
+        uint32_t w_cur[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) w_cur[k] = w_next[k];
+        if (tid < 360 && i + 1 < p.q) {
+#pragma unroll
+          for (int k = 0; k < NS; ++k) w_next[k] = __ldcg(state + k * R + (i + 1) * 360 + tid);
+        }
         const int cnt = p.cnt[i];
         const int nl = p.nlev[i];
-        const uint16_t* ea = p.ea + i * CNL;
-        const uint16_t* et = p.et + i * CNL;
-        CheckNode<CNL, ST> cn;
+        const uint16_t* eb = p.eb + i * CNL;
+        const uint16_t* es = p.es + i * CNL;
+        CheckNode<CNL> cn;
         if (nl == 1) {
           if (tid < 360) {
             cn.begin(post, w_cur);
             if (cnt == CNL) {
-              cn.template load<ALL_SLOTS>(ea, et, cnt, ~0u, true, i, tid, p.K, p.q);
-              cn.template store<ALL_SLOTS>(cnt, ~0u, true, i, tid);
+              cn.template load<ALL_SLOTS>(eb, es, cnt, ~0u, true, i, tid, p.K, p.q);
+              cn.template store<ALL_SLOTS>(cnt, ~0u, i, tid, 0u, w_cur);
             } else {
-              cn.template load<PREDICATED>(ea, et, cnt, ~0u, true, i, tid, p.K, p.q);
-              cn.template store<PREDICATED>(cnt, ~0u, true, i, tid);
+              cn.template load<PREDICATED>(eb, es, cnt, ~0u, true, i, tid, p.K, p.q);
+              cn.template store<PREDICATED>(cnt, ~0u, i, tid, 0u, w_cur);
             }
-            __stcg(state + i * 360 + tid, cn.finish());
+#pragma unroll
+            for (int k = 0; k < NS; ++k) __stcg(state + k * R + i * 360 + tid, w_cur[k]);
           }
           __syncthreads();
         } else {
@@ -408,42 +422,48 @@ __global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __gri
           // shared edges are resolved level by level along the dependency chains.
           const uint32_t sh = p.shared[i];
           int mylev = 0;
+          uint32_t shared_neg = 0;
           if (tid < 360) {
             mylev = __ldg(p.level + (int)p.cidx[i] * 360 + tid);
             cn.begin(post, w_cur);
-            cn.template load<PREDICATED>(ea, et, cnt, ~sh, true, i, tid, p.K, p.q);
+            cn.template load<PREDICATED>(eb, es, cnt, ~sh, true, i, tid, p.K, p.q);
           }
           if (__popc(sh) == 2) {
             // one pair of shared edges (the common case): addresses and stored messages are prepared
             // up front so that a level is just load -> min/sign merge -> store on two posteriors
             const int cA = __ffs(sh) - 1, cB = 31 - __clz(sh);
-            int aA = tid + (int)ea[cA], aB = tid + (int)ea[cB];
-            if (tid >= (int)et[cA]) aA -= 360;
-            if (tid >= (int)et[cB]) aB -= 360;
+            const unsigned tA = (unsigned)tid + (unsigned)es[cA], tB = (unsigned)tid + (unsigned)es[cB];
+            int aA = (int)__viaddmin_u32(tA, 0xfffffe98u, tA) + (int)eb[cA];
+            int aB = (int)__viaddmin_u32(tB, 0xfffffe98u, tB) + (int)eb[cB];
+            int nA = 0, nB = 0;
             if (tid >= 360) { aA = 0; aB = 0; }
-            const int nA = cn.stored_neg(cA), nB = cn.stored_neg(cB);
+            else { nA = cn.stored_neg_rt(cA); nB = cn.stored_neg_rt(cB); }
             for (int l = 1; l <= nl; ++l) {
               if (mylev == l) {
                 const int vA = cn.shared_in(cA, aA, nA);
                 const int vB = cn.shared_in(cB, aB, nB);
-                const int m0 = cn.key0 >> 5, idn = cn.key0 & 31, m1 = cn.key1 >> 5;
-                cn.shared_out(cA, aA, vA, m0, m1, idn);
-                cn.shared_out(cB, aB, vB, m0, m1, idn);
+                int m0, m1, idn;
+                cn.minima(m0, m1, idn);
+                shared_neg |= cn.shared_out(cA, aA, vA, m0, m1, idn) << cA;
+                shared_neg |= cn.shared_out(cB, aB, vB, m0, m1, idn) << cB;
               }
               __syncthreads();
             }
           } else {
             for (int l = 1; l <= nl; ++l) {
               if (mylev == l) {
-                cn.template load<BRANCHED>(ea, et, cnt, sh, false, i, tid, p.K, p.q);
-                cn.template store<BRANCHED>(cnt, sh, false, i, tid);
+                cn.template shared_load_generic<0>(eb, es, sh, tid);
+                int m0, m1, idn;
+                cn.minima(m0, m1, idn);
+                shared_neg |= cn.template shared_store_generic<0>(sh, m0, m1, idn);
               }
               __syncthreads();
             }
           }
           if (tid < 360) {
-            cn.template store<PREDICATED>(cnt, ~sh, true, i, tid);
-            __stcg(state + i * 360 + tid, cn.finish());
+            cn.template store<PREDICATED>(cnt, ~sh, i, tid, shared_neg, w_cur);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) __stcg(state + k * R + i * 360 + tid, w_cur[k]);
           }
           __syncthreads();
         }
@@ -490,10 +510,10 @@ __global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __gri
   }
 }
 
-template <int CNL, typename ST, int MINB>
+template <int CNL, int MINB>
 cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
 {
-  auto k = ldpc_decode_kernel<CNL, ST, MINB>;
+  auto k = ldpc_decode_kernel<CNL, MINB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (p.group_lanes > 1) {     // lock-step lanes spin on each other: they must be co-resident
@@ -504,10 +524,10 @@ cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
   return cudaGetLastError();
 }
 
-template <int CNL, typename ST, int MINB>
+template <int CNL, int MINB>
 cudaError_t occupancy(size_t smem, int* blocks_per_sm)
 {
-  auto k = ldpc_decode_kernel<CNL, ST, MINB>;
+  auto k = ldpc_decode_kernel<CNL, MINB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, kThreads, smem);
@@ -535,12 +555,12 @@ const int kCnlBuckets[] = {4, 5, 7, 8, 9, 11, 12, 13, 16, 17, 20};
 
 cudaError_t launch_dispatch(int cnl, int minb, const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
 {
-#define CALL_L(C, T, B) launch<C, T, B>(p, grid, smem, st)
+#define CALL_L(C, T, B) launch<C, B>(p, grid, smem, st)
   DISPATCH(CALL_L)
 }
 cudaError_t occupancy_dispatch(int cnl, int minb, size_t smem, int* bps)
 {
-#define CALL_O(C, T, B) occupancy<C, T, B>(smem, bps)
+#define CALL_O(C, T, B) occupancy<C, B>(smem, bps)
   DISPATCH(CALL_O)
 }
 
@@ -568,7 +588,10 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
   if (!d->cnl || s.q > kMaxLayers || s.q * d->cnl > kMaxEdgeWords) {
     delete d; ctx->err = "LDPC code geometry not instantiated"; return T2B200_ERR_ARG;
   }
-  d->state_bytes = d->cnl + 2 <= 15 ? 4 : 8;
+  {
+    const int slots = d->cnl + 2, nw = (slots + 7) / 8, tail = slots - 8 * (nw - 1);
+    d->state_bytes = 4 * (size_t)(nw + (tail <= 5 ? 0 : 1));       // CnLayout<CNL>::NS words per check node
+  }
   // shared memory: posteriors | packed sign plane (+ 2 padding words, rounded); check-node words are in global scratch
   d->smem = (size_t)((s.N + 15) & ~15) + (size_t)(((s.N + 31) / 32 + 3) & ~1) * 4;
   LdpcParams& p = d->proto;
@@ -576,8 +599,10 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
   p.N = s.N; p.K = s.K; p.q = s.q;
   for (int i = 0; i < s.q; ++i) {
     for (int c = 0; c < s.cnl_max; ++c) {
-      p.ea[i * d->cnl + c] = (uint16_t)(s.edge[(size_t)i * s.cnl_max + c] & 0xffffu);
-      p.et[i * d->cnl + c] = (uint16_t)(s.edge[(size_t)i * s.cnl_max + c] >> 16);
+      const uint32_t e = s.edge[(size_t)i * s.cnl_max + c];
+      const int shift = e ? 360 - (int)(e >> 16) : 0;              // edge word: 360*g + shift | (360 - shift) << 16
+      p.es[i * d->cnl + c] = (uint16_t)shift;
+      p.eb[i * d->cnl + c] = (uint16_t)((e & 0xffffu) - shift);
     }
     p.shared[i] = s.shared[i]; p.cidx[i] = s.conflict_index[i]; p.cnt[i] = s.cnt[i]; p.nlev[i] = s.nlev[i];
   }
@@ -656,7 +681,7 @@ static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, 
     // one row of check-node words per resident CTA; the kernel clears its row per codeword
     void* cs; int rc;
     if ((rc = t2_dev_scratch(ctx, 8, (size_t)capacity * d->s.R * d->state_bytes, &cs))) return rc;
-    p.cn_state = cs;
+    p.cn_state = (uint32_t*)cs;
   }
   T2_CUDA(ctx, launch_dispatch(d->cnl, d->minb, p, grid, d->smem, st));
   ctx->launches++;
