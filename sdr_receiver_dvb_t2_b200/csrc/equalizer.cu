@@ -19,9 +19,11 @@
 // through the de-interleaver as 8-byte scattered stores that merge in L2.  Arithmetic is written with
 // explicit round-to-nearest intrinsics so no FMA contraction changes a bit relative to the CPU oracle.
 #include "ctx.h"
+#include <cuda_pipeline.h>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -31,9 +33,12 @@ enum { DATA_CARRIER = 1, P2CARRIER, P2PAPR_CARRIER, TRPAPR_CARRIER, SCATTERED_CA
 struct PlanPilot { uint16_t k; uint8_t second_half; uint8_t pad; float ref; float amp; };
 struct PlanHost {
   std::vector<PlanPilot> pilots;
+  std::vector<int> first;            // per pilot: index of the first data cell to its right
   std::vector<uint2> cells;          // x = k | left_pilot << 16 ; y = j | n << 8 | h << 16
 };
-struct PlanDev { PlanPilot* pilots = nullptr; uint2* cells = nullptr; int n_pilots = 0, n_cells = 0, n_first = 0, pad = 0; };
+struct PlanDev { PlanPilot* pilots = nullptr; uint2* cells = nullptr; int* first = nullptr; int* chunk_lo = nullptr; int* chunk_k = nullptr; int n_pilots = 0, n_cells = 0, n_first = 0, pad = 0; };
+// chunk_lo[c] = interval (left pilot) holding data cell c * kEqChunk; chunk_k[2c], [2c+1] = first / last carrier of chunk c
+// first[ip] = index in cells[] of the first data cell right of pilot ip (first[n_pilots - 1] = n_cells)
 
 }  // namespace
 
@@ -71,67 +76,150 @@ __device__ __forceinline__ float atan2_approx_dev(float y, float x)      // DSP/
 struct EqParams {
   const float2* freq; float2* out; float* sro; float* phase; const int* idx_symbol;
   const PlanDev* plans; const int* plan_even; const int* plan_odd;
-  const float* lut_sin; const float* lut_cos;
+  const float2* lut_cs;           // {cos, sin} of DSP/fast_math.h's tables, interleaved
   int fft_size, l_nulls, n_out, first_symbol, n_symbols_kind;
+  int n_symbols;                 // symbols in this launch
+  int split;                     // CTAs per symbol
+  long long in_stride, out_stride;   // float2 elements between consecutive symbols of the launch
 };
 
-__global__ void __launch_bounds__(512) equalize_kernel(const EqParams p)
+constexpr int kEqThreads = 256;
+constexpr int kEqChunk = 1024;          // data cells whose interpolated (angle, amplitude) are staged in shared memory
+constexpr int kEqSpan = 2 * kEqChunk;   // carriers of the spectrum staged next to them (pilots and reserved tones between the cells)
+constexpr int kEqU = kEqChunk / kEqThreads;
+constexpr int kEqSplitDefault = 8;             // CTAs sharing one symbol (chunks dealt round-robin): keeps few symbols in flight so that the
+                                        // scattered 8-byte stores of a symbol meet in L2 before their sectors are evicted
+
+// One CTA per symbol.  Pilots are estimated in parallel into shared memory.  The data cells are then handled in
+// chunks of 4096 (carrier order): phase A -- one THREAD per pilot interval runs the reference's repeated float
+// additions of the interpolation step ONCE per interval (the n-th cell carries n rounded adds; a chain is
+// serial, the ~45 chains of a chunk are not) and leaves (angle, amplitude) per cell in shared memory; phase B --
+// all threads equalise the chunk's cells independently, fully coalesced, and send them through the frequency
+// de-interleaver as 8-byte scattered stores that merge in L2.  The last thread forms the ordered pilot sums.
+__global__ void __launch_bounds__(kEqThreads) equalize_kernel(const EqParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int s = blockIdx.x;
-  const int idx = p.idx_symbol[s];
-  int rel = idx - p.first_symbol;
-  rel = min(max(rel, 0), p.n_symbols_kind - 1);
-  const PlanDev pl = p.plans[(idx & 1) ? p.plan_odd[rel] : p.plan_even[rel]];
-  float* ang = reinterpret_cast<float*>(smem_raw);
-  float* amp = ang + pl.n_pilots;
-  float2* est = reinterpret_cast<float2*>(amp + pl.n_pilots);          // 2 * n_pilots floats in: 8-byte aligned
-  const float2* cell = p.freq + (size_t)s * p.fft_size + p.l_nulls;
-  float2* out = p.out + (size_t)s * p.n_out;
-
-  for (int i = threadIdx.x; i < pl.n_pilots; i += blockDim.x) {
-    const PlanPilot pp = pl.pilots[i];
-    const float2 c = __ldg(cell + pp.k);
-    const float er = __fmul_rn(c.x, pp.ref), ei = __fmul_rn(c.y, pp.ref);        // cell * pilot_refer
-    est[i] = make_float2(er, ei);
-    ang[i] = atan2_approx_dev(ei, er);
-    amp[i] = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y))), pp.amp);
-  }
-  __syncthreads();
-
-  if (threadIdx.x == 0) {
-    // ordered sums (data_symbol.cpp:162-163,183-193,319-324): the first pilot feeds sum_pilot_1 only
-    float s1r = est[0].x, s1i = est[0].y, s2r = 0.f, s2i = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int i = 1; i < pl.n_first; ++i) {                         // pilots left of the centre carrier
-      const float2 e = est[i];
-      s1r = __fadd_rn(s1r, e.x); s1i = __fadd_rn(s1i, e.y); a1 = __fadd_rn(a1, ang[i]);
-    }
-    for (int i = pl.n_first; i < pl.n_pilots; ++i) {               // right of it
-      const float2 e = est[i];
-      s2r = __fadd_rn(s2r, e.x); s2i = __fadd_rn(s2i, e.y); a2 = __fadd_rn(a2, ang[i]);
-    }
-    if (p.phase) p.phase[s] = __fadd_rn(atan2_approx_dev(s2i, s2r), atan2_approx_dev(s1i, s1r));
-    if (p.sro) p.sro[s] = __fsub_rn(a2, a1);
-  }
-
   const float PI = 3.14159265358979323846f;
   const float k_table = 32767.0f / (2.0f * PI);
-  for (int d = threadIdx.x; d < pl.n_cells; d += blockDim.x) {
-    const uint2 w = pl.cells[d];
-    const int k = w.x & 0xffff, ip = w.x >> 16, j = w.y & 0xff, n = (w.y >> 8) & 0xff, h = w.y >> 16;
-    const float ang_l = ang[ip], ang_r = ang[ip + 1], amp_l = amp[ip], amp_r = amp[ip + 1];
-    float dif = __fsub_rn(ang_r, ang_l);
-    if (dif > PI) dif = __fsub_rn(__fmul_rn(PI, 2.0f), dif);                      // data_symbol.cpp:190-191
-    else if (dif < -PI) dif = __fadd_rn(__fmul_rn(PI, 2.0f), dif);
-    const float fn = (float)(n + 1);
-    const float da = __fdiv_rn(dif, fn), dm = __fdiv_rn(__fsub_rn(amp_r, amp_l), fn);
-    float a = ang_l, m = amp_l;
-    for (int t = 0; t < j; ++t) { a = __fadd_rn(a, da); m = __fadd_rn(m, dm); }
-    const int li = __float2int_rz(__fadd_rn(__fmul_rn(a, k_table), 32767.0f)) & 65535;
-    const float dr = __fdiv_rn(__ldg(p.lut_cos + li), m), di = __fdiv_rn(__ldg(p.lut_sin + li), m);
-    const float2 c = __ldg(cell + k);
-    out[h] = make_float2(__fadd_rn(__fmul_rn(c.x, dr), __fmul_rn(c.y, di)),
-                         __fsub_rn(__fmul_rn(c.y, dr), __fmul_rn(c.x, di)));
+  float2* chain = reinterpret_cast<float2*>(smem_raw);
+  const int part = blockIdx.x % p.split;
+  for (int s = blockIdx.x / p.split; s < p.n_symbols; s += gridDim.x / p.split) {
+    const int idx = p.idx_symbol[s];
+    int rel = idx - p.first_symbol;
+    rel = min(max(rel, 0), p.n_symbols_kind - 1);
+    const PlanDev pl = p.plans[(idx & 1) ? p.plan_odd[rel] : p.plan_even[rel]];
+    float2* spec = chain + kEqChunk;
+    float2* est = spec + kEqSpan;
+    float* ang = reinterpret_cast<float*>(est + pl.n_pilots);
+    float* amp = ang + pl.n_pilots;
+    int* first = reinterpret_cast<int*>(amp + pl.n_pilots);
+    const float2* cell = p.freq + (size_t)s * p.in_stride + p.l_nulls;
+    float2* out = p.out + (size_t)s * p.out_stride;
+
+    for (int i = threadIdx.x; i < pl.n_pilots; i += blockDim.x) {
+      const PlanPilot pp = pl.pilots[i];
+      const float2 c = __ldg(cell + pp.k);
+      const float er = __fmul_rn(c.x, pp.ref), ei = __fmul_rn(c.y, pp.ref);        // cell * pilot_refer
+      est[i] = make_float2(er, ei);
+      ang[i] = atan2_approx_dev(ei, er);
+      amp[i] = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y))), pp.amp);
+      first[i] = __ldg(pl.first + i);
+    }
+    __syncthreads();
+
+    for (int c0 = part * kEqChunk; c0 < pl.n_cells; c0 += p.split * kEqChunk) {
+      const int c1 = min(c0 + kEqChunk, pl.n_cells);
+      // Loads that depend on nothing go first and stay in flight under phase A: the carriers spanned by the chunk's
+      // cells (cp.async straight into shared memory) and the plan words of this thread's cells.
+      const int ci = c0 / kEqChunk;
+      const int k_lo = __ldg(pl.chunk_k + 2 * ci), k_hi = __ldg(pl.chunk_k + 2 * ci + 1);
+      const bool staged = k_hi - k_lo < kEqSpan;
+      if (staged)
+        for (int k = k_lo + threadIdx.x; k <= k_hi; k += blockDim.x)
+          __pipeline_memcpy_async(spec + (k - k_lo), cell + k, sizeof(float2));
+      __pipeline_commit();
+      uint2 w[kEqU];
+#pragma unroll
+      for (int u = 0; u < kEqU; ++u) {
+        const int d = c0 + threadIdx.x + u * kEqThreads;
+        w[u] = d < c1 ? __ldg(pl.cells + d) : make_uint2(0u, 0u);
+      }
+      // ---- phase A: one thread per interval that overlaps the chunk (shared memory only) ----
+      for (int ip = __ldg(pl.chunk_lo + ci) + threadIdx.x; ip + 1 < pl.n_pilots; ip += blockDim.x) {
+        const int d0 = first[ip], d1 = first[ip + 1];
+        if (d0 >= c1) break;
+        if (d0 >= d1) continue;
+        const float ang_l = ang[ip], ang_r = ang[ip + 1], amp_l = amp[ip], amp_r = amp[ip + 1];
+        float dif = __fsub_rn(ang_r, ang_l);
+        if (dif > PI) dif = __fsub_rn(__fmul_rn(PI, 2.0f), dif);                      // data_symbol.cpp:190-191
+        else if (dif < -PI) dif = __fadd_rn(__fmul_rn(PI, 2.0f), dif);
+        const float fn = (float)(d1 - d0 + 1);
+        const float da = __fdiv_rn(dif, fn), dm = __fdiv_rn(__fsub_rn(amp_r, amp_l), fn);
+        float a = ang_l, m = amp_l;
+        const int dend = min(d1, c1);
+        for (int d = d0; d < dend; ++d) {
+          a = __fadd_rn(a, da); m = __fadd_rn(m, dm);
+          if (d >= c0) chain[d - c0] = make_float2(a, m);
+        }
+      }
+      __pipeline_wait_prior(0);
+      __syncthreads();
+      // ---- phase B: all cells of the chunk, independently; the table look-ups of a thread's cells are in flight together ----
+      float2 am[kEqU], cs[kEqU];
+#pragma unroll
+      for (int u = 0; u < kEqU; ++u) {
+        const int d = c0 + threadIdx.x + u * kEqThreads;
+        if (d < c1) {
+          am[u] = chain[d - c0];
+          const int li = __float2int_rz(__fadd_rn(__fmul_rn(am[u].x, k_table), 32767.0f)) & 65535;
+          cs[u] = __ldg(p.lut_cs + li);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kEqU; ++u) {
+        const int d = c0 + threadIdx.x + u * kEqThreads;
+        if (d < c1) {
+          const int k = (int)(w[u].x & 0xffff);
+          const float2 c = staged ? spec[k - k_lo] : __ldg(cell + k);
+          const float dr = __fdiv_rn(cs[u].x, am[u].y), di = __fdiv_rn(cs[u].y, am[u].y);
+          out[w[u].y >> 16] = make_float2(__fadd_rn(__fmul_rn(c.x, dr), __fmul_rn(c.y, di)),
+                                          __fsub_rn(__fmul_rn(c.y, dr), __fmul_rn(c.x, di)));
+        }
+      }
+      __syncthreads();
+    }
+
+    if (part == 0 && threadIdx.x == blockDim.x - 1 && (p.phase || p.sro)) {
+      // ordered sums (data_symbol.cpp:162-163,183-193,319-324): the first pilot feeds sum_pilot_1 only.
+      // Operands are fetched eight at a time so that only the three FADD chains are serial.
+      float s1r = est[0].x, s1i = est[0].y, s2r = 0.f, s2i = 0.f, a1 = 0.f, a2 = 0.f;
+      int i = 1;
+      for (; i + 8 <= pl.n_first; i += 8) {
+        float2 e[8]; float g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { e[u] = est[i + u]; g[u] = ang[i + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1r = __fadd_rn(s1r, e[u].x); s1i = __fadd_rn(s1i, e[u].y); a1 = __fadd_rn(a1, g[u]); }
+      }
+      for (; i < pl.n_first; ++i) {                                  // pilots left of the centre carrier
+        const float2 e = est[i];
+        s1r = __fadd_rn(s1r, e.x); s1i = __fadd_rn(s1i, e.y); a1 = __fadd_rn(a1, ang[i]);
+      }
+      for (; i + 8 <= pl.n_pilots; i += 8) {
+        float2 e[8]; float g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { e[u] = est[i + u]; g[u] = ang[i + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s2r = __fadd_rn(s2r, e[u].x); s2i = __fadd_rn(s2i, e[u].y); a2 = __fadd_rn(a2, g[u]); }
+      }
+      for (; i < pl.n_pilots; ++i) {                                 // right of it
+        const float2 e = est[i];
+        s2r = __fadd_rn(s2r, e.x); s2i = __fadd_rn(s2i, e.y); a2 = __fadd_rn(a2, ang[i]);
+      }
+      if (p.phase) p.phase[s] = __fadd_rn(atan2_approx_dev(s2i, s2r), atan2_approx_dev(s1i, s1r));
+      if (p.sro) p.sro[s] = __fsub_rn(a2, a1);
+    }
+    __syncthreads();                        // the pilot arrays are reused by the next symbol
   }
 }
 
@@ -140,8 +228,9 @@ bool build_plan(int kind, int k_total, const int32_t* map, const float* refer, c
                 float amp_cp, PlanHost& out, std::string& err)
 {
   const int half_total = k_total / 2;
-  out.pilots.clear(); out.cells.clear();
+  out.pilots.clear(); out.cells.clear(); out.first.clear();
   out.pilots.push_back({0, 0, 0, refer[0], amp_main});            // carrier 0: always the first (edge) pilot
+  out.first.push_back(0);
   std::vector<int> pending;                                        // carriers of buffered data cells
   int d = 0;
   for (int i = 1; i < k_total; ++i) {
@@ -168,6 +257,7 @@ bool build_plan(int kind, int k_total, const int32_t* map, const float* refer, c
                                      (uint32_t)(j + 1) | ((uint32_t)n << 8) | ((uint32_t)h[d] << 16)));
     }
     pending.clear();
+    out.first.push_back((int)out.cells.size());        // cells right of the pilot just added start here
   }
   if (out.pilots.size() > 65535) { err = "too many pilots"; return false; }
   return true;
@@ -176,7 +266,7 @@ bool build_plan(int kind, int k_total, const int32_t* map, const float* refer, c
 void free_tables(SymbolTables* t)
 {
   if (!t) return;
-  for (auto& p : t->plans) { cudaFree(p.pilots); cudaFree(p.cells); }
+  for (auto& p : t->plans) { cudaFree(p.pilots); cudaFree(p.cells); cudaFree(p.first); cudaFree(p.chunk_lo); cudaFree(p.chunk_k); }
   cudaFree(t->d_plan_even); cudaFree(t->d_plan_odd); cudaFree(t->d_plans);
   delete t;
 }
@@ -193,9 +283,9 @@ void t2_eq_free(t2b200_ctx* ctx)
 static int ensure_lut(t2b200_ctx* ctx)
 {
   if (ctx->d_lut) return T2B200_OK;
-  std::vector<float> h(2 * 65536, 0.0f);                          // DSP/fast_math.h:25-40: entry 65535 stays 0
+  std::vector<float> h(2 * 65536, 0.0f);                          // DSP/fast_math.h:25-40: entry 65535 stays 0; {cos, sin} pairs
   const float k_table = 32767.0f / (2.0f * 3.14159265358979323846f);
-  for (int i = -32767; i < 32768; i++) { h[i + 32767] = sinf(i / k_table); h[65536 + i + 32767] = cosf(i / k_table); }
+  for (int i = -32767; i < 32768; i++) { h[2 * (i + 32767) + 1] = sinf(i / k_table); h[2 * (i + 32767)] = cosf(i / k_table); }
   T2_CUDA(ctx, cudaMalloc(&ctx->d_lut, h.size() * sizeof(float)));
   T2_CUDA(ctx, cudaMemcpy(ctx->d_lut, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
   return T2B200_OK;
@@ -246,6 +336,20 @@ extern "C" int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int
     T2_CUDA(ctx, cudaMalloc(&d.cells, std::max<size_t>(1, ph.cells.size()) * sizeof(uint2)));
     T2_CUDA(ctx, cudaMemcpy(d.pilots, ph.pilots.data(), ph.pilots.size() * sizeof(PlanPilot), cudaMemcpyHostToDevice));
     T2_CUDA(ctx, cudaMemcpy(d.cells, ph.cells.data(), ph.cells.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    T2_CUDA(ctx, cudaMalloc(&d.first, ph.first.size() * sizeof(int)));
+    T2_CUDA(ctx, cudaMemcpy(d.first, ph.first.data(), ph.first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> clo, ck;
+    for (int c0 = 0, ip = 0; c0 < (int)ph.cells.size() || clo.empty(); c0 += kEqChunk) {
+      while (ip + 1 < (int)ph.first.size() && ph.first[ip + 1] <= c0) ++ip;       // largest ip with first[ip] <= c0
+      clo.push_back(ip);
+      const int c1 = std::min<int>(c0 + kEqChunk, (int)ph.cells.size());
+      ck.push_back(ph.cells.empty() ? 0 : (int)(ph.cells[c0].x & 0xffff));
+      ck.push_back(ph.cells.empty() ? 0 : (int)(ph.cells[c1 - 1].x & 0xffff));
+    }
+    T2_CUDA(ctx, cudaMalloc(&d.chunk_k, ck.size() * sizeof(int)));
+    T2_CUDA(ctx, cudaMemcpy(d.chunk_k, ck.data(), ck.size() * sizeof(int), cudaMemcpyHostToDevice));
+    T2_CUDA(ctx, cudaMalloc(&d.chunk_lo, clo.size() * sizeof(int)));
+    T2_CUDA(ctx, cudaMemcpy(d.chunk_lo, clo.data(), clo.size() * sizeof(int), cudaMemcpyHostToDevice));
     t->plans.push_back(d);
     t->max_pilots = std::max(t->max_pilots, d.n_pilots);
   }
@@ -277,11 +381,14 @@ extern "C" int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const i
   EqParams p;
   p.freq = (const float2*)dfreq; p.out = (float2*)dout; p.sro = (float*)dsro; p.phase = (float*)dph; p.idx_symbol = (const int*)didx;
   p.plans = t->d_plans; p.plan_even = t->d_plan_even; p.plan_odd = t->d_plan_odd;
-  p.lut_sin = ctx->d_lut; p.lut_cos = ctx->d_lut + 65536;
+  p.lut_cs = reinterpret_cast<const float2*>(ctx->d_lut);
   p.fft_size = t->fft_size; p.l_nulls = t->l_nulls; p.n_out = t->n_out; p.first_symbol = t->first_symbol; p.n_symbols_kind = t->n_symbols;
-  const size_t smem = (size_t)(t->max_pilots + 2) * 16;
+  p.n_symbols = n_symbols; p.in_stride = t->fft_size; p.out_stride = t->n_out;
+  const size_t smem = (size_t)(kEqChunk + kEqSpan) * sizeof(float2) + (size_t)(t->max_pilots + 2) * 20;
   T2_CUDA(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  equalize_kernel<<<n_symbols, 512, smem, ctx->stream>>>(p);
+  p.split = kEqSplitDefault;
+  if (const char* e = getenv("T2B200_EQ_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.split = v; }   // development aid
+  equalize_kernel<<<n_symbols * p.split, kEqThreads, smem, ctx->stream>>>(p);
   T2_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   if ((rc = t2_finish_out(ctx, cells_out, dout, (size_t)n_symbols * t->n_out * 8))) return rc;
