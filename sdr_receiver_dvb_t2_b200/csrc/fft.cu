@@ -24,112 +24,150 @@ struct FftPlan {
 
 namespace {
 
-constexpr int TILE = 16;       // transforms per CTA
-constexpr int PITCH = 17;      // shared-memory pitch per element (float2 units)
 constexpr int N2 = 256;
+constexpr int kColsA = 32;     // columns per pass-A CTA (one warp = 32 consecutive columns = 256 contiguous bytes)
+constexpr int kRowsB = 16;     // rows per pass-B CTA
+constexpr int kPitchB = 17;    // shared-memory pitch (float2) of the pass-B exchange
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// One radix-R Stockham stage over TILE transforms of length L: x -> y (both [L][PITCH]).
-// wl = W_L^m table (L entries, built from W_256 by stride).  Ns = product of the radices already done.
-template <int R>
-__device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, float2* __restrict__ y,
-                                               const float2* __restrict__ w256, int L, int Ns)
+// 4-point DFT in place, natural order
+__device__ __forceinline__ void fft4(float2& x0, float2& x1, float2& x2, float2& x3)
 {
-  const int T = L / R;
-  const int wstep = (N2 / L) * (L / (Ns * R));       // exp(-2 pi i r k / (Ns R)) = W_256^(r k wstep)
-  for (int t = threadIdx.x; t < T * TILE; t += blockDim.x) {
-    const int c = t % TILE, j = t / TILE;
-    const int k = j & (Ns - 1);
-    float2 u[R];
+  const float2 a0 = cadd(x0, x2), a1 = csub(x0, x2), a2 = cadd(x1, x3), d = csub(x1, x3);
+  const float2 a3 = make_float2(d.y, -d.x);                      // (x1 - x3) * (-j)
+  x0 = cadd(a0, a2); x1 = cadd(a1, a3); x2 = csub(a0, a2); x3 = csub(a1, a3);
+}
+// multiply by W_16^e, e a compile-time constant
+template <int E> __device__ __forceinline__ float2 mul_w16(float2 v)
+{
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+  constexpr int e = E & 15;
+  if (e == 0) return v;
+  if (e == 4) return make_float2(v.y, -v.x);
+  if (e == 8) return make_float2(-v.x, -v.y);
+  if (e == 12) return make_float2(-v.y, v.x);
+  if (e == 2) return make_float2(H * (v.x + v.y), H * (v.y - v.x));
+  if (e == 6) return make_float2(H * (v.y - v.x), -H * (v.x + v.y));
+  constexpr float wr = e == 1 ? C1 : e == 3 ? S1 : e == 9 ? -C1 : e == 5 ? -S1 : e == 7 ? -C1 : 0.0f;
+  constexpr float wi = e == 1 ? -S1 : e == 3 ? -C1 : e == 9 ? S1 : e == 5 ? -C1 : e == 7 ? -S1 : 0.0f;
+  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+}
+// 16-point DFT of x[n] in place (n = 4*n1 + n2).  Output X[K] is left in x[4*(K & 3) + (K >> 2)].
+__device__ __forceinline__ void fft16(float2 (&x)[16])
+{
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      u[r] = x[(j + r * T) * PITCH + c];
-      if (r) u[r] = cmul(u[r], w256[(r * k * wstep) & (N2 - 1)]);
-    }
-    const int j0 = (j - k) * R + k;
-    if (R == 2) {
-      y[j0 * PITCH + c] = make_float2(u[0].x + u[1].x, u[0].y + u[1].y);
-      y[(j0 + Ns) * PITCH + c] = make_float2(u[0].x - u[1].x, u[0].y - u[1].y);
-    } else {
-      const float2 a0 = make_float2(u[0].x + u[2].x, u[0].y + u[2].y), a1 = make_float2(u[0].x - u[2].x, u[0].y - u[2].y);
-      const float2 a2 = make_float2(u[1].x + u[3].x, u[1].y + u[3].y);
-      const float2 d = make_float2(u[1].x - u[3].x, u[1].y - u[3].y);
-      const float2 a3 = make_float2(d.y, -d.x);                                   // (u1 - u3) * (-j)
-      y[j0 * PITCH + c] = make_float2(a0.x + a2.x, a0.y + a2.y);
-      y[(j0 + Ns) * PITCH + c] = make_float2(a1.x + a3.x, a1.y + a3.y);
-      y[(j0 + 2 * Ns) * PITCH + c] = make_float2(a0.x - a2.x, a0.y - a2.y);
-      y[(j0 + 3 * Ns) * PITCH + c] = make_float2(a1.x - a3.x, a1.y - a3.y);
-    }
+  for (int n2 = 0; n2 < 4; ++n2) fft4(x[n2], x[4 + n2], x[8 + n2], x[12 + n2]);     // k1 now at x[4*k1 + n2]
+  x[5] = mul_w16<1>(x[5]);  x[6] = mul_w16<2>(x[6]);   x[7] = mul_w16<3>(x[7]);       // W_16^(n2*k1)
+  x[9] = mul_w16<2>(x[9]);  x[10] = mul_w16<4>(x[10]); x[11] = mul_w16<6>(x[11]);
+  x[13] = mul_w16<3>(x[13]); x[14] = mul_w16<6>(x[14]); x[15] = mul_w16<9>(x[15]);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) fft4(x[4 * k1], x[4 * k1 + 1], x[4 * k1 + 2], x[4 * k1 + 3]);
+}
+__device__ __forceinline__ constexpr int pos16(int K) { return 4 * (K & 3) + (K >> 2); }
+
+// A-point DFT (A = 1, 2, 4, 8) of x[0..A) in place, natural order
+template <int A> __device__ __forceinline__ void fft_small(float2 (&x)[8])
+{
+  if (A == 2) { const float2 t = x[0]; x[0] = cadd(t, x[1]); x[1] = csub(t, x[1]); }
+  if (A == 4) fft4(x[0], x[1], x[2], x[3]);
+  if (A == 8) {
+    // n = 2*n1 + n2: two 4-point DFTs over n1, twiddle W_8^(n2*k1), then the 2-point stage
+    fft4(x[0], x[2], x[4], x[6]);
+    fft4(x[1], x[3], x[5], x[7]);
+    const float2 y1 = mul_w16<2>(x[3]), y2 = mul_w16<4>(x[5]), y3 = mul_w16<6>(x[7]);
+    const float2 e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6], o0 = x[1];
+    x[0] = cadd(e0, o0); x[4] = csub(e0, o0);
+    x[1] = cadd(e1, y1); x[5] = csub(e1, y1);
+    x[2] = cadd(e2, y2); x[6] = csub(e2, y2);
+    x[3] = cadd(e3, y3); x[7] = csub(e3, y3);
   }
 }
 
-// all stages of the length-L transforms held in buf0; returns the buffer holding the result
-__device__ __forceinline__ float2* stockham_all(float2* buf0, float2* buf1, const float2* w256, int L)
+// Pass A: columns n2 of the N1 x 256 view: Y[k1][n2] = W_n^(k1 n2) * sum_n1 x[n1*256 + n2] W_N1^(n1 k1), N1 = 16*A.
+// Thread (a = warp, c = lane) loads the 16 samples n1 = A*r + a of column n2_0 + c straight from global memory (a warp
+// reads 256 contiguous bytes per instruction), runs the radix-16 butterflies in registers, passes the results through one
+// shared-memory exchange to the radix-A stage (again in registers) and stores Y, inter-pass twiddle applied, as 256-byte rows.
+template <int A>
+__global__ void __launch_bounds__(32 * A) fft_pass_a(const float2* __restrict__ in, float2* __restrict__ tmp,
+                                                      const float2* __restrict__ wn, int n)
 {
-  float2 *x = buf0, *y = buf1;
-  int Ns = 1;
-  while (Ns < L) {
-    if (L / Ns >= 4) { stockham_stage<4>(x, y, w256, L, Ns); Ns *= 4; }
-    else { stockham_stage<2>(x, y, w256, L, Ns); Ns *= 2; }
-    __syncthreads();
-    float2* t = x; x = y; y = t;
-  }
-  return x;
-}
-
-// Pass A: for 16 consecutive columns n2: Y[k1][n2] = W_n^(k1 n2) * sum_n1 x[n1*256 + n2] W_n1^(n1 k1)
-__global__ void __launch_bounds__(256) fft_pass_a(const float2* __restrict__ in, float2* __restrict__ tmp,
-                                                   const float2* __restrict__ wn, const float2* __restrict__ w256g,
-                                                   int n, int n1)
-{
-  extern __shared__ __align__(16) float2 sm[];
-  float2* w256 = sm;
-  float2* buf0 = sm + N2;
-  float2* buf1 = buf0 + n1 * PITCH;
-  const int n2_0 = blockIdx.x * TILE;
-  const float2* src = in + (size_t)blockIdx.y * n;
-  float2* dst = tmp + (size_t)blockIdx.y * n;
-  for (int i = threadIdx.x; i < N2; i += blockDim.x) w256[i] = __ldg(w256g + i);
-  for (int t = threadIdx.x; t < n1 * TILE; t += blockDim.x) {
-    const int c = t % TILE, e = t / TILE;
-    buf0[e * PITCH + c] = __ldg(src + (size_t)e * N2 + n2_0 + c);
+  constexpr int N1 = 16 * A;
+  __shared__ float2 sm[16 * A * kColsA];
+  const int c = threadIdx.x & 31, a = threadIdx.x >> 5;
+  const int n2 = blockIdx.x * kColsA + c;
+  const float2* src = in + (size_t)blockIdx.y * n + n2;
+  float2* dst = tmp + (size_t)blockIdx.y * n + n2;
+  float2 x[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) x[r] = __ldg(src + (size_t)(A * r + a) * N2);
+  fft16(x);
+  const int wstep1 = n / N1;                                       // W_N1^e = W_n^(e * n / N1)
+#pragma unroll
+  for (int kr = 0; kr < 16; ++kr) {
+    float2 v = x[pos16(kr)];
+    if (A > 1 && kr) v = cmul(v, __ldg(wn + ((a * kr * wstep1) & (n - 1))));    // warp-uniform address
+    sm[(kr * A + a) * kColsA + c] = v;
   }
   __syncthreads();
-  const float2* res = stockham_all(buf0, buf1, w256, n1);
-  for (int t = threadIdx.x; t < n1 * TILE; t += blockDim.x) {
-    const int c = t % TILE, k1 = t / TILE;
-    const float2 w = __ldg(wn + k1 * (n2_0 + c));
-    dst[(size_t)k1 * N2 + n2_0 + c] = cmul(res[k1 * PITCH + c], w);
+  const float2 wstep = __ldg(wn + ((16 * n2) & (n - 1)));          // W_n^(16 n2): k1 -> k1 + 16
+#pragma unroll
+  for (int j = 0; j < 16 / A; ++j) {
+    const int kr = a + A * j;
+    float2 y[8];
+#pragma unroll
+    for (int aa = 0; aa < A; ++aa) y[aa] = sm[(kr * A + aa) * kColsA + c];
+    fft_small<A>(y);
+    float2 w = __ldg(wn + ((kr * n2) & (n - 1)));
+#pragma unroll
+    for (int ka = 0; ka < A; ++ka) {
+      dst[(size_t)(kr + 16 * ka) * N2] = cmul(y[ka], w);
+      w = cmul(w, wstep);
+    }
   }
 }
 
-// Pass B: for 16 consecutive rows k1: X[k1 + n1*k2] = sum_n2 Y[k1][n2] W_256^(n2 k2), stored half-swapped
+// Pass B: rows k1 of Y: X[k1 + N1*k2] = sum_n2 Y[k1][n2] W_256^(n2 k2), stored half-swapped.  16 rows per CTA.  Stage 1:
+// thread (a = lane & 15, row) takes n2 = 16*r + a (a half-warp reads 128 contiguous bytes); stage 2: thread (kr, row) with
+// the ROW index fastest across lanes, so that the 16 results X[k1_0 .. k1_0+15 + N1*k2] of a half-warp are contiguous.
 __global__ void __launch_bounds__(256) fft_pass_b(const float2* __restrict__ tmp, float2* __restrict__ out,
                                                    const float2* __restrict__ w256g, int n, int n1)
 {
-  extern __shared__ __align__(16) float2 sm[];
-  float2* w256 = sm;
-  float2* buf0 = sm + N2;
-  float2* buf1 = buf0 + N2 * PITCH;
-  const int k1_0 = blockIdx.x * TILE;
+  __shared__ float2 sm[256 * kPitchB];
+  const int k1_0 = blockIdx.x * kRowsB;
   const float2* src = tmp + (size_t)blockIdx.y * n;
   float2* dst = out + (size_t)blockIdx.y * n;
-  for (int i = threadIdx.x; i < N2; i += blockDim.x) w256[i] = __ldg(w256g + i);
-  for (int t = threadIdx.x; t < N2 * TILE; t += blockDim.x) {
-    const int e = t % N2, c = t / N2;                       // coalesced along the row
-    buf0[e * PITCH + c] = __ldg(src + (size_t)(k1_0 + c) * N2 + e);
+  float2 x[16];
+  {
+    const int a = threadIdx.x & 15, c = threadIdx.x >> 4;
+    const float2* row = src + (size_t)(k1_0 + c) * N2 + a;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = __ldg(row + 16 * r);
+    fft16(x);
+#pragma unroll
+    for (int kr = 0; kr < 16; ++kr) {
+      float2 v = x[pos16(kr)];
+      if (kr) v = cmul(v, __ldg(w256g + ((a * kr) & (N2 - 1))));
+      sm[(kr * 16 + a) * kPitchB + c] = v;
+    }
   }
   __syncthreads();
-  const float2* res = stockham_all(buf0, buf1, w256, N2);
-  const int half = n >> 1;
-  for (int t = threadIdx.x; t < N2 * TILE; t += blockDim.x) {
-    const int c = t % TILE, k2 = t / TILE;
-    const int k = k1_0 + c + n1 * k2;
-    dst[(k + half) & (n - 1)] = res[k2 * PITCH + c];          // fast_fourier_transform.h:67-68
+  {
+    const int c = threadIdx.x & 15, kr = threadIdx.x >> 4;
+#pragma unroll
+    for (int a = 0; a < 16; ++a) x[a] = sm[(kr * 16 + a) * kPitchB + c];
+    fft16(x);
+    const int half = n >> 1;
+#pragma unroll
+    for (int ka = 0; ka < 16; ++ka) {
+      const int k = k1_0 + c + n1 * (kr + 16 * ka);
+      dst[(k + half) & (n - 1)] = x[pos16(ka)];                    // fast_fourier_transform.h:67-68
+    }
   }
 }
 
@@ -145,7 +183,7 @@ static int get_plan(t2b200_ctx* ctx, int n, FftPlan** out)
 {
   auto it = ctx->fft.find(n);
   if (it != ctx->fft.end()) { *out = it->second; return T2B200_OK; }
-  if (n < 1024 || n > 32768 || (n & (n - 1))) { ctx->err = "t2b200_fft: n must be a power of two in [1024, 32768]"; return T2B200_ERR_ARG; }
+  if (n < 4096 || n > 32768 || (n & (n - 1))) { ctx->err = "t2b200_fft: n must be a power of two in [4096, 32768]"; return T2B200_ERR_ARG; }
   FftPlan* p = new FftPlan();
   p->n = n; p->n1 = n / N2;
   std::vector<float2> wn(n), w256(N2);
@@ -166,17 +204,21 @@ int t2_fft_device(t2b200_ctx* ctx, int n, const float2* d_in, int batch, float2*
 {
   FftPlan* p; int rc;
   if ((rc = get_plan(ctx, n, &p))) return rc;
-  const size_t smem_a = (size_t)(N2 + 2 * p->n1 * PITCH) * sizeof(float2);
-  const size_t smem_b = (size_t)(N2 + 2 * N2 * PITCH) * sizeof(float2);
-  T2_CUDA(ctx, cudaFuncSetAttribute(fft_pass_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-  T2_CUDA(ctx, cudaFuncSetAttribute(fft_pass_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   // walk the batch in chunks whose input + intermediate + output stay well inside the 126 MB L2
   const int chunk = std::max(1, (int)((48u << 20) / ((size_t)n * sizeof(float2) * 2)));
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = std::min(chunk, batch - b0);
-    fft_pass_a<<<dim3(N2 / TILE, nb), 256, smem_a, ctx->stream>>>(d_in + (size_t)b0 * n, d_tmp + (size_t)(b0 % chunk) * n, p->d_wn, p->d_w256, n, p->n1);
+    const float2* cin = d_in + (size_t)b0 * n;
+    float2* ctmp = d_tmp;
+    const dim3 ga(N2 / kColsA, nb);
+    switch (p->n1 / 16) {
+      case 1: fft_pass_a<1><<<ga, 32, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
+      case 2: fft_pass_a<2><<<ga, 64, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
+      case 4: fft_pass_a<4><<<ga, 128, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
+      default: fft_pass_a<8><<<ga, 256, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
+    }
     T2_CUDA(ctx, cudaGetLastError());
-    fft_pass_b<<<dim3(p->n1 / TILE, nb), 256, smem_b, ctx->stream>>>(d_tmp + (size_t)(b0 % chunk) * n, d_out + (size_t)b0 * n, p->d_w256, n, p->n1);
+    fft_pass_b<<<dim3(p->n1 / kRowsB, nb), 256, 0, ctx->stream>>>(ctmp, d_out + (size_t)b0 * n, p->d_w256, n, p->n1);
     T2_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
   }
