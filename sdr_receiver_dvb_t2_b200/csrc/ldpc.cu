@@ -43,6 +43,7 @@ constexpr int kMaxEdgeWords = 648;     // max q * CNL over all codes (rate 3/5 n
 struct LdpcParams {
   const int8_t* llr; uint8_t* bits; int32_t* trials_left; int32_t* iters; int8_t* post_out;
   const uint8_t* level; const uint8_t* prbs; unsigned* gsync;
+  unsigned* gqueue;                   // [0] next unclaimed group; [1 + slot * (n_groups + 1) + round] group (+1) claimed by a slot's lane 0
   uint32_t* cn_state;                 // [grid][NS][R] packed check-node words (L2-resident scratch, thread-private)
   int n_cw, group_lanes, max_trials; unsigned flags;
   int N, K, q, k_out;
@@ -351,10 +352,31 @@ __global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __gri
 
   const int tid = threadIdx.x;
   const int GL = p.group_lanes;
-  const int lane = blockIdx.x % GL, slot = blockIdx.x / GL, nslots = gridDim.x / GL;
+  const int lane = blockIdx.x % GL, slot = blockIdx.x / GL;
   const int n_groups = (p.n_cw + GL - 1) / GL;
 
-  for (int g = slot; g < n_groups; g += nslots) {
+  // Groups are claimed dynamically (an atomic counter; lane 0 of a slot claims, the slot's other lanes pick the claim
+  // up from the queue word of that round): lock-step groups differ in iteration count, a static round-robin would leave
+  // slots idle at the end.
+  __shared__ int s_group;
+  for (int round = 0;; ++round) {
+    if (tid == 0) {
+      unsigned* w = p.gqueue + 1 + (size_t)slot * (n_groups + 1) + round;
+      int gg;
+      if (lane == 0) {
+        gg = (int)atomicAdd(p.gqueue, 1u);
+        if (GL > 1) { __threadfence(); atomicExch(w, (unsigned)gg + 1u); }
+      } else {
+        unsigned v;
+        while ((v = ld_acquire(w)) == 0u) __nanosleep(64);
+        gg = (int)v - 1;
+      }
+      s_group = gg;
+    }
+    __syncthreads();
+    const int g = s_group;
+    __syncthreads();
+    if (g >= n_groups) break;
     const int lanes_here = min(GL, p.n_cw - g * GL);
     if (lane >= lanes_here) continue;
     const int cw = g * GL + lane;
@@ -654,8 +676,19 @@ extern "C" int t2b200_ldpc_n(int code) { auto t = t2_ldpc_code_data(code); retur
 extern "C" int t2b200_ldpc_k(int code) { auto t = t2_ldpc_code_data(code); return t ? t->K : 0; }
 extern "C" int t2b200_ldpc_k_bch(int code) { return t2_ldpc_k_bch(code); }
 
+// rows (of kSyncStride words) of the zeroed sync area one launch uses: one per group + the claim queue
+static size_t ldpc_sync_rows(const LdpcDeviceCode* d, int sm_count, int n_cw, unsigned flags)
+{
+  const int gl = (flags & T2B200_LDPC_GROUP32) ? 32 : 1;
+  const size_t n_groups = ((size_t)n_cw + gl - 1) / gl;
+  const size_t slots = std::max<size_t>(1, std::min<size_t>((size_t)d->blocks_per_sm * sm_count / gl, n_groups));
+  if (gl == 1) return 1;                                          // the claim counter only
+  const size_t queue_rows = (1 + slots * (n_groups + 1) + kSyncStride - 1) / kSyncStride;
+  return n_groups + queue_rows;
+}
+
 // Launch the decoder on device-resident buffers (all pointers device memory or null).
-// sync_off: first group-sync row this launch may use (rows are zeroed by the caller).
+// sync_off: first row of the sync area this launch may use (rows are zeroed by the caller).
 static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, int n_cw, uint8_t* d_bits,
                        int32_t* d_tr, int32_t* d_it, int8_t* d_post, int max_trials, unsigned flags, int k_out,
                        size_t sync_off, cudaStream_t st)
@@ -674,8 +707,10 @@ static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, 
     if (slots < 1) { ctx->err = "GPU cannot co-schedule one 32-lane group"; return T2B200_ERR_CUDA; }
     grid = slots * 32;
     p.gsync = ctx->d_group_sync + sync_off * kSyncStride;
+    p.gqueue = p.gsync + (size_t)n_groups * kSyncStride;
   } else {
     grid = std::min(capacity, n_cw);
+    p.gqueue = ctx->d_group_sync + sync_off * kSyncStride;
   }
   {
     // one row of check-node words per resident CTA; the kernel clears its row per codeword
@@ -688,9 +723,9 @@ static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, 
   return T2B200_OK;
 }
 
-static int ensure_group_sync(t2b200_ctx* ctx, int n_groups, cudaStream_t st)
+static int ensure_group_sync(t2b200_ctx* ctx, size_t rows, cudaStream_t st)
 {
-  const size_t need = (size_t)n_groups * kSyncStride * sizeof(unsigned);
+  const size_t need = rows * kSyncStride * sizeof(unsigned);
   if (ctx->group_sync_cap < need) {
     T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
@@ -727,8 +762,11 @@ static int ldpc_decode_pipelined(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_
   if ((rc = t2_dev_scratch(ctx, 1, 2 * (size_t)chunk * out_row, &b_out))) return rc;
   if ((rc = t2_dev_scratch(ctx, 2, 4 * (size_t)n_cw, &b_tr))) return rc;
   if ((rc = t2_dev_scratch(ctx, 3, 4 * (size_t)n_cw, &b_it))) return rc;
-  if (flags & T2B200_LDPC_GROUP32)
-    if ((rc = ensure_group_sync(ctx, (n_cw + 31) / 32 + n_chunks, ctx->stream))) return rc;
+  {
+    size_t rows = 0;
+    for (int c = 0; c < n_chunks; ++c) rows += ldpc_sync_rows(d, ctx->sm_count, std::min(chunk, n_cw - c * chunk), flags);
+    if ((rc = ensure_group_sync(ctx, rows, ctx->stream))) return rc;
+  }
   // the copy streams must not start before earlier work on the context stream (memset above, previous calls)
   T2_CUDA(ctx, cudaEventRecord(ctx->ev_k[0], ctx->stream));
   T2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_k[0], 0));
@@ -745,7 +783,7 @@ static int ldpc_decode_pipelined(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_
     if (c >= 2) T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // D2H c-2 drained dout
     if ((rc = ldpc_launch(ctx, d, din, n, bits_out ? dout : nullptr, (int32_t*)b_tr + c0, (int32_t*)b_it + c0, nullptr,
                           max_trials, flags, k_out, sync_off, ctx->stream))) return rc;
-    sync_off += (n + 31) / 32;
+    sync_off += ldpc_sync_rows(d, ctx->sm_count, n, flags);
     T2_CUDA(ctx, cudaEventRecord(ctx->ev_k[b], ctx->stream));
     if (bits_out) {
       T2_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[b], 0));
@@ -793,8 +831,7 @@ extern "C" int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, 
   if (trials_left && (rc = t2_out_device(ctx, 2, trials_left, 4 * (size_t)n_cw, &d_tr))) return rc;
   if (iterations && (rc = t2_out_device(ctx, 3, iterations, 4 * (size_t)n_cw, &d_it))) return rc;
   if ((flags & T2B200_LDPC_WANT_POST) && (rc = t2_out_device(ctx, 4, post_out, (size_t)n_cw * s.N, &d_post))) return rc;
-  if (flags & T2B200_LDPC_GROUP32)
-    if ((rc = ensure_group_sync(ctx, (n_cw + 31) / 32, ctx->stream))) return rc;
+  if ((rc = ensure_group_sync(ctx, ldpc_sync_rows(d, ctx->sm_count, n_cw, flags), ctx->stream))) return rc;
   if ((rc = ldpc_launch(ctx, d, (const int8_t*)d_llr, n_cw, (uint8_t*)d_bits, (int32_t*)d_tr, (int32_t*)d_it,
                         (int8_t*)d_post, max_trials, flags, k_out, 0, ctx->stream))) return rc;
   if (bits_out && (rc = t2_finish_out(ctx, bits_out, d_bits, out_row * n_cw))) return rc;
