@@ -174,6 +174,7 @@ def ref_chain():
         L.ref_fec_feed_p2.argtypes = [_i32p, _i32p, C.c_int, C.c_void_p]
         L.ref_fec_feed.argtypes = [C.c_int, C.c_void_p]
         L.ref_demap.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_bb_deheader.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.ref_ti_permutation.argtypes = [C.c_int, _i32p, C.c_int]
         L.ref_demap_address.argtypes = [C.c_int, C.c_int, C.c_int, _i32p]
         for n in ('ti_cells', 'ti_sizes', 'llr', 'ldpc_bits', 'bb_bits', 'bb_len', 'snr', 'ts', 'ts_datagrams'):
@@ -285,6 +286,14 @@ class RefFec:
         cells = np.ascontiguousarray(cells, np.complex64).copy()
         self.L.ref_demap(len(cells), cells.ctypes.data, plp)
 
+    def deheader(self, bits, plp=0):
+        """one BBFRAME (uint8, one byte per bit) through the reference's bb_de_header::execute; the datagram is in taps()['ts']"""
+        n = len(bits)
+        # normal mode reads its per-packet CRC bytes without counting them against DFL (bb_de_header.cpp:286-296), i.e.
+        # past the end of a full data field: give both implementations the same defined bytes there
+        bits = np.concatenate([np.ascontiguousarray(bits, np.uint8), np.zeros(4096, np.uint8)])
+        self.L.ref_bb_deheader(plp, n, bits.ctypes.data)
+
     def permutation(self, plp=0):
         out = np.zeros(1 << 22, np.int32)
         n = self.L.ref_ti_permutation(plp, out, len(out))
@@ -365,3 +374,25 @@ def port_fft(x):
     out = np.empty_like(x)
     port().port_fft_shift(x.ctypes.data, len(x), out.ctypes.data)
     return out
+
+
+# ---- port oracle: BBFRAME -> TS re-packetiser (oracle/port/ts_port.c) ----
+class PortTs:
+    """stateful restatement of bb_de_header::execute: feed(bits) -> datagram bytes (None when the frame is dropped)"""
+
+    def __init__(self):
+        L = port()
+        L.port_ts_state_size.restype = C.c_int
+        L.port_ts_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.port_ts_frame.restype = C.c_int
+        L.port_ts_reset.argtypes = [C.c_void_p]
+        self.L = L
+        self.state = np.zeros(L.port_ts_state_size(), np.uint8)
+        L.port_ts_reset(self.state.ctypes.data)
+
+    def feed(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        padded = np.concatenate([bits, np.zeros(4096, np.uint8)])      # normal mode reads its CRC bytes beyond DFL
+        out = np.zeros(len(bits) // 8 + 2 * 188 + 64, np.uint8)
+        n = self.L.port_ts_frame(self.state.ctypes.data, padded.ctypes.data, len(bits), out.ctypes.data)
+        return None if n < 0 else out[:n].copy()

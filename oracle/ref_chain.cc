@@ -279,6 +279,12 @@ void ref_fec_feed(int n_cells, float* cells) { g_rx->ti->execute(n_cells, reinte
 // stand-alone stage entry points (stage objects of the same instance)
 void ref_demap(int n_cells, float* cells, int plp) { g_rx->ti->qam->execute(n_cells, reinterpret_cast<complex*>(cells), plp, g_rx->l1_post); }
 
+// bb_de_header::execute alone (bb_de_header.cpp:84-445) on one BBFRAME (one byte per bit): its datagram lands in the TS sink
+void ref_bb_deheader(int plp, int len, uint8_t* bits)
+{
+  g_rx->ti->qam->decoder->decoder->deheader->execute(plp, g_rx->l1_post, len, bits);
+}
+
 // cell-deinterleaver permutation the reference built for plp (time_deinterleaver.cpp:174-266)
 int ref_ti_permutation(int plp, int* out, int max)
 {
