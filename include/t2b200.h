@@ -182,6 +182,22 @@ int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx
  * FFTW is a binary-only dependency of the reference: agreement is to <= 1e-5 * max|X| (float64 DFT). */
 int t2b200_fft(t2b200_ctx* ctx, int n, const float* in, int batch, float* out);
 
+/* ---- N1: BBFRAME -> transport stream ---------------------------------------------------------- */
+/* Replaces bb_de_header::execute (bb_de_header.cpp:84-445) for a batch of BBFRAMEs of ONE PLP (the caller applies the
+ * reference's need_plp filter), high-efficiency mode.
+ *   bbframes      uint8[n_frames][k_bch], one byte per bit: what t2b200_ldpc_decode(BCH_DESCRAMBLE) or
+ *                 bch_decoder::execute emit (bch_decoder.cpp:139-160)
+ *   ts_out        the datagrams the reference would send (bb_de_header.cpp:431-441), back to back
+ *   datagram_len  int32[n_frames] or NULL: bytes of each frame's datagram (0 for a dropped frame)
+ *   status        int32[n_frames] or NULL: 0 ok; 1 header CRC-8 error (dropped, :108-113); 2 SYNCD == 65535 (dropped,
+ *                 :160-163); 3 normal-mode frame: NOT handled here (the reference's normal-mode path reads its CRC bytes
+ *                 outside DFL): the frame is skipped and must go to the host bb_de_header
+ *   total_out     bytes written to ts_out, or NULL (then the call stays asynchronous for device buffers)
+ * The packet phase and the held-back tail (< 188 bytes) persist per PLP between calls; t2b200_ts_reset clears them. */
+int t2b200_ts_reset(t2b200_ctx* ctx, int plp);
+int t2b200_ts_packetize(t2b200_ctx* ctx, int plp, const uint8_t* bbframes, int n_frames, int k_bch,
+                        uint8_t* ts_out, size_t ts_cap, int32_t* datagram_len, int32_t* status, long long* total_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ void t2_ldpc_free(t2b200_ctx* ctx);
 void t2_fft_free(t2b200_ctx* ctx);
 void t2_eq_free(t2b200_ctx* ctx);
 void t2_ti_free(t2b200_ctx* ctx);
+void t2_ts_free(t2b200_ctx* ctx);
 
 bool t2_is_device_ptr(const void* p)
 {
@@ -112,6 +113,7 @@ void t2b200_destroy(t2b200_ctx* ctx)
   t2_fft_free(ctx);
   t2_eq_free(ctx);
   t2_ti_free(ctx);
+  t2_ts_free(ctx);
   if (ctx->d_prbs) cudaFree(ctx->d_prbs);
   if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
   for (auto& s : ctx->dev) if (s.p) cudaFree(s.p);
@@ -156,3 +158,4 @@ long long t2b200_launch_count(const t2b200_ctx* ctx) { return ctx ? ctx->launche
 __attribute__((weak)) void t2_fft_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_eq_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_ti_free(t2b200_ctx*) {}
+__attribute__((weak)) void t2_ts_free(t2b200_ctx*) {}

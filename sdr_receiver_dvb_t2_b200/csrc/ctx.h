@@ -12,6 +12,7 @@ struct LdpcDeviceCode;   // ldpc.cu
 struct FftPlan;          // fft.cu
 struct SymbolTables;     // equalizer.cu
 struct TiDemapState;     // demap.cu
+struct TsState;          // ts.cu
 
 struct Scratch {
   void* p = nullptr; size_t cap = 0; bool pinned_host = false;
@@ -34,6 +35,7 @@ struct t2b200_ctx {
   std::map<int, FftPlan*> fft;                // by log2 n
   SymbolTables* sym[3] = {nullptr, nullptr, nullptr};
   TiDemapState* ti = nullptr;
+  TsState* ts = nullptr;
   // staging scratch, grown on demand
   Scratch dev[16];
   Scratch pin[8];

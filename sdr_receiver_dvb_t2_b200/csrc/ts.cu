@@ -1,0 +1,248 @@
+// N1: BBFRAME -> MPEG transport stream re-packetiser on the GPU, high-efficiency mode.
+//
+// Reference semantics reproduced (bb_de_header.cpp, paths relative to the reference's src/DVB_T2):
+//   :70-82,101-113  CRC-8 of the 80 header bits: residue 0xAB => HEM, 0 => normal mode, else the frame is dropped
+//   :136-163        DFL, SYNCD (bits); SYNCD == 65535 => frame dropped
+//   :332-428        HEM: 187-byte user packets on air, 0x47 re-inserted in front of each; bytes are emitted while at
+//                   least 188 bytes of data field remain, the rest (< 188 bytes, with the sync byte if a packet
+//                   boundary falls inside) is held back and opens the NEXT frame's datagram, completed by SYNCD / 8
+//                   bytes of that frame (equal / longer / shorter SYNCD: :341-382, 0xF0 fill in the last case)
+//   :431-441        one BBFRAME = one datagram
+// The reference walks the frame bit by bit; here the only serial part is the packet phase carried from frame to
+// frame: a one-thread scan over 12-byte header records turns every frame into a descriptor (where its datagram
+// starts, which bit ranges feed it, where the sync bytes fall), and one CTA per frame then builds the datagram
+// with one thread per output byte.  Normal-mode frames are reported (status 3) and left to the host
+// bb_de_header: the reference's normal-mode path reads its CRC bytes outside DFL and is not reproducible as such.
+#include "ctx.h"
+#include <algorithm>
+
+namespace {
+
+constexpr int PKT = 188;
+
+struct TsHdr { int status, dfl, syncd; };              // status: 0 HEM ok, 1 header CRC, 2 SYNCD == 65535, 3 normal mode
+struct TsDesc {
+  long long out_off; int out_len;
+  int carry_len, carry_src, carry_bit, carry_sync;     // carry_src: frame index, -1 = state buffer of the previous call
+  int head_n, head_f0;
+  int main_bit, main_n, main_phase;
+};
+struct TsDevState {                                    // survives between calls (device memory)
+  int split, idx_packet, idx_buffer, pad;
+  long long total;                                     // bytes emitted by the last call
+  int tail_src, tail_bit, tail_ndata, tail_sync;       // where the held-back bytes of the last call live
+  uint8_t buffer[PKT + 4];
+};
+
+__device__ __forceinline__ unsigned field(const uint8_t* b, int n)
+{
+  unsigned v = 0;
+  for (int i = 0; i < n; ++i) v = (v << 1) | (b[i] & 1u);
+  return v;
+}
+
+__global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames, int k_bch, TsHdr* __restrict__ hdr)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const uint8_t* b = frames + (size_t)f * k_bch;
+  unsigned reg = 0;                                      // bb_de_header.cpp:70-82
+  for (int i = 0; i < 80; ++i) {
+    const unsigned bit = (b[i] ^ reg) & 1u;
+    reg >>= 1;
+    if (bit) reg ^= 0xABu;
+  }
+  TsHdr h;
+  h.dfl = (int)field(b + 32, 16);
+  h.syncd = (int)field(b + 56, 16);
+  h.status = reg == 0xABu ? 0 : reg == 0u ? 3 : 1;
+  if (h.status == 0 && h.syncd == 65535) h.status = 2;
+  hdr[f] = h;
+}
+
+__global__ void ts_scan_kernel(const TsHdr* __restrict__ hdr, int n_frames, TsDesc* __restrict__ desc,
+                               TsDevState* __restrict__ st, int32_t* __restrict__ dlen, int32_t* __restrict__ status)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  int split = st->split, idx_packet = st->idx_packet, idx_buffer = st->idx_buffer;
+  int tail_src = -1, tail_bit = 0, tail_ndata = 0, tail_sync = -1;   // the carried bytes of a previous call sit in st->buffer
+  long long off = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const TsHdr h = hdr[f];
+    TsDesc d;
+    d.out_off = off; d.out_len = 0; d.carry_len = 0; d.carry_src = -1; d.carry_bit = 0; d.carry_sync = -1;
+    d.head_n = 0; d.head_f0 = 0; d.main_bit = 0; d.main_n = 0; d.main_phase = 0;
+    if (status) status[f] = h.status;
+    if (h.status == 0) {
+      int in_bit = 80, dfl = h.dfl;
+      if (split) {
+        split = 0;
+        d.carry_src = tail_src; d.carry_bit = tail_bit; d.carry_sync = tail_sync;
+        d.carry_len = idx_buffer;
+        const int missing = PKT - idx_packet, sb = h.syncd / 8;
+        if (missing <= sb) {
+          d.head_n = missing;
+          in_bit += missing == sb ? missing * 8 : h.syncd;
+        } else {
+          d.head_n = sb; d.head_f0 = missing - sb;
+          in_bit += sb * 8;
+        }
+        idx_packet = PKT;
+      } else {
+        in_bit += h.syncd;
+      }
+      dfl -= h.syncd;
+      int T = 0;
+      if (dfl >= PKT * 8) {
+        const int M = (dfl - PKT * 8) / 8 + 1;
+        const int phase = idx_packet == PKT ? 0 : idx_packet;
+        if (phase == 0) T = M + (M + PKT - 2) / (PKT - 1);
+        else if (M <= PKT - phase) T = M;
+        else T = M + (M - (PKT - phase) + PKT - 2) / (PKT - 1);
+        d.main_bit = in_bit; d.main_n = M; d.main_phase = phase;
+        in_bit += 8 * M; dfl -= 8 * M;
+        idx_packet = (phase + T) % PKT;
+        if (idx_packet == 0) idx_packet = PKT;
+      }
+      if (dfl > 0) {                                     // held back for the next frame (bb_de_header.cpp:386-402)
+        split = 1;
+        const int ntail = dfl / 8;
+        tail_src = f; tail_bit = in_bit; tail_ndata = ntail; tail_sync = -1;
+        if (idx_packet == PKT) { if (ntail > 0) tail_sync = 0; }
+        else if (idx_packet != 0 && PKT - idx_packet < ntail) tail_sync = PKT - idx_packet;
+        if (tail_sync >= 0) idx_packet = 1 + (ntail - tail_sync); else idx_packet += ntail;
+        idx_buffer = ntail + (tail_sync >= 0 ? 1 : 0);
+      }
+      d.out_len = d.carry_len + d.head_n + d.head_f0 + T;
+    }
+    desc[f] = d;
+    if (dlen) dlen[f] = d.out_len;
+    off += d.out_len;
+  }
+  st->split = split; st->idx_packet = idx_packet; st->idx_buffer = idx_buffer; st->total = off;
+  st->tail_src = tail_src; st->tail_bit = tail_bit; st->tail_ndata = tail_ndata; st->tail_sync = tail_sync;
+}
+
+__device__ __forceinline__ uint8_t gather8(const uint8_t* __restrict__ bits)
+{
+  unsigned v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v = (v << 1) | (bits[i] & 1u);
+  return (uint8_t)v;
+}
+
+// carried byte j of a tail that lives in `frame` (sync byte inserted at index `sync`)
+__device__ __forceinline__ uint8_t tail_byte(const uint8_t* __restrict__ frame, int bit, int sync, int j)
+{
+  if (j == sync) return 0x47;
+  const int idx = j - (sync >= 0 && j > sync ? 1 : 0);
+  return gather8(frame + bit + 8 * idx);
+}
+
+__global__ void __launch_bounds__(256) ts_assemble_kernel(const uint8_t* __restrict__ frames, int k_bch,
+                                                          const TsDesc* __restrict__ desc, const uint8_t* __restrict__ carry0,
+                                                          uint8_t* __restrict__ out, long long cap)
+{
+  const TsDesc d = desc[blockIdx.x];
+  const uint8_t* me = frames + (size_t)blockIdx.x * k_bch;
+  const int c1 = d.carry_len, c2 = c1 + d.head_n, c3 = c2 + d.head_f0;
+  for (int j = threadIdx.x; j < d.out_len; j += blockDim.x) {
+    uint8_t v;
+    if (j < c1) v = d.carry_src >= 0 ? tail_byte(frames + (size_t)d.carry_src * k_bch, d.carry_bit, d.carry_sync, j) : carry0[j];
+    else if (j < c2) v = gather8(me + 80 + 8 * (j - c1));
+    else if (j < c3) v = 0xF0;
+    else {
+      const int jj = j - c3, t = d.main_phase + jj;
+      if (t % PKT == 0) v = 0x47;
+      else {
+        const int nsync = t / PKT + (d.main_phase == 0 ? 1 : 0);
+        v = gather8(me + d.main_bit + 8 * (jj - nsync));
+      }
+    }
+    if (d.out_off + j < cap) out[d.out_off + j] = v;
+  }
+}
+
+// keep the held-back bytes of the call's last frame for the next call
+__global__ void ts_save_tail_kernel(const uint8_t* __restrict__ frames, int k_bch, TsDevState* __restrict__ st)
+{
+  if (!st->split || st->tail_src < 0) return;            // nothing new held back (an older tail stays where it is)
+  const int n = st->tail_ndata + (st->tail_sync >= 0 ? 1 : 0);
+  for (int j = threadIdx.x; j < n; j += blockDim.x)
+    st->buffer[j] = tail_byte(frames + (size_t)st->tail_src * k_bch, st->tail_bit, st->tail_sync, j);
+}
+
+}  // namespace
+
+struct TsState { std::map<int, TsDevState*> plp; };
+
+void t2_ts_free(t2b200_ctx* ctx)
+{
+  if (!ctx->ts) return;
+  for (auto& kv : ctx->ts->plp) cudaFree(kv.second);
+  delete ctx->ts;
+  ctx->ts = nullptr;
+}
+
+static int ts_state(t2b200_ctx* ctx, int plp, TsDevState** out)
+{
+  if (!ctx->ts) ctx->ts = new TsState();
+  auto it = ctx->ts->plp.find(plp);
+  if (it == ctx->ts->plp.end()) {
+    TsDevState* d;
+    T2_CUDA(ctx, cudaMalloc(&d, sizeof(TsDevState)));
+    T2_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(TsDevState), ctx->stream));
+    it = ctx->ts->plp.emplace(plp, d).first;
+  }
+  *out = it->second;
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_ts_reset(t2b200_ctx* ctx, int plp)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  TsDevState* st; int rc;
+  if ((rc = ts_state(ctx, plp, &st))) return rc;
+  T2_CUDA(ctx, cudaMemsetAsync(st, 0, sizeof(TsDevState), ctx->stream));
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_ts_packetize(t2b200_ctx* ctx, int plp, const uint8_t* bbframes, int n_frames, int k_bch,
+                                   uint8_t* ts_out, size_t ts_cap, int32_t* datagram_len, int32_t* status,
+                                   long long* total_out)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (!bbframes || n_frames < 0 || k_bch < 80 + PKT * 8 || k_bch > 65535 || !ts_out) { ctx->err = "t2b200_ts_packetize: bad argument"; return T2B200_ERR_ARG; }
+  if (total_out) *total_out = 0;
+  if (n_frames == 0) return T2B200_OK;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  TsDevState* st; int rc;
+  if ((rc = ts_state(ctx, plp, &st))) return rc;
+  const void* din; void *dout, *dlen = nullptr, *dstat = nullptr, *dhdr, *ddesc;
+  if ((rc = t2_to_device(ctx, 0, bbframes, (size_t)n_frames * k_bch, &din))) return rc;
+  if ((rc = t2_out_device(ctx, 1, ts_out, ts_cap, &dout))) return rc;
+  if (datagram_len && (rc = t2_out_device(ctx, 2, datagram_len, 4 * (size_t)n_frames, &dlen))) return rc;
+  if (status && (rc = t2_out_device(ctx, 3, status, 4 * (size_t)n_frames, &dstat))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 9, sizeof(TsHdr) * (size_t)n_frames, &dhdr))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 10, sizeof(TsDesc) * (size_t)n_frames, &ddesc))) return rc;
+  ts_parse_kernel<<<(n_frames + 127) / 128, 128, 0, ctx->stream>>>((const uint8_t*)din, n_frames, k_bch, (TsHdr*)dhdr);
+  T2_CUDA(ctx, cudaGetLastError());
+  ts_scan_kernel<<<1, 32, 0, ctx->stream>>>((const TsHdr*)dhdr, n_frames, (TsDesc*)ddesc, st, (int32_t*)dlen, (int32_t*)dstat);
+  T2_CUDA(ctx, cudaGetLastError());
+  ts_assemble_kernel<<<n_frames, 256, 0, ctx->stream>>>((const uint8_t*)din, k_bch, (const TsDesc*)ddesc, st->buffer,
+                                                        (uint8_t*)dout, (long long)ts_cap);
+  T2_CUDA(ctx, cudaGetLastError());
+  ts_save_tail_kernel<<<1, 256, 0, ctx->stream>>>((const uint8_t*)din, k_bch, st);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 4;
+  if (total_out) {
+    T2_CUDA(ctx, cudaMemcpyAsync(total_out, &st->total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((size_t)*total_out > ts_cap) { ctx->err = "t2b200_ts_packetize: ts_out too small"; return T2B200_ERR_ARG; }
+  }
+  if ((rc = t2_finish_out(ctx, ts_out, dout, total_out ? (size_t)*total_out : ts_cap))) return rc;
+  if (datagram_len && (rc = t2_finish_out(ctx, datagram_len, dlen, 4 * (size_t)n_frames))) return rc;
+  if (status && (rc = t2_finish_out(ctx, status, dstat, 4 * (size_t)n_frames))) return rc;
+  return T2B200_OK;
+}

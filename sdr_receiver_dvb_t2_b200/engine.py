@@ -28,6 +28,7 @@ SYMBOLS = [
     't2b200_ldpc_decode', 't2b200_bch_descramble',
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
     't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
+    't2b200_ts_reset', 't2b200_ts_packetize',
 ]
 
 
@@ -72,6 +73,8 @@ def lib():
     L.t2b200_eq_configure.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float]
     L.t2b200_equalize.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.t2b200_fft.argtypes = [vp, i32, vp, i32, vp]
+    L.t2b200_ts_reset.argtypes = [vp, i32]
+    L.t2b200_ts_packetize.argtypes = [vp, i32, vp, i32, i32, vp, C.c_size_t, vp, vp, C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -213,6 +216,21 @@ class Engine:
         self._chk(self.L.t2b200_demap(self.h, _ptr(ti_cells), len(nf), _ptr(nf), mod, rotation, fec_type, code_rate,
                                       _ptr(llr), _ptr(snr), _ptr(prec), _ptr(precision_in)))
         return {'llr': llr, 'snr': snr, 'precision': prec}
+
+    # ---- N1: BBFRAME -> TS ----
+    def ts_reset(self, plp=0):
+        self._chk(self.L.t2b200_ts_reset(self.h, plp))
+
+    def ts_packetize(self, bbframes, plp=0):
+        """bbframes uint8[n][k_bch] (one byte per bit; numpy / torch cuda) -> (ts bytes, datagram_len[n], status[n])"""
+        n, k_bch = bbframes.shape
+        cap = n * (k_bch // 8 + 2 * 188)
+        ts = _like(bbframes, (cap,), np.uint8)
+        dl, st = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        total = C.c_longlong(0)
+        self._chk(self.L.t2b200_ts_packetize(self.h, plp, _ptr(bbframes), n, k_bch, _ptr(ts), cap, _ptr(dl), _ptr(st),
+                                             C.byref(total)))
+        return ts[:total.value], dl, st
 
     # ---- K1 ----
     def fft(self, x, out=None):
