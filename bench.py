@@ -165,6 +165,35 @@ def cpu_reference_rate(seconds_budget=12.0, sample=None):
                                   % (per_thread, EBN0_DB, ncpu, dt)}
 
 
+def cpu_reference_front_stages(frame_time):
+    """Single-core time of the reference's OTHER stages (FFTW FFT, equaliser, TI + demapper; oracle/_ref/libref_chain.so,
+    compiled from the unmodified sources) on one C32 T2 frame: context for the LDPC-only CPU number, which leaves them out.
+    Returns ms per frame per stage, or None when the compiled reference is not on this box."""
+    import numpy as np
+    from oracle import pyoracle as O
+    if not O.have_ref('libref_chain.so'):
+        return None
+    rx = O.RefRx('32K', True, 7, '1/128', 59)
+    L = frame_time.shape[0]
+    t0 = time.perf_counter()
+    freq = [rx.fft(frame_time[i]) for i in range(L)]
+    t_fft = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cells = [rx.p2_symbol(freq[0])[0]] + [rx.data_symbol(i, freq[i])[0] for i in range(1, L)]
+    t_eq = time.perf_counter() - t0
+    fec = O.RefFec(rx, [dict(id=0, cod=2, mod=3, rot=1, fec=1, blocks_max=68, ti_len=3, ti_type=0)], 360)
+    fec.chain(after_ti=True, after_demap=False, after_ldpc=False, after_bch=False)
+    t0 = time.perf_counter()
+    fec.feed_p2([0], [FEC_PER_FRAME], cells[0])
+    for c in cells[1:]:
+        fec.feed(c)
+    t_fec = time.perf_counter() - t0
+    return {'fft_ms': 1e3 * t_fft, 'equalize_ms': 1e3 * t_eq, 'ti_demap_ms': 1e3 * t_fec, 'frames': 1,
+            'codewords_per_frame': FEC_PER_FRAME,
+            'note': 'one core, one C32 frame (60 symbols, 202 FECFRAMEs) through the compiled reference stages; the LDPC '
+                    'number above does not include them'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -310,6 +339,24 @@ def run_t2b200(args):
         ldpc_ms = k0.elapsed_time(k1) / 5
         sample_llr = llr[:256].cpu().numpy()
 
+        # ---- N1: BBFRAME bits -> TS datagrams, on the decoded bits of this batch ----
+        ts_ms, ts_bytes = None, 0
+        try:
+            eng.ts_reset(0)
+            tsb, _, tst = eng.ts_packetize(out_bits)
+            ts_bytes = int(tsb.shape[0])
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record(stream)
+            for _ in range(3):
+                eng.ts_packetize(out_bits)
+            t1e.record(stream)
+            stream.synchronize()
+            ts_ms = t0e.elapsed_time(t1e) / 3
+            ts_ok = float((torch.as_tensor(tst) == 0).float().mean().item())
+        except Exception as e:  # reported, never required for the headline number
+            ts_ok = 0.0
+            print('ts_packetize failed: %s' % e, file=sys.stderr)
+
         # ---- SURVEY 8e scatter / gather variant (N > 1): rank 0 holds the LLRs of a pooled batch, every rank decodes a
         # shard of whole 32-codeword groups, bits return to rank 0 over NCCL point-to-point ----
         sg = None
@@ -409,6 +456,10 @@ def run_t2b200(args):
         try:
             v, info = cpu_reference_rate(seconds_budget=12.0, sample=sample_llr)
             cpu = dict(info, value=v, unit='codewords/s')
+            try:
+                cpu['other_stages_1core'] = cpu_reference_front_stages(clean[0])
+            except Exception as e:
+                cpu['other_stages_1core'] = 'failed: %s' % e
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu = {'value': None, 'unit': 'codewords/s', 'cores': 0, 'kind': 'port', 'sample': 'failed: %s' % e}
         # algorithmic bytes per frame of every stage and the HBM fraction each reaches
@@ -442,6 +493,9 @@ def run_t2b200(args):
             'gpu_launches': int(launches),
             'stages': stages,
             'ldpc_only': {'value': cw_step / (ldpc_ms * 1e-3), 'unit': 'codewords/s', 'ms': ldpc_ms},
+            'ts_packetize': {'ms': ts_ms, 'ts_bytes': ts_bytes, 'frames_ok': ts_ok,
+                             'gb_s': (cw_step * CODE_KBCH + ts_bytes) / (ts_ms * 1e-3) / 1e9 if ts_ms else None,
+                             'note': 'N1: HEM BBFRAME bits (byte per bit) -> TS datagrams on the GPU, incl. D2H of lengths'},
             'reference_exact_cast': {'ms_per_step': exact_ms, 'codewords_per_s': cw_step / (exact_ms * 1e-3),
                                      'converged_fraction': exact_conv,
                                      'note': 'wrapping cast: every group runs 25 trials and is dropped, as in the reference'},
