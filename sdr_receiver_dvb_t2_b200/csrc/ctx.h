@@ -50,6 +50,10 @@ struct t2b200_ctx {
     }                                                                                 \
   } while (0)
 
+// The LDPC decoder asks for the largest shared-memory carve-out: two resident decoders then leave 81 KB of shared memory
+// (next to a quarter of the registers and 1 280 threads) on which the streaming kernels of another stream run.
+#define T2_CARVEOUT(kernel) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+
 // true if p is device-accessible memory of this process (device or managed)
 bool t2_is_device_ptr(const void* p);
 // grow-on-demand scratch; slot identifies the user

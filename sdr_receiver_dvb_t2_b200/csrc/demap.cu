@@ -130,7 +130,7 @@ __global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockD
 // associatively, and one CTA scans 8192 elements per pass.  The (rare: ~40 per TI block) additions that carry
 // s into the next binade are found by the scan, executed as one real float addition, and the scan resumes
 // behind them.  tools/ordered_sum_model.py is the bit-level model this kernel follows.
-constexpr int kSumThreads = 1024, kSumE = 8, kSumChunk = kSumThreads * kSumE;
+constexpr int kSumThreads = 512, kSumE = 8, kSumChunk = kSumThreads * kSumE;   // <= 32 registers x 512 threads: fits next to a resident LDPC decoder
 constexpr int kSumSerialHead = 768;        // the sums double every few cells at first: no point scanning there
 constexpr int kSumSat = 1 << 26;           // deltas saturate far above 2^24 (= "left the binade")
 
@@ -164,7 +164,7 @@ __device__ __forceinline__ int sum_apply(int S, uint32_t w)
 }
 
 template <int MOD>
-__global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const float2* __restrict__ terms,
+__global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const float2* __restrict__ terms,
                                                                          const DemapBlockDesc* __restrict__ blocks,
                                                                          float* __restrict__ precision, float* __restrict__ snr,
                                                                          const float* __restrict__ precision_in)
@@ -196,17 +196,15 @@ __global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const fl
     }
     const int S0 = (int)((b0 & 0x7fffffu) | 0x800000u), S1 = (int)((b1 & 0x7fffffu) | 0x800000u);
     const int m = min(kSumChunk, n - base);
-    uint32_t w0[kSumE], w1[kSumE];
     int x00 = 0, x01 = 1, x10 = 0, x11 = 1;                       // pseudo-S started even / odd, per sum
 #pragma unroll
     for (int i = 0; i < kSumE; ++i) {
       const int k = tid * kSumE + i;
       float2 v = make_float2(0.0f, 0.0f);
       if (k < m) v = __ldg(t + base + k);
-      w0[i] = sum_elem(es0, __float_as_uint(v.x));
-      w1[i] = sum_elem(es1, __float_as_uint(v.y));
-      x00 = sum_apply(x00, w0[i]); x01 = sum_apply(x01, w0[i]);
-      x10 = sum_apply(x10, w1[i]); x11 = sum_apply(x11, w1[i]);
+      const uint32_t w0 = sum_elem(es0, __float_as_uint(v.x)), w1 = sum_elem(es1, __float_as_uint(v.y));
+      x00 = sum_apply(x00, w0); x01 = sum_apply(x01, w0);
+      x10 = sum_apply(x10, w1); x11 = sum_apply(x11, w1);
     }
     SumPair p0 = {x00, x01 - 1}, p1 = {x10, x11 - 1};
     // inclusive scan inside the warp, warp totals through shared memory
@@ -224,7 +222,9 @@ __global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const fl
     if (lane == 0) { e0.a0 = e0.a1 = 0; e1.a0 = e1.a1 = 0; }
     __syncthreads();
     if (warp == 0) {                                             // exclusive scan of the warp totals
-      SumPair t0 = wt[0][lane], t1 = wt[1][lane];
+      constexpr int NWARP = kSumThreads / 32;
+      SumPair t0 = {0, 0}, t1 = {0, 0};
+      if (lane < NWARP) { t0 = wt[0][lane]; t1 = wt[1][lane]; }
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         SumPair o0, o1;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const fl
       x0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, 1); x0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, 1);
       x1.a0 = __shfl_up_sync(0xffffffffu, t1.a0, 1); x1.a1 = __shfl_up_sync(0xffffffffu, t1.a1, 1);
       if (lane == 0) { x0.a0 = x0.a1 = 0; x1.a0 = x1.a1 = 0; }
-      wt[0][lane] = x0; wt[1][lane] = x1;
+      if (lane < NWARP) { wt[0][lane] = x0; wt[1][lane] = x1; }
     }
     __syncthreads();
     const SumPair q0 = sum_compose(wt[0][warp], e0), q1 = sum_compose(wt[1][warp], e1);
@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(kSumThreads) demap_ordered_sum_kernel(const fl
 #pragma unroll
       for (int i = 0; i < kSumE; ++i) {
         if (my_cross == INT_MAX && tid * kSumE + i < m) {
-          const int na = sum_apply(Sa, w0[i]), nb = sum_apply(Sb, w1[i]);
+          const float2 v = __ldg(t + base + tid * kSumE + i);     // second read of the thread's own 64 bytes: an L1 hit
+          const int na = sum_apply(Sa, sum_elem(es0, __float_as_uint(v.x))), nb = sum_apply(Sb, sum_elem(es1, __float_as_uint(v.y)));
           if (na >= (1 << 24) || nb >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; Sb_before = Sb; }
           else { Sa = na; Sb = nb; }
         }

@@ -14,6 +14,7 @@
 // laid out [element][17] so that stage accesses and tile loads / stores are bank-conflict free.
 #include "ctx.h"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 struct FftPlan {

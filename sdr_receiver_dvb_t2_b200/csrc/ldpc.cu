@@ -335,8 +335,14 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
 
 // co-resident CTAs per SM the register budget is cut for (65536 / (384 * MINB) registers per thread)
 
+// Register budget: 64 per thread for the codes whose check nodes fit (two CTAs = 49 152 registers, 146 KB of shared memory
+// and 768 threads per SM), so that a quarter of every SM's register file, 81 KB of shared memory and 1 280 threads stay
+// free: the streaming kernels of the OTHER stream (FFT, equaliser, de-interleaver, demapper: all <= 16 384 registers per
+// CTA) run underneath a resident decoder instead of waiting for it.
+template <int CNL> constexpr int kLdpcRegs = CNL <= 13 ? 64 : 80;
+
 template <int CNL, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
+__global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
 {
   using LY = CnLayout<CNL>;
   constexpr int NS = LY::NS;
@@ -538,6 +544,8 @@ cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
   auto k = ldpc_decode_kernel<CNL, MINB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  // largest shared-memory carve-out: what the two resident decoders leave over can hold the other stream's kernels
+  T2_CARVEOUT(k);
   if (p.group_lanes > 1) {     // lock-step lanes spin on each other: they must be co-resident
     void* args[] = {(void*)&p};
     return cudaLaunchCooperativeKernel((void*)k, dim3(grid), dim3(kThreads), args, smem, st);
@@ -560,18 +568,13 @@ const int kCnlBuckets[] = {4, 5, 7, 8, 9, 11, 12, 13, 16, 17, 20};
 
 // (CNL bucket, register budget) instantiations: minb = co-resident CTAs per SM the register allocation is cut for
 #define DISPATCH(CALL)                                                                    \
-  switch (cnl * 4 + minb) {                                                               \
-    case 4 * 4 + 2:  return CALL(4, uint32_t, 2);   case 4 * 4 + 3:  return CALL(4, uint32_t, 3);   \
-    case 5 * 4 + 2:  return CALL(5, uint32_t, 2);   case 5 * 4 + 3:  return CALL(5, uint32_t, 3);   \
-    case 7 * 4 + 2:  return CALL(7, uint32_t, 2);   case 7 * 4 + 3:  return CALL(7, uint32_t, 3);   \
-    case 8 * 4 + 2:  return CALL(8, uint32_t, 2);   case 8 * 4 + 3:  return CALL(8, uint32_t, 3);   \
-    case 9 * 4 + 2:  return CALL(9, uint32_t, 2);   case 9 * 4 + 3:  return CALL(9, uint32_t, 3);   \
-    case 11 * 4 + 2: return CALL(11, uint32_t, 2);  case 11 * 4 + 3: return CALL(11, uint32_t, 3);  \
-    case 12 * 4 + 2: return CALL(12, uint32_t, 2);  case 12 * 4 + 3: return CALL(12, uint32_t, 3);  \
-    case 13 * 4 + 2: return CALL(13, uint32_t, 2);  case 13 * 4 + 3: return CALL(13, uint32_t, 3);  \
-    case 16 * 4 + 1: return CALL(16, uint64_t, 1);  case 16 * 4 + 2: return CALL(16, uint64_t, 2);  \
-    case 17 * 4 + 1: return CALL(17, uint64_t, 1);  case 17 * 4 + 2: return CALL(17, uint64_t, 2);  \
-    case 20 * 4 + 1: return CALL(20, uint64_t, 1);  case 20 * 4 + 2: return CALL(20, uint64_t, 2);  \
+  switch (cnl) {                                                                          \
+    case 4:  return CALL(4, uint32_t, 2);   case 5:  return CALL(5, uint32_t, 2);         \
+    case 7:  return CALL(7, uint32_t, 2);   case 8:  return CALL(8, uint32_t, 2);         \
+    case 9:  return CALL(9, uint32_t, 2);   case 11: return CALL(11, uint32_t, 2);        \
+    case 12: return CALL(12, uint32_t, 2);  case 13: return CALL(13, uint32_t, 2);        \
+    case 16: return CALL(16, uint64_t, 2);  case 17: return CALL(17, uint64_t, 2);        \
+    case 20: return CALL(20, uint64_t, 2);                                                \
     default: return cudaErrorInvalidValue;                                                \
   }
 
@@ -633,10 +636,6 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
   T2_CUDA(ctx, cudaMemcpy(d->d_level, level.data(), level.size(), cudaMemcpyHostToDevice));
   p.level = d->d_level;
   d->minb = 2;
-  if (const char* e = getenv("T2B200_LDPC_MINB")) {          // development aid: pick the register-budget variant
-    const int v = atoi(e);
-    if (d->cnl <= 13 ? (v == 2 || v == 3) : (v == 1 || v == 2)) d->minb = v;
-  }
   T2_CUDA(ctx, occupancy_dispatch(d->cnl, d->minb, d->smem, &d->blocks_per_sm));
   if (d->blocks_per_sm < 1) { ctx->err = "LDPC kernel does not fit on an SM"; return T2B200_ERR_CUDA; }
   ctx->ldpc[code] = d;
