@@ -21,6 +21,9 @@ class FrameChain:
         import torch
         self.torch = torch
         self.eng, self.t, self.p = eng, tables, tables['p']
+        # the glue between the stages is torch copies: the engine must run on the stream they run on (calls are
+        # asynchronous).  Call the chain under the torch stream that was current here.
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
         p = self.p
         self.mod, self.cod, self.fec_type, self.rot, self.plp = mod, cod, fec_type, rotation, plp
         self.nbits = 64800 if fec_type else 16200
@@ -86,8 +89,8 @@ class FrameChain:
         # frame cell stream: P2 cells | data symbols | FC
         per_frame = p['c_p2'] + self.n_data_sym * p['c_data'] + (p['n_fc'] if p['l_fc'] else 0)
         cells = self._buf('cells', (F, per_frame), torch.complex64)
-        sro = np.zeros((F, L), np.float32)
-        ph = np.zeros((F, L), np.float32)
+        sro = torch.zeros((F, L), dtype=torch.float32, device=cells.device)
+        ph = torch.zeros((F, L), dtype=torch.float32, device=cells.device)
         # P2 symbols of all frames in one launch, data symbols of all frames in one launch (strided views are
         # materialised once: the equaliser wants [n][fft_size] / writes [n][n_out] contiguous)
         p2f = freq3[:, 0, :].contiguous()
@@ -127,10 +130,15 @@ class FrameChain:
             r['llr'], r['ti'] = d['llr'], ti
         return r
 
-    def decode_frames(self, time, **kw):
+    def decode_frames(self, time, host_feedback=True, **kw):
+        """host_feedback=False leaves sro / phase / snr / precision on the device: nothing in the call waits for the GPU"""
         stream, sro, ph = self.demodulate(time)
         r = self.fec(stream, **kw)
         r['sro'], r['phase'] = sro, ph
+        if host_feedback:
+            self.eng.sync()                                   # the engine's stream need not be torch's current stream
+            for k in ('sro', 'phase', 'snr', 'precision'):
+                r[k] = r[k].cpu().numpy()
         return r
 
 

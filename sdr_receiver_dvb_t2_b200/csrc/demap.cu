@@ -442,7 +442,7 @@ extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cel
                                                          (const TiBlockDesc*)ddesc, p.rows, p.cells_per_fec);
   T2_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
-  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the host descriptor vector goes out of scope
+  // (the descriptor upload above is a pageable-memory copy: the runtime has consumed the host vector when it returns)
   return t2_finish_out(ctx, cells_out, dout, (size_t)off * 8);
 }
 
@@ -529,6 +529,8 @@ extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, c
   // the reference derotates its input in place (llr_demapper.cpp:555-557): mirror that for host buffers too
   if (!cells_on_dev && rotation)
     T2_CUDA(ctx, cudaMemcpyAsync(ti_cells, dcells, (size_t)off * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // host outputs must be filled when the call returns; with device buffers everywhere the call stays asynchronous
+  const bool any_host = !cells_on_dev || (snr_out && !t2_is_device_ptr(snr_out)) || (precision_out && !t2_is_device_ptr(precision_out));
+  if (any_host) T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return t2_finish_out(ctx, llr_out, dllr, (size_t)fec * fec_bits);
 }

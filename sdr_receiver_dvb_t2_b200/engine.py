@@ -209,8 +209,8 @@ class Engine:
         nf = np.ascontiguousarray(n_fec_per_block, np.int32)
         n_fec, nbits = int(nf.sum()), (64800 if fec_type else 16200)
         llr = _like(ti_cells, (n_fec, nbits), np.int8)
-        snr = np.zeros(len(nf), np.float32)
-        prec = np.zeros(len(nf), np.float32)
+        snr = _like(ti_cells, (len(nf),), np.float32)          # device buffers in, device buffers out: the call stays asynchronous
+        prec = _like(ti_cells, (len(nf),), np.float32)
         if precision_in is not None:
             precision_in = np.ascontiguousarray(precision_in, np.float32)
         self._chk(self.L.t2b200_demap(self.h, _ptr(ti_cells), len(nf), _ptr(nf), mod, rotation, fec_type, code_rate,
@@ -257,7 +257,7 @@ class Engine:
         idx = np.ascontiguousarray(idx_symbol, np.int32)
         n = len(idx)
         cells = out if out is not None else _like(freq, (n, n_out), np.complex64)
-        sro, ph = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        sro, ph = _like(freq, (n,), np.float32), _like(freq, (n,), np.float32)
         self._chk(self.L.t2b200_equalize(self.h, kind, n, _ptr(idx), _ptr(freq), _ptr(cells), _ptr(sro), _ptr(ph)))
         return cells, sro, ph
 

@@ -90,7 +90,7 @@ def test_post_fft_chain_bit_exact_c32_256qam(engine):
         llr_o.append(l), prec_o.append(pr)
         off += nf * 8100
     llr_o = np.concatenate(llr_o)
-    assert np.array_equal(r['precision'], np.array(prec_o, np.float32))
+    assert np.array_equal(r['precision'].cpu().numpy(), np.array(prec_o, np.float32))
     assert np.array_equal(r['llr'].cpu().numpy(), llr_o)
     tr, bits_o, _ = O.port_ldpc_decode(2, llr_o[:32], 25)
     assert tr == -1 and (r['trials_left'].cpu().numpy()[:32] == -1).all()         # the reference drops this batch

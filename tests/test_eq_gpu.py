@@ -60,6 +60,7 @@ def test_low_snr_phase_wrap_and_device_buffers(engine):
     d = torch.from_numpy(freq).cuda()
     cells, sro, ph = engine.equalize(1, idx, d)
     engine.sync()
+    sro, ph = sro.cpu().numpy(), ph.cpu().numpy()
     cells = cells.cpu().numpy()
     for s, i in enumerate(idx):
         want, wsro, wph = O.port_equalize(1, freq[s], p['l_nulls'], p['k_total'], maps[i - 1], refs[i - 1],
