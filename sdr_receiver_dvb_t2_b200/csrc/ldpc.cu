@@ -392,8 +392,7 @@ __global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_cons
       const int2* src = reinterpret_cast<const int2*>(p.llr + (size_t)cw * p.N);
       int2* dst = reinterpret_cast<int2*>(post);
       for (int k = tid; k < p.N / 8; k += kThreads) dst[k] = __ldg(src + k);
-      if (tid < 360)
-        for (int k = 0; k < NS * p.q; ++k) __stcg(state + k * 360 + tid, 0u);
+      // (reset(): the check-node words are not cleared in memory -- the first update() reads them as zero)
     }
     __syncthreads();
 
@@ -414,14 +413,15 @@ __global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_cons
       }
       if (!(group_bad && --trials >= 0)) break;
       // ---- one update() ----
+      const bool stored = iters > 0 && tid < 360;                // first pass: all messages are zero, nothing to read
       uint32_t w_next[NS];
 #pragma unroll
-      for (int k = 0; k < NS; ++k) w_next[k] = tid < 360 ? __ldcg(state + k * R + tid) : 0u;
+      for (int k = 0; k < NS; ++k) w_next[k] = stored ? __ldcg(state + k * R + tid) : 0u;
       for (int i = 0; i < p.q; ++i) {
         uint32_t w_cur[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) w_cur[k] = w_next[k];
-        if (tid < 360 && i + 1 < p.q) {
+        if (stored && i + 1 < p.q) {
 #pragma unroll
           for (int k = 0; k < NS; ++k) w_next[k] = __ldcg(state + k * R + (i + 1) * 360 + tid);
         }

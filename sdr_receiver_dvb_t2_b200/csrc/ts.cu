@@ -60,67 +60,85 @@ __global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames
   hdr[f] = h;
 }
 
-__global__ void ts_scan_kernel(const TsHdr* __restrict__ hdr, int n_frames, TsDesc* __restrict__ desc,
-                               TsDevState* __restrict__ st, int32_t* __restrict__ dlen, int32_t* __restrict__ status)
+// One warp: the lanes stage 32 header records in shared memory and write 32 descriptors back; lane 0 walks them.
+__global__ void __launch_bounds__(32) ts_scan_kernel(const TsHdr* __restrict__ hdr, int n_frames, TsDesc* __restrict__ desc,
+                                                     TsDevState* __restrict__ st, int32_t* __restrict__ dlen, int32_t* __restrict__ status)
 {
-  if (blockIdx.x || threadIdx.x) return;
+  __shared__ TsHdr sh[32];
+  __shared__ TsDesc sd[32];
+  const int lane = threadIdx.x;
   int split = st->split, idx_packet = st->idx_packet, idx_buffer = st->idx_buffer;
   int tail_src = -1, tail_bit = 0, tail_ndata = 0, tail_sync = -1;   // the carried bytes of a previous call sit in st->buffer
   long long off = 0;
-  for (int f = 0; f < n_frames; ++f) {
-    const TsHdr h = hdr[f];
-    TsDesc d;
-    d.out_off = off; d.out_len = 0; d.carry_len = 0; d.carry_src = -1; d.carry_bit = 0; d.carry_sync = -1;
-    d.head_n = 0; d.head_f0 = 0; d.main_bit = 0; d.main_n = 0; d.main_phase = 0;
-    if (status) status[f] = h.status;
-    if (h.status == 0) {
-      int in_bit = 80, dfl = h.dfl;
-      if (split) {
-        split = 0;
-        d.carry_src = tail_src; d.carry_bit = tail_bit; d.carry_sync = tail_sync;
-        d.carry_len = idx_buffer;
-        const int missing = PKT - idx_packet, sb = h.syncd / 8;
-        if (missing <= sb) {
-          d.head_n = missing;
-          in_bit += missing == sb ? missing * 8 : h.syncd;
-        } else {
-          d.head_n = sb; d.head_f0 = missing - sb;
-          in_bit += sb * 8;
+  for (int f0 = 0; f0 < n_frames; f0 += 32) {
+    const int nf = min(32, n_frames - f0);
+    if (lane < nf) sh[lane] = hdr[f0 + lane];
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = 0; i < nf; ++i) {
+        const int f = f0 + i;
+        const TsHdr h = sh[i];
+        TsDesc d;
+        d.out_off = off; d.out_len = 0; d.carry_len = 0; d.carry_src = -1; d.carry_bit = 0; d.carry_sync = -1;
+        d.head_n = 0; d.head_f0 = 0; d.main_bit = 0; d.main_n = 0; d.main_phase = 0;
+        if (h.status == 0) {
+          int in_bit = 80, dfl = h.dfl;
+          if (split) {
+            split = 0;
+            d.carry_src = tail_src; d.carry_bit = tail_bit; d.carry_sync = tail_sync;
+            d.carry_len = idx_buffer;
+            const int missing = PKT - idx_packet, sb = h.syncd / 8;
+            if (missing <= sb) {
+              d.head_n = missing;
+              in_bit += missing == sb ? missing * 8 : h.syncd;
+            } else {
+              d.head_n = sb; d.head_f0 = missing - sb;
+              in_bit += sb * 8;
+            }
+            idx_packet = PKT;
+          } else {
+            in_bit += h.syncd;
+          }
+          dfl -= h.syncd;
+          int T = 0;
+          if (dfl >= PKT * 8) {
+            const int M = (dfl - PKT * 8) / 8 + 1;
+            const int phase = idx_packet == PKT ? 0 : idx_packet;
+            if (phase == 0) T = M + (M + PKT - 2) / (PKT - 1);
+            else if (M <= PKT - phase) T = M;
+            else T = M + (M - (PKT - phase) + PKT - 2) / (PKT - 1);
+            d.main_bit = in_bit; d.main_n = M; d.main_phase = phase;
+            in_bit += 8 * M; dfl -= 8 * M;
+            idx_packet = (phase + T) % PKT;
+            if (idx_packet == 0) idx_packet = PKT;
+          }
+          if (dfl > 0) {                                     // held back for the next frame (bb_de_header.cpp:386-402)
+            split = 1;
+            const int ntail = dfl / 8;
+            tail_src = f; tail_bit = in_bit; tail_ndata = ntail; tail_sync = -1;
+            if (idx_packet == PKT) { if (ntail > 0) tail_sync = 0; }
+            else if (idx_packet != 0 && PKT - idx_packet < ntail) tail_sync = PKT - idx_packet;
+            if (tail_sync >= 0) idx_packet = 1 + (ntail - tail_sync); else idx_packet += ntail;
+            idx_buffer = ntail + (tail_sync >= 0 ? 1 : 0);
+          }
+          d.out_len = d.carry_len + d.head_n + d.head_f0 + T;
         }
-        idx_packet = PKT;
-      } else {
-        in_bit += h.syncd;
+        sd[i] = d;
+        off += d.out_len;
       }
-      dfl -= h.syncd;
-      int T = 0;
-      if (dfl >= PKT * 8) {
-        const int M = (dfl - PKT * 8) / 8 + 1;
-        const int phase = idx_packet == PKT ? 0 : idx_packet;
-        if (phase == 0) T = M + (M + PKT - 2) / (PKT - 1);
-        else if (M <= PKT - phase) T = M;
-        else T = M + (M - (PKT - phase) + PKT - 2) / (PKT - 1);
-        d.main_bit = in_bit; d.main_n = M; d.main_phase = phase;
-        in_bit += 8 * M; dfl -= 8 * M;
-        idx_packet = (phase + T) % PKT;
-        if (idx_packet == 0) idx_packet = PKT;
-      }
-      if (dfl > 0) {                                     // held back for the next frame (bb_de_header.cpp:386-402)
-        split = 1;
-        const int ntail = dfl / 8;
-        tail_src = f; tail_bit = in_bit; tail_ndata = ntail; tail_sync = -1;
-        if (idx_packet == PKT) { if (ntail > 0) tail_sync = 0; }
-        else if (idx_packet != 0 && PKT - idx_packet < ntail) tail_sync = PKT - idx_packet;
-        if (tail_sync >= 0) idx_packet = 1 + (ntail - tail_sync); else idx_packet += ntail;
-        idx_buffer = ntail + (tail_sync >= 0 ? 1 : 0);
-      }
-      d.out_len = d.carry_len + d.head_n + d.head_f0 + T;
     }
-    desc[f] = d;
-    if (dlen) dlen[f] = d.out_len;
-    off += d.out_len;
+    __syncwarp();
+    if (lane < nf) {
+      desc[f0 + lane] = sd[lane];
+      if (dlen) dlen[f0 + lane] = sd[lane].out_len;
+      if (status) status[f0 + lane] = sh[lane].status;
+    }
+    __syncwarp();
   }
-  st->split = split; st->idx_packet = idx_packet; st->idx_buffer = idx_buffer; st->total = off;
-  st->tail_src = tail_src; st->tail_bit = tail_bit; st->tail_ndata = tail_ndata; st->tail_sync = tail_sync;
+  if (lane == 0) {
+    st->split = split; st->idx_packet = idx_packet; st->idx_buffer = idx_buffer; st->total = off;
+    st->tail_src = tail_src; st->tail_bit = tail_bit; st->tail_ndata = tail_ndata; st->tail_sync = tail_sync;
+  }
 }
 
 __device__ __forceinline__ uint8_t gather8(const uint8_t* __restrict__ bits)
