@@ -256,6 +256,8 @@ def run_t2b200(args):
     # The throughput workload therefore runs with the documented saturating-cast option; every other operation is
     # the reference's.  The reference-exact (never converging, 25 trials) timing is reported next to it.
     eng.set_option(E.OPT_DEMAP_SATURATE, 1)
+    plain = int(os.environ.get('T2B200_BENCH_PLAIN_LAUNCH', '0'))
+    eng.set_option(E.OPT_LDPC_PLAIN_LAUNCH, plain)          # experiment: measured no gain over the cooperative launch (237.7k vs 242.1k cw/s)
     tables = load_tables(os.path.join(ROOT, 'tests', 'golden', 'tables_c32.npz'))
     p = tables['p']
     L, N = p['len_frame'], p['fft_size']
@@ -286,6 +288,7 @@ def run_t2b200(args):
         stream2 = torch.cuda.Stream(device=dev)
         eng2 = t2.Engine(local, stream=stream2.cuda_stream)
         eng2.set_option(E.OPT_DEMAP_SATURATE, 1)
+        eng2.set_option(E.OPT_LDPC_PLAIN_LAUNCH, plain)
         with torch.cuda.stream(stream2):
             chain2 = FrameChain(eng2, tables, mod=3, cod=2, fec_type=1, n_blocks=FEC_PER_FRAME, ti_len=3)
             chain2.decode_frames(bufs[1], want_status=False)
@@ -402,6 +405,7 @@ def run_t2b200(args):
         # its own 315 MB of IQ in and its own BBFRAME bits out.
         eng2 = t2.Engine(local, stream=stream2.cuda_stream)
         eng2.set_option(E.OPT_DEMAP_SATURATE, 1)
+        eng2.set_option(E.OPT_LDPC_PLAIN_LAUNCH, plain)
         with torch.cuda.stream(stream2):
             chain2 = FrameChain(eng2, tables, mod=3, cod=2, fec_type=1, n_blocks=FEC_PER_FRAME, ti_len=3)
         lanes = [(stream, chain), (stream2, chain2)]

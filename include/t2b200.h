@@ -72,7 +72,12 @@ const char* t2b200_version(void);
  * ~116, so the outer constellation levels always wrap and the reference's own LDPC stage cannot converge on
  * a clean AWGN signal (DESIGN.md "reference quirks").  1 = clamp to [-128,127] instead -- NOT bit-compatible
  * with the reference, provided so the engine is usable; parity tests run with 0.                         */
-enum { T2B200_OPT_DEMAP_SATURATE = 1 };
+enum { T2B200_OPT_DEMAP_SATURATE = 1, T2B200_OPT_LDPC_PLAIN_LAUNCH = 2 };
+/* T2B200_OPT_LDPC_PLAIN_LAUNCH (default 0): lock-step (GROUP32) decodes are launched cooperatively, which makes a decode
+ * wait until the whole GPU is free.  1 = ordinary launch of the same grid: with TWO contexts on two streams taking turns
+ * (bench.py, chain.py) the next decode starts on the SMs the previous one's last groups have left.  Do not run more than
+ * two such decodes concurrently on one GPU: partially resident groups of a third could starve the second (the kernel
+ * traps after a few seconds rather than hang).  Results are identical either way.                              */
 int t2b200_set_option(t2b200_ctx* ctx, int option, int value);
 /* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
 long long t2b200_launch_count(const t2b200_ctx* ctx);

@@ -28,6 +28,7 @@ struct t2b200_ctx {
   std::string err;
   long long launches = 0;
   int opt_demap_saturate = 0;                 // T2B200_OPT_DEMAP_SATURATE
+  int opt_ldpc_plain_launch = 0;              // T2B200_OPT_LDPC_PLAIN_LAUNCH
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id
   float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes

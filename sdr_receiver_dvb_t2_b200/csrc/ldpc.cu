@@ -263,6 +263,8 @@ struct CheckNode {
   }
 };
 
+constexpr unsigned kSpinLimit = 1u << 22;     // ~64 ns per poll: a few seconds, then the kernel traps instead of hanging the GPU
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p)
 {
   unsigned v;
@@ -373,8 +375,8 @@ __global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_cons
         gg = (int)atomicAdd(p.gqueue, 1u);
         if (GL > 1) { __threadfence(); atomicExch(w, (unsigned)gg + 1u); }
       } else {
-        unsigned v;
-        while ((v = ld_acquire(w)) == 0u) __nanosleep(64);
+        unsigned v, polls = 0;
+        while ((v = ld_acquire(w)) == 0u) { __nanosleep(64); if (++polls > kSpinLimit) __trap(); }
         gg = (int)v - 1;
       }
       s_group = gg;
@@ -404,8 +406,8 @@ __global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_cons
         if (tid == 0) {
           unsigned* w = p.gsync + (size_t)g * kSyncStride + iters;
           atomicAdd(w, 1u | (lane_bad ? 0x10000u : 0u));
-          unsigned v;
-          while (((v = ld_acquire(w)) & 0xffffu) != (unsigned)lanes_here) __nanosleep(64);
+          unsigned v, polls = 0;
+          while (((v = ld_acquire(w)) & 0xffffu) != (unsigned)lanes_here) { __nanosleep(64); if (++polls > kSpinLimit) __trap(); }
           s_flag = (v >> 16) != 0;
         }
         __syncthreads();
@@ -539,14 +541,14 @@ __global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_cons
 }
 
 template <int CNL, int MINB>
-cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch(const LdpcParams& p, int grid, size_t smem, cudaStream_t st, bool cooperative)
 {
   auto k = ldpc_decode_kernel<CNL, MINB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // largest shared-memory carve-out: what the two resident decoders leave over can hold the other stream's kernels
   T2_CARVEOUT(k);
-  if (p.group_lanes > 1) {     // lock-step lanes spin on each other: they must be co-resident
+  if (p.group_lanes > 1 && cooperative) {     // lock-step lanes spin on each other: they must be co-resident
     void* args[] = {(void*)&p};
     return cudaLaunchCooperativeKernel((void*)k, dim3(grid), dim3(kThreads), args, smem, st);
   }
@@ -578,9 +580,9 @@ const int kCnlBuckets[] = {4, 5, 7, 8, 9, 11, 12, 13, 16, 17, 20};
     default: return cudaErrorInvalidValue;                                                \
   }
 
-cudaError_t launch_dispatch(int cnl, int minb, const LdpcParams& p, int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_dispatch(int cnl, int minb, const LdpcParams& p, int grid, size_t smem, cudaStream_t st, bool cooperative)
 {
-#define CALL_L(C, T, B) launch<C, B>(p, grid, smem, st)
+#define CALL_L(C, T, B) launch<C, B>(p, grid, smem, st, cooperative)
   DISPATCH(CALL_L)
 }
 cudaError_t occupancy_dispatch(int cnl, int minb, size_t smem, int* bps)
@@ -717,7 +719,9 @@ static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, 
     if ((rc = t2_dev_scratch(ctx, 8, (size_t)capacity * d->s.R * d->state_bytes, &cs))) return rc;
     p.cn_state = (uint32_t*)cs;
   }
-  T2_CUDA(ctx, launch_dispatch(d->cnl, d->minb, p, grid, d->smem, st));
+  // With T2B200_OPT_LDPC_PLAIN_LAUNCH the grid (never larger than what fits the GPU) goes out as an ordinary launch: the
+  // head of the next decode on ANOTHER stream then starts on the SMs the tail of this one has left.
+  T2_CUDA(ctx, launch_dispatch(d->cnl, d->minb, p, grid, d->smem, st, !ctx->opt_ldpc_plain_launch));
   ctx->launches++;
   return T2B200_OK;
 }

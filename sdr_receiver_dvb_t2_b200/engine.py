@@ -19,6 +19,7 @@ C1_2, C3_5, C2_3, C3_4, C4_5, C5_6 = range(6)
 MOD_QPSK, MOD_16QAM, MOD_64QAM, MOD_256QAM = range(4)
 FEC_SHORT, FEC_NORMAL = 0, 1
 OPT_DEMAP_SATURATE = 1
+OPT_LDPC_PLAIN_LAUNCH = 2
 
 # every symbol include/t2b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
