@@ -24,6 +24,7 @@
 struct TiPlp {
   int cells_per_fec = 0, n_fec_max = 0, rows = 0;
   int32_t* d_perm = nullptr;
+  uint32_t* d_src = nullptr;      // per OUTPUT cell a: (row << 16 | column) of the memory cell d = perm^-1[a] that lands there
 };
 struct DemapTable { int32_t* d_addr = nullptr; };
 struct TiDemapState {
@@ -39,23 +40,25 @@ constexpr float kNorm[4] = {0.707106781f, 0.316227766f, 0.15430335f, 0.076696499
 // ---- K3 ------------------------------------------------------------------------------------
 struct TiBlockDesc { long long in_off, out_off; int n_fec; };
 
+// Gather form: one thread per OUTPUT cell.  The table gives, for output cell a, the (row, column) of the interleaver
+// memory cell that lands there, i.e. arrival index k = row * cols + column; the Q component comes from the cell that lands
+// on a + 1 (cyclic inside the FEC block).  Two coalesced table reads, two 4-byte gathers from the L2-resident TI block,
+// one coalesced 8-byte store -- no scattered stores.
 __global__ void ti_deinterleave_kernel(const float2* __restrict__ in, float2* __restrict__ out,
-                                       const int32_t* __restrict__ perm, const TiBlockDesc* __restrict__ blocks,
+                                       const uint32_t* __restrict__ srcmap, const TiBlockDesc* __restrict__ blocks,
                                        int rows, int cpf)
 {
   const TiBlockDesc b = blocks[blockIdx.y];
   const int cols = 5 * b.n_fec;
   const int n = cols * rows;
-  const float2* src = in + b.in_off;
-  float* dst = reinterpret_cast<float*>(out + b.out_off);
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const float2 c = __ldg(src + k);
-    const int col = k % cols, row = k / cols;
-    const int a = __ldg(perm + col * rows + row);
+  const float* src = reinterpret_cast<const float*>(in + b.in_off);
+  float2* dst = out + b.out_off;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
     const int r = a % cpf;
-    const int qa = r == 0 ? a + cpf - 1 : a - 1;
-    dst[2 * a] = c.x;
-    dst[2 * qa + 1] = c.y;
+    const int an = r == cpf - 1 ? a - (cpf - 1) : a + 1;
+    const uint32_t s1 = __ldg(srcmap + a), s2 = __ldg(srcmap + an);
+    const int k1 = (int)(s1 >> 16) * cols + (int)(s1 & 0xffffu), k2 = (int)(s2 >> 16) * cols + (int)(s2 & 0xffffu);
+    dst[a] = make_float2(__ldg(src + 2 * k1), __ldg(src + 2 * k2 + 1));
   }
 }
 
@@ -361,7 +364,7 @@ TiDemapState* state(t2b200_ctx* ctx)
 void t2_ti_free(t2b200_ctx* ctx)
 {
   if (!ctx->ti) return;
-  for (auto& kv : ctx->ti->plp) cudaFree(kv.second.d_perm);
+  for (auto& kv : ctx->ti->plp) { cudaFree(kv.second.d_perm); cudaFree(kv.second.d_src); }
   for (auto& kv : ctx->ti->addr) cudaFree(kv.second.d_addr);
   delete ctx->ti;
   ctx->ti = nullptr;
@@ -397,6 +400,7 @@ extern "C" int t2b200_ti_configure(t2b200_ctx* ctx, int plp, int fec_type, int m
   TiPlp& p = st->plp[plp];
   T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (p.d_perm) { cudaFree(p.d_perm); p.d_perm = nullptr; }
+  if (p.d_src) { cudaFree(p.d_src); p.d_src = nullptr; }
   p.cells_per_fec = t2_cells_per_fec(fec_type, mod);
   p.rows = p.cells_per_fec / 5;
   p.n_fec_max = n_fec_blocks_max;
@@ -405,6 +409,15 @@ extern "C" int t2b200_ti_configure(t2b200_ctx* ctx, int plp, int fec_type, int m
   if (!permutation) { t2_cell_deinterleaver_permutation(n_fec_blocks_max, p.cells_per_fec, own); permutation = own.data(); }
   T2_CUDA(ctx, cudaMalloc(&p.d_perm, n * sizeof(int32_t)));
   T2_CUDA(ctx, cudaMemcpy(p.d_perm, permutation, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // inverse, split into (row, column) of the interleaver memory so that the kernel needs no division by `rows`
+  std::vector<uint32_t> srcmap(n, 0);
+  for (size_t d = 0; d < n; ++d) {
+    const int32_t a = permutation[d];
+    if (a < 0 || (size_t)a >= n) { ctx->err = "t2b200_ti_configure: permutation entry out of range"; return T2B200_ERR_ARG; }
+    srcmap[a] = ((uint32_t)(d % p.rows) << 16) | (uint32_t)(d / p.rows);
+  }
+  T2_CUDA(ctx, cudaMalloc(&p.d_src, n * sizeof(uint32_t)));
+  T2_CUDA(ctx, cudaMemcpy(p.d_src, srcmap.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   return T2B200_OK;
 }
 
@@ -438,7 +451,7 @@ extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cel
   if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)off * 8, &dout))) return rc;
   if ((rc = upload_descs(ctx, 5, d.data(), d.size() * sizeof(TiBlockDesc), &ddesc))) return rc;
   dim3 grid(std::min((max_cells + 255) / 256, ctx->sm_count * 8), n_ti_blocks);
-  ti_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>((const float2*)din, (float2*)dout, p.d_perm,
+  ti_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>((const float2*)din, (float2*)dout, p.d_src,
                                                          (const TiBlockDesc*)ddesc, p.rows, p.cells_per_fec);
   T2_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
