@@ -17,7 +17,7 @@ class FrameChain:
             (keys as oracle RefRx.tables() / tools.make_golden_tables.load()) and the mode parameters under 'p'.
     """
 
-    def __init__(self, eng, tables, mod, cod, fec_type, n_blocks, ti_len, rotation=1, l1_post_size=360, plp=0):
+    def __init__(self, eng, tables, mod, cod, fec_type, n_blocks, ti_len, rotation=1, l1_post_size=360, plp=0, cell_offset=0):
         import torch
         self.torch = torch
         self.eng, self.t, self.p = eng, tables, tables['p']
@@ -31,7 +31,9 @@ class FrameChain:
         base = n_blocks // ti_len
         self.blocks = [base + (1 if j >= ti_len - n_blocks % ti_len else 0) for j in range(ti_len)]   # time_deinterleaver.cpp:275-282
         self.n_blocks = n_blocks
-        self.p2_start = 1840 + l1_post_size                                                          # time_deinterleaver.cpp:44
+        # first PLP cell of the frame: behind the L1 cells (time_deinterleaver.cpp:44) and the cells of the PLPs in front
+        # of this one (type 1, contiguous: l1_postsignalling_dynamic.start)
+        self.p2_start = 1840 + l1_post_size + cell_offset
         self.n_data_sym = p['len_frame'] - p['n_p2'] - p['l_fc']
         self.code = eng.ldpc_code_id(fec_type, cod)
         t = tables
@@ -111,8 +113,13 @@ class FrameChain:
             c, s, h = eng.equalize(E_SYM_FC, np.full(F, L - 1, np.int32), fcf)
             cells[:, p['c_p2'] + nd * p['c_data']:] = c
             sro[:, L - 1], ph[:, L - 1] = s, h
-        stream = cells[:, self.p2_start:self.p2_start + self.need].contiguous()
-        return stream, sro, ph
+        self.last_cells = cells
+        return self.plp_cells(cells), sro, ph
+
+    def plp_cells(self, cells):
+        """this PLP's cells out of the frame cell streams [F][c_p2 + n_data*c_data (+ n_fc)] (another chain of the same
+        frame geometry may have produced them: `other.last_cells`)"""
+        return cells[:, self.p2_start:self.p2_start + self.need].contiguous()
 
     def fec(self, stream, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE, precision_in=None, want_llr=False, max_trials=25,
             want_status=True):

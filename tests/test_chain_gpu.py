@@ -114,3 +114,35 @@ def test_c32_256qam_decodes_with_saturating_cast_option(engine):
     tl = r['trials_left'].cpu().numpy()
     assert (tl >= 0).all()
     assert np.array_equal(r['bits'].cpu().numpy(), f['bb'])
+
+
+def test_config5_multi_plp_r34_pooled_fec(engine):
+    """BASELINE config 5 geometry on one GPU: 32K, two PLPs (type 1, contiguous), both 256-QAM rotated r3/4 64 800.
+    The frame is demodulated once; each PLP runs its own time de-interleaver + demapper; the FEC blocks of BOTH PLPs are
+    pooled into one lock-step LDPC call (what CodewordSharder spreads over the GPUs of a box) and every BBFRAME comes
+    back as transmitted.  (Saturating LLR cast: the reference's wrapping cast cannot decode 256-QAM)"""
+    import torch
+    t = tables('c32')
+    nb = (96, 64)
+    m0 = Modulator(t, mod=3, cod=3, fec_normal=True, n_blocks=nb[0], ti_len=3, seed=21)
+    m1 = Modulator(t, mod=3, cod=3, fec_normal=True, n_blocks=nb[1], ti_len=2, seed=22)
+    bb1, _, _, stream1 = m1.plp_stream()
+    f = m0.frame(noise_cn_db=22.5, extra_streams=[stream1])
+    engine.set_option(E.OPT_DEMAP_SATURATE, 1)
+    try:
+        c0 = FrameChain(engine, t, mod=3, cod=3, fec_type=1, n_blocks=nb[0], ti_len=3, plp=0)
+        c1 = FrameChain(engine, t, mod=3, cod=3, fec_type=1, n_blocks=nb[1], ti_len=2, plp=1, cell_offset=nb[0] * 8100)
+        s0, _, _ = c0.demodulate(torch.from_numpy(f['time'][None]).cuda())
+        s1 = c1.plp_cells(c0.last_cells)
+        llrs = []
+        for ch, s in ((c0, s0), (c1, s1)):
+            ti = engine.ti_deinterleave(ch.plp, s.reshape(-1), ch.blocks)
+            llrs.append(engine.demap(ti, ch.blocks, 3, 1, 1, 3)['llr'])
+        pooled = torch.cat(llrs)                                  # 160 codewords = 5 lock-step groups
+        r = engine.ldpc_decode(c0.code, pooled, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE)
+        engine.sync()
+    finally:
+        engine.set_option(E.OPT_DEMAP_SATURATE, 0)
+    bits = r['bits'].cpu().numpy()
+    assert (r['trials_left'].cpu().numpy() >= 0).all()
+    assert np.array_equal(bits[:nb[0]], f['bb']) and np.array_equal(bits[nb[0]:], bb1)

@@ -177,10 +177,8 @@ class Modulator:
         d = (k % cols) * rows + k // cols
         return tx[self.perm[:n * self.cpf][d]]
 
-    # ---- one T2 frame ----
-    def frame(self, noise_cn_db=None, scale=200.0):
-        """-> dict(time complex64[len_frame][fft_size], bb bits [n_blocks][K_bch], cells ...)"""
-        p, t = self.p, self.t
+    # ---- one interleaving frame of this PLP: BBFRAMEs -> cells in arrival order ----
+    def plp_stream(self):
         bb, info = make_bbframes(self.code, self.nb, self.rng)
         cw = ldpc_encode(self.code, info)
         cells = self.fec_cells(cw)
@@ -188,12 +186,21 @@ class Modulator:
         for nf in self.blocks:
             stream.append(self.ti_stream(cells[off:off + nf]))
             off += nf
-        stream = np.concatenate(stream)
-        # frame cell stream: L1 cells (BPSK +-1, never parsed in replay mode) | PLP | dummy cells
+        return bb, cw, cells, np.concatenate(stream)
+
+    # ---- one T2 frame ----
+    def frame(self, noise_cn_db=None, scale=200.0, extra_streams=()):
+        """-> dict(time complex64[len_frame][fft_size], bb bits [n_blocks][K_bch], cells ...).
+        extra_streams: cell streams of further (type-1, contiguous) PLPs placed right behind this one."""
+        p, t = self.p, self.t
+        bb, cw, cells, stream = self.plp_stream()
+        # frame cell stream: L1 cells (BPSK +-1, never parsed in replay mode) | PLP(s) | dummy cells
         cap = p['c_p2'] - self.p2_start + self.n_data_sym * p['c_data'] + (p['n_fc'] if p['l_fc'] else 0)
-        dummy = qam_map(self.rng.integers(0, 2, (cap - len(stream), self.bpc), dtype=np.uint8), self.mod)
+        plps = np.concatenate([stream] + list(extra_streams))
+        assert len(plps) <= cap, 'PLPs do not fit the frame'
+        dummy = qam_map(self.rng.integers(0, 2, (cap - len(plps), self.bpc), dtype=np.uint8), self.mod)
         l1 = (1.0 - 2.0 * self.rng.integers(0, 2, self.p2_start)).astype(np.complex128)
-        allc = np.concatenate([l1, stream, dummy])
+        allc = np.concatenate([l1, plps, dummy])
         syms = []
         # P2 (idx_symbol 0 -> h_odd), data symbols (parity of idx), frame closing
         pos = 0
