@@ -133,7 +133,7 @@ __global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockD
 // associatively, and one CTA scans 8192 elements per pass.  The (rare: ~40 per TI block) additions that carry
 // s into the next binade are found by the scan, executed as one real float addition, and the scan resumes
 // behind them.  tools/ordered_sum_model.py is the bit-level model this kernel follows.
-constexpr int kSumThreads = 512, kSumE = 8, kSumChunk = kSumThreads * kSumE;   // <= 32 registers x 512 threads: fits next to a resident LDPC decoder
+constexpr int kSumThreads = 512, kSumE = 16, kSumChunk = kSumThreads * kSumE;   // <= 32 registers x 512 threads: fits next to a resident LDPC decoder
 constexpr int kSumSerialHead = 768;        // the sums double every few cells at first: no point scanning there
 constexpr int kSumSat = 1 << 26;           // deltas saturate far above 2^24 (= "left the binade")
 
@@ -172,18 +172,30 @@ __global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const
                                                                          float* __restrict__ precision, float* __restrict__ snr,
                                                                          const float* __restrict__ precision_in)
 {
-  __shared__ SumPair wt[2][kSumThreads / 32];      // warp totals, then their exclusive scan
+  __shared__ SumPair wt[2][kSumThreads / 32];      // warp totals
   __shared__ float sh_s[2];
-  __shared__ int sh_cross;
+  __shared__ int sh_cross[2];                      // first binade crossing of the pass (double-buffered by pass parity)
+  int pass = 0;
   const DemapBlockDesc b = blocks[blockIdx.x];
   const float2* t = terms + b.cell_off;
   const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float2 head[kSumSerialHead];
   int base = min(n, kSumSerialHead);
+  for (int k = tid; k < base; k += kSumThreads) head[k] = __ldg(t + k);      // staged so that only the two FADD chains are serial
+  __syncthreads();
   if (tid == 0) {
     float a = 0.0f, c = 0.0f;
-    for (int k = 0; k < base; ++k) { const float2 v = __ldg(t + k); a = __fadd_rn(a, v.x); c = __fadd_rn(c, v.y); }
-    sh_s[0] = a; sh_s[1] = c; sh_cross = INT_MAX;
+    int k = 0;
+    for (; k + 8 <= base; k += 8) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = head[k + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a = __fadd_rn(a, v[u].x); c = __fadd_rn(c, v[u].y); }
+    }
+    for (; k < base; ++k) { a = __fadd_rn(a, head[k].x); c = __fadd_rn(c, head[k].y); }
+    sh_s[0] = a; sh_s[1] = c; sh_cross[0] = INT_MAX; sh_cross[1] = INT_MAX;
   }
   __syncthreads();
   while (base < n) {
@@ -199,17 +211,36 @@ __global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const
     }
     const int S0 = (int)((b0 & 0x7fffffu) | 0x800000u), S1 = (int)((b1 & 0x7fffffu) | 0x800000u);
     const int m = min(kSumChunk, n - base);
-    int x00 = 0, x01 = 1, x10 = 0, x11 = 1;                       // pseudo-S started even / odd, per sum
-#pragma unroll
+    // A thread's 16 terms as a (delta if S starts even, delta if S starts odd) pair.  Without an exact tie (f == 1/2: about
+    // one term in 2^(shift) -- rare) both deltas are the plain sum of q + [f > 1/2]; only a thread that saw a tie runs the
+    // parity-tracking recurrence.
+    int d0 = 0, d1 = 0;
+    uint32_t ties = 0;
+#pragma unroll 8
     for (int i = 0; i < kSumE; ++i) {
       const int k = tid * kSumE + i;
       float2 v = make_float2(0.0f, 0.0f);
       if (k < m) v = __ldg(t + base + k);
       const uint32_t w0 = sum_elem(es0, __float_as_uint(v.x)), w1 = sum_elem(es1, __float_as_uint(v.y));
-      x00 = sum_apply(x00, w0); x01 = sum_apply(x01, w0);
-      x10 = sum_apply(x10, w1); x11 = sum_apply(x11, w1);
+      d0 += (int)(w0 & 0x1ffffffu) + (int)((w0 >> 30) & 1u);
+      d1 += (int)(w1 & 0x1ffffffu) + (int)((w1 >> 30) & 1u);
+      ties |= w0 | w1;
     }
-    SumPair p0 = {x00, x01 - 1}, p1 = {x10, x11 - 1};
+    SumPair p0 = {min(d0, kSumSat), min(d0, kSumSat)}, p1 = {min(d1, kSumSat), min(d1, kSumSat)};
+    if (ties >> 31) {
+      int x00 = 0, x01 = 1, x10 = 0, x11 = 1;                     // pseudo-S started even / odd, per sum
+      for (int i = 0; i < kSumE; ++i) {
+        const int k = tid * kSumE + i;
+        if (k < m) {
+          const float2 v = __ldg(t + base + k);
+          const uint32_t w0 = sum_elem(es0, __float_as_uint(v.x)), w1 = sum_elem(es1, __float_as_uint(v.y));
+          x00 = sum_apply(x00, w0); x01 = sum_apply(x01, w0);
+          x10 = sum_apply(x10, w1); x11 = sum_apply(x11, w1);
+        }
+      }
+      p0.a0 = x00; p0.a1 = x01 - 1; p1.a0 = x10; p1.a1 = x11 - 1;
+    }
+    const SumPair own0 = p0, own1 = p1;
     // inclusive scan inside the warp, warp totals through shared memory
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -224,43 +255,49 @@ __global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const
     e1.a0 = __shfl_up_sync(0xffffffffu, p1.a0, 1); e1.a1 = __shfl_up_sync(0xffffffffu, p1.a1, 1);
     if (lane == 0) { e0.a0 = e0.a1 = 0; e1.a0 = e1.a1 = 0; }
     __syncthreads();
-    if (warp == 0) {                                             // exclusive scan of the warp totals
+    // every warp scans the warp totals for itself (16 entries: four shuffle steps) -- cheaper than a second barrier
+    SumPair q0, q1;
+    {
       constexpr int NWARP = kSumThreads / 32;
       SumPair t0 = {0, 0}, t1 = {0, 0};
       if (lane < NWARP) { t0 = wt[0][lane]; t1 = wt[1][lane]; }
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
+      for (int off = 1; off < NWARP; off <<= 1) {
         SumPair o0, o1;
         o0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, off);
         o1.a0 = __shfl_up_sync(0xffffffffu, t1.a0, off); o1.a1 = __shfl_up_sync(0xffffffffu, t1.a1, off);
         if (lane >= off) { t0 = sum_compose(o0, t0); t1 = sum_compose(o1, t1); }
       }
+      // exclusive prefix of this warp = inclusive total of warp - 1
+      const int srcl = warp == 0 ? 0 : warp - 1;
       SumPair x0, x1;
-      x0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, 1); x0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, 1);
-      x1.a0 = __shfl_up_sync(0xffffffffu, t1.a0, 1); x1.a1 = __shfl_up_sync(0xffffffffu, t1.a1, 1);
-      if (lane == 0) { x0.a0 = x0.a1 = 0; x1.a0 = x1.a1 = 0; }
-      if (lane < NWARP) { wt[0][lane] = x0; wt[1][lane] = x1; }
+      x0.a0 = __shfl_sync(0xffffffffu, t0.a0, srcl); x0.a1 = __shfl_sync(0xffffffffu, t0.a1, srcl);
+      x1.a0 = __shfl_sync(0xffffffffu, t1.a0, srcl); x1.a1 = __shfl_sync(0xffffffffu, t1.a1, srcl);
+      if (warp == 0) { x0.a0 = x0.a1 = 0; x1.a0 = x1.a1 = 0; }
+      q0 = sum_compose(x0, e0); q1 = sum_compose(x1, e1);
     }
-    __syncthreads();
-    const SumPair q0 = sum_compose(wt[0][warp], e0), q1 = sum_compose(wt[1][warp], e1);
     int Sa = sum_sat(S0, (S0 & 1) ? q0.a1 : q0.a0), Sb = sum_sat(S1, (S1 & 1) ? q1.a1 : q1.a0);
-    // walk the thread's elements with the true S: find the first addition that leaves a binade
+    // S only grows: a binade is left inside this thread's range iff S is still inside before it and outside after it.
+    // Only that thread (at most one per sum and pass) walks its terms to find the addition that does it.
     int my_cross = INT_MAX, Sa_before = Sa, Sb_before = Sb;
-    if (Sa >= (1 << 24) || Sb >= (1 << 24)) my_cross = tid * kSumE;   // happened in an earlier thread (never the minimum)
-    else {
-#pragma unroll
-      for (int i = 0; i < kSumE; ++i) {
-        if (my_cross == INT_MAX && tid * kSumE + i < m) {
-          const float2 v = __ldg(t + base + tid * kSumE + i);     // second read of the thread's own 64 bytes: an L1 hit
-          const int na = sum_apply(Sa, sum_elem(es0, __float_as_uint(v.x))), nb = sum_apply(Sb, sum_elem(es1, __float_as_uint(v.y)));
-          if (na >= (1 << 24) || nb >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; Sb_before = Sb; }
-          else { Sa = na; Sb = nb; }
+    const int Sa_out = sum_sat(Sa, (Sa & 1) ? own0.a1 : own0.a0), Sb_out = sum_sat(Sb, (Sb & 1) ? own1.a1 : own1.a0);
+    if (Sa < (1 << 24) && Sb < (1 << 24)) {
+      if (Sa_out >= (1 << 24) || Sb_out >= (1 << 24)) {
+        for (int i = 0; i < kSumE; ++i) {
+          if (my_cross == INT_MAX && tid * kSumE + i < m) {
+            const float2 v = __ldg(t + base + tid * kSumE + i);   // second read of the thread's own 128 bytes: an L1 hit
+            const int na = sum_apply(Sa, sum_elem(es0, __float_as_uint(v.x))), nb = sum_apply(Sb, sum_elem(es1, __float_as_uint(v.y)));
+            if (na >= (1 << 24) || nb >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; Sb_before = Sb; }
+            else { Sa = na; Sb = nb; }
+          }
         }
-      }
+      } else { Sa = Sa_out; Sb = Sb_out; }
     }
-    if (my_cross != INT_MAX) atomicMin(&sh_cross, my_cross);
+    if (tid == 0) sh_cross[(pass + 1) & 1] = INT_MAX;             // next pass's slot: last read before this pass's first barrier
+    if (my_cross != INT_MAX) atomicMin(&sh_cross[pass & 1], my_cross);
     __syncthreads();
-    const int cross = sh_cross;
+    const int cross = sh_cross[pass & 1];
+    ++pass;
     if (cross == INT_MAX) {
       if (tid == (m - 1) / kSumE) {                              // owner of the last element holds the totals
         sh_s[0] = __uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa & 0x7fffffu));
@@ -275,8 +312,6 @@ __global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const
       }
       base += cross + 1;
     }
-    __syncthreads();
-    if (tid == 0) sh_cross = INT_MAX;
     __syncthreads();
   }
   if (tid == 0) {
