@@ -13,11 +13,12 @@
 // B200 design: the serial scan of the reference is turned inside out.  At table-upload time the host
 // compiles each symbol's carrier map into a PLAN: the list of estimating pilots and, per data cell, its
 // carrier, its left pilot, its position inside the interval and its de-interleaved address (8 bytes per
-// cell, identical plans shared between symbols).  One CTA then handles one symbol: pilots are estimated
-// in parallel into shared memory, one thread forms the ordered pilot sums while all others equalise the
-// data cells independently (each re-running its interval's additions, <= 191 FADDs), and results leave
-// through the de-interleaver as 8-byte scattered stores that merge in L2.  Arithmetic is written with
-// explicit round-to-nearest intrinsics so no FMA contraction changes a bit relative to the CPU oracle.
+// cell, identical plans shared between symbols), plus the first-cell index of every pilot interval.  Eight
+// CTAs share a symbol (1 024-cell chunks dealt round-robin; see equalize_kernel): pilots are estimated in
+// parallel into shared memory, the interpolation chains run once per interval, the cells of a chunk are
+// equalised independently and leave through the de-interleaver as 8-byte scattered stores that merge in L2
+// because few symbols are in flight.  Arithmetic is written with explicit round-to-nearest intrinsics so no
+// FMA contraction changes a bit relative to the CPU oracle.
 #include "ctx.h"
 #include <cuda_pipeline.h>
 #include <algorithm>

@@ -1,4 +1,4 @@
-// K1: batched forward complex FFT (fp32) for OFDM symbols -- 32K / 16K (and any n = 256 * 2^m >= 1024),
+// K1: batched forward complex FFT (fp32) for OFDM symbols -- 32K / 16K (and 8K / 4K: n = 256 * 16 * A, A = 1, 2, 4, 8),
 // unnormalised, with the half-swap (fftshift) of fast_fourier_transform::execute folded into the store.
 //
 // Reference semantics (src/DSP/fast_fourier_transform.h:54-70): out = fftshift(DFT_forward(in)), FFTW
@@ -6,12 +6,13 @@
 // there is no bit-exact target: the contract is <= 1e-5 * max|X| against a float64 DFT.
 //
 // B200 design: four-step decomposition N = N1 x 256 in two streaming passes.  A 32K symbol (256 KiB) does
-// not fit one SM's shared memory, so pass A transforms 16 columns at a time (length N1, stride 256) and
+// not fit one SM's shared memory, so pass A transforms 32 columns at a time (length N1 = 16 A, stride 256) and
 // applies the inter-pass twiddle, pass B transforms 16 rows at a time (length 256) and writes the shifted
-// spectrum; every global access is a full 128-byte line and the intermediate stays L2-resident because
-// the batch is walked in chunks smaller than L2.  Inside a tile the 16 transforms run side by side as
-// radix-4 Stockham stages (auto-sorting: no bit reversal) ping-ponging between two shared-memory images
-// laid out [element][17] so that stage accesses and tile loads / stores are bank-conflict free.
+// spectrum; every global access is a full 128- or 256-byte run and the intermediate stays L2-resident because
+// the batch is walked in chunks smaller than L2.  The butterflies run in REGISTERS: every thread loads 16
+// samples straight from global memory, does a radix-16 DFT (two radix-4 levels, constants folded), and one
+// shared-memory exchange hands the data to the second register stage (radix-A in pass A, radix-16 in pass B),
+// whose results are stored straight to global memory.
 #include "ctx.h"
 #include <cmath>
 #include <cstdlib>

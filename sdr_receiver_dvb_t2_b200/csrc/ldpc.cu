@@ -1,6 +1,6 @@
-// K5 + K6: layered offset-min-sum LDPC decoder for every DVB-T2 code, one CTA per codeword,
-// whole decoder state resident in shared memory, with the BCH-parity strip + BB descramble fused
-// into the epilogue.
+// K5 + K6: layered offset-min-sum LDPC decoder for every DVB-T2 code, one CTA per codeword, two CTAs
+// per SM: posteriors in shared memory, check-node messages in an L2-resident scratch, with the
+// BCH-parity strip + BB descramble fused into the epilogue.
 //
 // Semantics reproduced bit-for-bit (paths relative to the reference's src/DVB_T2):
 //   LDPC/layered_decoder.hh:83-110   update(): layers i = 0..q-1, check nodes j = 0..359 SERIALLY
@@ -13,9 +13,12 @@
 //   bch_decoder.cpp:50-61,139-142    PRBS 1+x^14+x^15 (0x4A80), out[i] = in[i] ^ prbs[i], i < K_bch
 //
 // B200 design (DESIGN.md "K5"):
-//   * posteriors int8[N] (<= 64.8 KB) + one packed word per check node (two clamped minima, arg-min
-//     slot, output signs: the min-sum messages of a check node are fully determined by those) stay
-//     in shared memory for the whole decode -> HBM traffic is the compulsory N bytes in, K out.
+//   * posteriors int8[N] (<= 64.8 KB) stay in shared memory for the whole decode; the min-sum messages of a
+//     check node are fully determined by (two clamped minima, arg-min slot, output signs) and are kept as
+//     8-16 bytes per check node in a global scratch that only the owning thread touches (L2-resident,
+//     prefetched a layer ahead) -> two codewords per SM, HBM traffic = the compulsory N bytes in, K out.
+//   * 64 registers per thread + the largest shared-memory carve-out: what two resident decoders leave
+//     free on an SM runs the streaming kernels of another stream (see kLdpcRegs).
 //   * the quasi-cyclic structure makes every edge of a layer a contiguous (rotated) run of 360
 //     posteriors: thread j of the CTA owns check node (i, j), so all shared-memory traffic is
 //     conflict-free byte-contiguous across a warp; no position table is read, addresses come from
@@ -24,7 +27,7 @@
 //     the host precomputes the dependency depth of every check node in such layers and the CTA runs
 //     them level by level (ldpc_schedule.cpp), everything else is one parallel step per layer.
 //   * lock-step groups of 32 (reference batch semantics) are 32 co-resident CTAs that exchange their
-//     parity verdict through one global word per iteration.
+//     parity verdict through one global word per iteration; groups are claimed from an atomic queue.
 #include "ctx.h"
 #include "ldpc_schedule.h"
 #include <cstring>
