@@ -289,23 +289,20 @@ template <int CNL>
 __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uint32_t* __restrict__ hb,
                                             const LdpcParams& p)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int nwords = (p.N + 31) >> 5;
-  const int nchunks = (p.N + 127) >> 7;                      // 128 posteriors = 32 lanes x 4 bytes
-  const uint32_t* pw = reinterpret_cast<const uint32_t*>(post);
+  // one thread packs the signs of 8 posteriors (one 8-byte load) into one byte of the plane
+  const uint2* pw = reinterpret_cast<const uint2*>(post);
+  uint8_t* hbb = reinterpret_cast<uint8_t*>(hb);
   uint32_t anyzero = 0;
-  for (int ch = warp; ch < nchunks; ch += kThreads / 32) {
-    const int wi = ch * 32 + lane;
-    uint32_t w = wi * 4 < p.N ? pw[wi] : 0x01010101u;        // N is a multiple of 4
-    anyzero |= (w - 0x01010101u) & ~w & 0x80808080u;         // some byte == 0
-    uint32_t nib = ((((w >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;   // 4 sign bits
-    nib <<= 4 * (lane & 7);
-    nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
-    nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
-    nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
-    if ((lane & 7) == 0 && ch * 4 + (lane >> 3) < nwords + 2) hb[ch * 4 + (lane >> 3)] = nib;
+  for (int k = tid; k < p.N / 8; k += kThreads) {                 // N is a multiple of 8
+    const uint2 w = pw[k];
+    anyzero |= ((w.x - 0x01010101u) & ~w.x & 0x80808080u) | ((w.y - 0x01010101u) & ~w.y & 0x80808080u);   // some byte == 0
+    const uint32_t lo = ((((w.x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+    const uint32_t hi = ((((w.y >> 7) & 0x01010101u) * 0x01020408u) >> 20) & 0xf0u;
+    hbb[k] = (uint8_t)(lo | hi);
   }
-  if (tid < 2 && (nchunks * 4) < nwords + 2) hb[nwords + tid] = 0;
+  for (int k = p.N / 8 + tid; k < 4 * (nwords + 2); k += kThreads) hbb[k] = 0;   // the windows below read up to two words past the end
   int bad = anyzero != 0;
   __syncthreads();
   for (int t = tid; t < p.q * 12; t += kThreads) {
