@@ -305,7 +305,8 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
   for (int k = p.N / 8 + tid; k < 4 * (nwords + 2); k += kThreads) hbb[k] = 0;   // the windows below read up to two words past the end
   int bad = anyzero != 0;
   __syncthreads();
-  for (int t = tid; t < p.q * 12; t += kThreads) {
+  // word-check (layer i, word w): parity of 32 check nodes at once
+  auto word_check = [&](int t) {
     const int i = t / 12, w = t - 12 * i;
     const int cnt = p.cnt[i];
     uint32_t x = 0;
@@ -330,7 +331,14 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
       x ^= r;
     }
     if (w == 11) x &= 0xffu;
-    bad |= (x != 0);
+    return (int)(x != 0);
+  };
+  const int n_tasks = p.q * 12;
+  if (tid < n_tasks) bad |= word_check(tid);
+  if (n_tasks > kThreads) {                                   // (uniform condition: every thread reaches the barrier)
+    // a codeword that still fails among the first 384 word-checks (the usual case until the last iterations) needs no more
+    if (__syncthreads_or(bad)) return 1;
+    for (int t = tid + kThreads; t < n_tasks; t += kThreads) bad |= word_check(t);
   }
   return bad;
 }
