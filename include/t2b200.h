@@ -203,6 +203,26 @@ int t2b200_ts_reset(t2b200_ctx* ctx, int plp);
 int t2b200_ts_packetize(t2b200_ctx* ctx, int plp, const uint8_t* bbframes, int n_frames, int k_bch,
                         uint8_t* ts_out, size_t ts_cap, int32_t* datagram_len, int32_t* status, long long* total_out);
 
+/* ---- whole frames in one call (replay mode) ----------------------------------------------------- */
+/* The per-stage calls above chained on the device for whole T2 frames of one PLP: what dvbt2_demodulator::
+ * symbol_acquisition (dvbt2_demodulator.cpp:332-385) and the signal chain behind it (time_deinterleaver -> llr_demapper ->
+ * ldpc_decoder -> bch_decoder) do symbol by symbol, for already synchronised frames.  Configure the symbol tables
+ * (t2b200_eq_configure for P2 / DATA / FC) and the PLP (t2b200_ti_configure) first.                                  */
+typedef struct {
+  int fft_size, len_frame, n_p2, l_fc;   /* symbols of a frame: n_p2 P2 symbols, data symbols, l_fc frame-closing symbol   */
+  int c_p2, c_data, n_fc;                /* cells per symbol of each kind (dvbt2_parameters, dvbt2_definition.h:215-260)  */
+  int first_cell;                        /* first PLP cell of the frame cell stream: 1840 + l1_post_size + cells of the    */
+                                         /* PLPs in front (time_deinterleaver.cpp:44, l1_postsignalling_dynamic.start)    */
+  int plp, mod, rotation, fec_type, code_rate, n_blocks, ti_len;   /* l1_postsignalling_plp + this frame's num_blocks       */
+} t2b200_frame_cfg;
+int t2b200_frames_configure(t2b200_ctx* ctx, const t2b200_frame_cfg* cfg);
+/*   iq          complex<float>[n_frames][len_frame][fft_size]: the FFT window of every symbol (dvbt2_demodulator.cpp:332)
+ *   bits_out    [n_frames * n_blocks][K_bch | K_ldpc] per ldpc_flags (T2B200_LDPC_GROUP32 | _BCH_DESCRAMBLE | _PACK_BITS)
+ *   trials_left int32[n_frames * n_blocks] or NULL;  sro, phase float[n_frames][len_frame] or NULL (the equalisers'
+ *   feedback floats);  snr float[n_frames * ti_len] or NULL.  Device buffers keep the call asynchronous.                 */
+int t2b200_frames_decode(t2b200_ctx* ctx, const float* iq, int n_frames, uint8_t* bits_out, int32_t* trials_left,
+                         float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags);
+
 #ifdef __cplusplus
 }
 #endif

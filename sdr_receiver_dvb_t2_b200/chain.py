@@ -46,6 +46,10 @@ class FrameChain:
                              t['fc_ref'][None], t['h_even_fc'], t['h_odd_fc'], t['amp_sp'])
         eng.ti_configure(plp, fec_type, mod, max(self.blocks))
         self.need = n_blocks * self.cpf
+        # the same chain as ONE C call (t2b200_frames_decode): no glue copies, nothing of this class on the data path
+        eng.frames_configure(fft_size=p['fft_size'], len_frame=p['len_frame'], n_p2=p['n_p2'], l_fc=p['l_fc'], c_p2=p['c_p2'],
+                             c_data=p['c_data'], n_fc=p['n_fc'] if p['l_fc'] else 0, first_cell=self.p2_start, plp=plp, mod=mod,
+                             rotation=rotation, fec_type=fec_type, code_rate=cod, n_blocks=n_blocks, ti_len=ti_len)
         self._bufs = {}
         self.events = None          # set to {} to collect per-stage CUDA events: name -> [(start, stop), ...]
 
@@ -136,6 +140,10 @@ class FrameChain:
         if want_llr:
             r['llr'], r['ti'] = d['llr'], ti
         return r
+
+    def decode_frames_fused(self, time, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE, max_trials=25, want_status=True, out=None):
+        """the whole chain through t2b200_frames_decode (the engine keeps ONE frame configuration: the last chain built)"""
+        return self.eng.frames_decode(time, flags=flags, max_trials=max_trials, want_status=want_status, out=out)
 
     def decode_frames(self, time, host_feedback=True, **kw):
         """host_feedback=False leaves sro / phase / snr / precision on the device: nothing in the call waits for the GPU"""

@@ -6,6 +6,7 @@ void t2_fft_free(t2b200_ctx* ctx);
 void t2_eq_free(t2b200_ctx* ctx);
 void t2_ti_free(t2b200_ctx* ctx);
 void t2_ts_free(t2b200_ctx* ctx);
+void t2_frames_free(t2b200_ctx* ctx);
 
 bool t2_is_device_ptr(const void* p)
 {
@@ -114,6 +115,7 @@ void t2b200_destroy(t2b200_ctx* ctx)
   t2_eq_free(ctx);
   t2_ti_free(ctx);
   t2_ts_free(ctx);
+  t2_frames_free(ctx);
   if (ctx->d_prbs) cudaFree(ctx->d_prbs);
   if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
   for (auto& s : ctx->dev) if (s.p) cudaFree(s.p);
@@ -160,3 +162,4 @@ __attribute__((weak)) void t2_fft_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_eq_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_ti_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_ts_free(t2b200_ctx*) {}
+__attribute__((weak)) void t2_frames_free(t2b200_ctx*) {}

@@ -13,6 +13,7 @@ struct FftPlan;          // fft.cu
 struct SymbolTables;     // equalizer.cu
 struct TiDemapState;     // demap.cu
 struct TsState;          // ts.cu
+struct FramePipe;        // frames.cu
 
 struct Scratch {
   void* p = nullptr; size_t cap = 0; bool pinned_host = false;
@@ -37,6 +38,7 @@ struct t2b200_ctx {
   SymbolTables* sym[3] = {nullptr, nullptr, nullptr};
   TiDemapState* ti = nullptr;
   TsState* ts = nullptr;
+  FramePipe* frames = nullptr;
   // staging scratch, grown on demand
   Scratch dev[16];
   Scratch pin[8];

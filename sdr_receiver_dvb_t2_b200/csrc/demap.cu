@@ -15,7 +15,7 @@
 // write pass whose working set (one TI block, <= 4.4 MB) lives in L2.  K4 runs one CTA per FECFRAME:
 // LLRs are produced into a 64.8 KB shared-memory image of the de-interleaved frame and leave the SM as
 // coalesced 16-byte stores, so the column-twist scatter never reaches HBM as byte writes.
-#include "ctx.h"
+#include "stages.h"
 #include "fec_tables.h"
 #include <algorithm>
 #include <cmath>
@@ -38,7 +38,6 @@ constexpr float kRot[4] = {0.506145483f, 0.293215314f, 0.150098316f, 0.062418810
 constexpr float kNorm[4] = {0.707106781f, 0.316227766f, 0.15430335f, 0.076696499f};      // dvbt2_definition.h:49-52
 
 // ---- K3 ------------------------------------------------------------------------------------
-struct TiBlockDesc { long long in_off, out_off; int n_fec; };
 
 // Gather form: one thread per OUTPUT cell.  The table gives, for output cell a, the (row, column) of the interleaver
 // memory cell that lands there, i.e. arrival index k = row * cols + column; the Q component comes from the cell that lands
@@ -94,7 +93,6 @@ __device__ __forceinline__ float slice_axis(float x, float a)
   return -s;
 }
 
-struct DemapBlockDesc { long long cell_off; int n_cells; int first_fec; };
 
 // levels k*a must be the same floats the reference holds (norm_x_k = NORM * k.0f): computed as a*k in float.
 // Pass 1a: derotate in place + per-cell |s|^2 and |e|^2 of the hard decision, stored for the ordered sum.
@@ -464,6 +462,25 @@ static int upload_descs(t2b200_ctx* ctx, int slot, const void* h, size_t bytes, 
   return T2B200_OK;
 }
 
+int t2_ti_device(t2b200_ctx* ctx, int plp, const float2* d_in, float2* d_out, const TiBlockDesc* d_desc, int n_ti_blocks,
+                 int max_cells)
+{
+  if (!ctx->ti || !ctx->ti->plp.count(plp)) { ctx->err = "TI: PLP not configured"; return T2B200_ERR_STATE; }
+  const TiPlp& p = ctx->ti->plp[plp];
+  dim3 grid(std::min((max_cells + 255) / 256, ctx->sm_count * 8), n_ti_blocks);
+  ti_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return T2B200_OK;
+}
+
+int t2_ti_geometry(t2b200_ctx* ctx, int plp, int* cells_per_fec, int* n_fec_max)
+{
+  if (!ctx->ti || !ctx->ti->plp.count(plp)) { ctx->err = "TI: PLP not configured"; return T2B200_ERR_STATE; }
+  *cells_per_fec = ctx->ti->plp[plp].cells_per_fec; *n_fec_max = ctx->ti->plp[plp].n_fec_max;
+  return T2B200_OK;
+}
+
 extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cells_in, int n_ti_blocks,
                                       const int32_t* n_fec_per_block, float* cells_out)
 {
@@ -485,11 +502,7 @@ extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cel
   if ((rc = t2_to_device(ctx, 0, cells_in, (size_t)off * 8, &din))) return rc;
   if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)off * 8, &dout))) return rc;
   if ((rc = upload_descs(ctx, 5, d.data(), d.size() * sizeof(TiBlockDesc), &ddesc))) return rc;
-  dim3 grid(std::min((max_cells + 255) / 256, ctx->sm_count * 8), n_ti_blocks);
-  ti_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>((const float2*)din, (float2*)dout, p.d_src,
-                                                         (const TiBlockDesc*)ddesc, p.rows, p.cells_per_fec);
-  T2_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
+  if ((rc = t2_ti_device(ctx, plp, (const float2*)din, (float2*)dout, (const TiBlockDesc*)ddesc, n_ti_blocks, max_cells))) return rc;
   // (the descriptor upload above is a pageable-memory copy: the runtime has consumed the host vector when it returns)
   return t2_finish_out(ctx, cells_out, dout, (size_t)off * 8);
 }
@@ -518,15 +531,10 @@ static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* 
   return T2B200_OK;
 }
 
-extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, const int32_t* n_fec_per_block,
-                            int mod, int rotation, int fec_type, int code_rate, int8_t* llr_out,
-                            float* snr_out, float* precision_out, const float* precision_in)
+int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_ti_blocks, int max_cells,
+                    long long total_cells, int max_fec, int mod, int rotation, int fec_type, int code_rate, int8_t* d_llr,
+                    float* d_prec, float* d_snr, const float* d_prec_in)
 {
-  if (!ctx) return T2B200_ERR_ARG;
-  if (!ti_cells || !llr_out || n_ti_blocks < 0 || !n_fec_per_block || mod < 0 || mod > 3 ||
-      (fec_type != 0 && fec_type != 1) || code_rate < 0 || code_rate > 5) { ctx->err = "t2b200_demap: bad argument"; return T2B200_ERR_ARG; }
-  if (n_ti_blocks == 0) return T2B200_OK;
-  T2_CUDA(ctx, cudaSetDevice(ctx->device));
   TiDemapState* st = state(ctx);
   const int cpf = t2_cells_per_fec(fec_type, mod), fec_bits = fec_type ? 64800 : 16200;
   const int cr_class = (fec_type && code_rate == 1) ? 1 : (fec_type && mod == 3 && code_rate == 2) ? 2 : 0;
@@ -539,6 +547,23 @@ extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, c
     T2_CUDA(ctx, cudaMemcpy(t.d_addr, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
     st->addr[key] = t;
   }
+  const int32_t* daddr = mod ? st->addr[key].d_addr : nullptr;
+#define DM(M) demap_launch<M>(ctx, d_cells, d_desc, n_ti_blocks, max_cells, total_cells, rotation, daddr, d_llr, cpf, fec_bits, \
+                              max_fec, d_prec, d_snr, d_prec_in)
+  switch (mod) { case 0: return DM(0); case 1: return DM(1); case 2: return DM(2); default: return DM(3); }
+#undef DM
+}
+
+extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, const int32_t* n_fec_per_block,
+                            int mod, int rotation, int fec_type, int code_rate, int8_t* llr_out,
+                            float* snr_out, float* precision_out, const float* precision_in)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (!ti_cells || !llr_out || n_ti_blocks < 0 || !n_fec_per_block || mod < 0 || mod > 3 ||
+      (fec_type != 0 && fec_type != 1) || code_rate < 0 || code_rate > 5) { ctx->err = "t2b200_demap: bad argument"; return T2B200_ERR_ARG; }
+  if (n_ti_blocks == 0) return T2B200_OK;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int cpf = t2_cells_per_fec(fec_type, mod), fec_bits = fec_type ? 64800 : 16200;
   std::vector<DemapBlockDesc> d(n_ti_blocks);
   long long off = 0; int fec = 0, max_cells = 0, max_fec = 0;
   for (int i = 0; i < n_ti_blocks; ++i) {
@@ -561,11 +586,8 @@ extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, c
                                  t2_is_device_ptr(precision_in) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     dpin = tmp;
   }
-  const int32_t* daddr = mod ? st->addr[key].d_addr : nullptr;
-#define DM(M) demap_launch<M>(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, off, rotation, daddr, \
-                              (int8_t*)dllr, cpf, fec_bits, max_fec, (float*)dprec, (float*)dsnr, (const float*)dpin)
-  switch (mod) { case 0: rc = DM(0); break; case 1: rc = DM(1); break; case 2: rc = DM(2); break; default: rc = DM(3); break; }
-  if (rc) return rc;
+  if ((rc = t2_demap_device(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, off, max_fec, mod, rotation,
+                            fec_type, code_rate, (int8_t*)dllr, (float*)dprec, (float*)dsnr, (const float*)dpin))) return rc;
   auto copy_small = [&](float* dst, const void* src) -> int {
     if (!dst) return T2B200_OK;
     T2_CUDA(ctx, cudaMemcpyAsync(dst, src, 4 * (size_t)n_ti_blocks,

@@ -19,7 +19,7 @@
 // equalised independently and leave through the de-interleaver as 8-byte scattered stores that merge in L2
 // because few symbols are in flight.  Arithmetic is written with explicit round-to-nearest intrinsics so no
 // FMA contraction changes a bit relative to the CPU oracle.
-#include "ctx.h"
+#include "stages.h"
 #include <cuda_pipeline.h>
 #include <algorithm>
 #include <cmath>
@@ -81,7 +81,11 @@ struct EqParams {
   int fft_size, l_nulls, n_out, first_symbol, n_symbols_kind;
   int n_symbols;                 // symbols in this launch
   int split;                     // CTAs per symbol
-  long long in_stride, out_stride;   // float2 elements between consecutive symbols of the launch
+  // symbol s of the launch = symbol r = s % per_frame of frame f = s / per_frame (a plain batch is one "frame"):
+  //   spectrum at freq + f * in_frame + r * in_sym, cells to out + f * out_frame + r * out_sym, feedback floats at
+  //   [f * fb_frame + r]; idx_symbol == nullptr means idx = first_symbol + r
+  int per_frame;
+  long long in_frame, in_sym, out_frame, out_sym, fb_frame;
 };
 
 constexpr int kEqThreads = 256;
@@ -105,7 +109,8 @@ __global__ void __launch_bounds__(kEqThreads) equalize_kernel(const EqParams p)
   float2* chain = reinterpret_cast<float2*>(smem_raw);
   const int part = blockIdx.x % p.split;
   for (int s = blockIdx.x / p.split; s < p.n_symbols; s += gridDim.x / p.split) {
-    const int idx = p.idx_symbol[s];
+    const int fr = s / p.per_frame, rs = s - fr * p.per_frame;
+    const int idx = p.idx_symbol ? p.idx_symbol[s] : p.first_symbol + rs;
     int rel = idx - p.first_symbol;
     rel = min(max(rel, 0), p.n_symbols_kind - 1);
     const PlanDev pl = p.plans[(idx & 1) ? p.plan_odd[rel] : p.plan_even[rel]];
@@ -114,8 +119,9 @@ __global__ void __launch_bounds__(kEqThreads) equalize_kernel(const EqParams p)
     float* ang = reinterpret_cast<float*>(est + pl.n_pilots);
     float* amp = ang + pl.n_pilots;
     int* first = reinterpret_cast<int*>(amp + pl.n_pilots);
-    const float2* cell = p.freq + (size_t)s * p.in_stride + p.l_nulls;
-    float2* out = p.out + (size_t)s * p.out_stride;
+    const float2* cell = p.freq + (size_t)fr * p.in_frame + (size_t)rs * p.in_sym + p.l_nulls;
+    float2* out = p.out + (size_t)fr * p.out_frame + (size_t)rs * p.out_sym;
+    const size_t fb = (size_t)fr * p.fb_frame + rs;
 
     for (int i = threadIdx.x; i < pl.n_pilots; i += blockDim.x) {
       const PlanPilot pp = pl.pilots[i];
@@ -217,8 +223,8 @@ __global__ void __launch_bounds__(kEqThreads) equalize_kernel(const EqParams p)
         const float2 e = est[i];
         s2r = __fadd_rn(s2r, e.x); s2i = __fadd_rn(s2i, e.y); a2 = __fadd_rn(a2, ang[i]);
       }
-      if (p.phase) p.phase[s] = __fadd_rn(atan2_approx_dev(s2i, s2r), atan2_approx_dev(s1i, s1r));
-      if (p.sro) p.sro[s] = __fsub_rn(a2, a1);
+      if (p.phase) p.phase[fb] = __fadd_rn(atan2_approx_dev(s2i, s2r), atan2_approx_dev(s1i, s1r));
+      if (p.sro) p.sro[fb] = __fsub_rn(a2, a1);
     }
     __syncthreads();                        // the pilot arrays are reused by the next symbol
   }
@@ -364,6 +370,31 @@ extern "C" int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int
   return T2B200_OK;
 }
 
+// Device-level launch (all pointers device memory): n_symbols symbols, per_frame of them per frame (see EqParams).
+int t2_equalize_device(t2b200_ctx* ctx, int kind, int n_symbols, int per_frame, const int* d_idx, const float2* d_freq,
+                       long long in_frame, long long in_sym, float2* d_out, long long out_frame, long long out_sym,
+                       float* d_sro, float* d_phase, long long fb_frame)
+{
+  SymbolTables* t = ctx->sym[kind];
+  if (!t) { ctx->err = "equalise: symbol tables not configured"; return T2B200_ERR_STATE; }
+  if (n_symbols == 0) return T2B200_OK;
+  EqParams p;
+  p.freq = d_freq; p.out = d_out; p.sro = d_sro; p.phase = d_phase; p.idx_symbol = d_idx;
+  p.plans = t->d_plans; p.plan_even = t->d_plan_even; p.plan_odd = t->d_plan_odd;
+  p.lut_cs = reinterpret_cast<const float2*>(ctx->d_lut);
+  p.fft_size = t->fft_size; p.l_nulls = t->l_nulls; p.n_out = t->n_out; p.first_symbol = t->first_symbol; p.n_symbols_kind = t->n_symbols;
+  p.n_symbols = n_symbols; p.per_frame = per_frame;
+  p.in_frame = in_frame; p.in_sym = in_sym; p.out_frame = out_frame; p.out_sym = out_sym; p.fb_frame = fb_frame;
+  const size_t smem = (size_t)(kEqChunk + kEqSpan) * sizeof(float2) + (size_t)(t->max_pilots + 2) * 20;
+  T2_CUDA(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.split = kEqSplitDefault;
+  if (const char* e = getenv("T2B200_EQ_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.split = v; }   // development aid
+  equalize_kernel<<<n_symbols * p.split, kEqThreads, smem, ctx->stream>>>(p);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return T2B200_OK;
+}
+
 extern "C" int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx_symbol, const float* freq,
                                float* cells_out, float* sro, float* phase)
 {
@@ -379,19 +410,8 @@ extern "C" int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const i
   if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)n_symbols * t->n_out * 8, &dout))) return rc;
   if (sro && (rc = t2_out_device(ctx, 2, sro, (size_t)n_symbols * 4, &dsro))) return rc;
   if (phase && (rc = t2_out_device(ctx, 3, phase, (size_t)n_symbols * 4, &dph))) return rc;
-  EqParams p;
-  p.freq = (const float2*)dfreq; p.out = (float2*)dout; p.sro = (float*)dsro; p.phase = (float*)dph; p.idx_symbol = (const int*)didx;
-  p.plans = t->d_plans; p.plan_even = t->d_plan_even; p.plan_odd = t->d_plan_odd;
-  p.lut_cs = reinterpret_cast<const float2*>(ctx->d_lut);
-  p.fft_size = t->fft_size; p.l_nulls = t->l_nulls; p.n_out = t->n_out; p.first_symbol = t->first_symbol; p.n_symbols_kind = t->n_symbols;
-  p.n_symbols = n_symbols; p.in_stride = t->fft_size; p.out_stride = t->n_out;
-  const size_t smem = (size_t)(kEqChunk + kEqSpan) * sizeof(float2) + (size_t)(t->max_pilots + 2) * 20;
-  T2_CUDA(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  p.split = kEqSplitDefault;
-  if (const char* e = getenv("T2B200_EQ_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.split = v; }   // development aid
-  equalize_kernel<<<n_symbols * p.split, kEqThreads, smem, ctx->stream>>>(p);
-  T2_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
+  if ((rc = t2_equalize_device(ctx, kind, n_symbols, n_symbols, (const int*)didx, (const float2*)dfreq, 0, t->fft_size,
+                               (float2*)dout, 0, t->n_out, (float*)dsro, (float*)dph, 0))) return rc;
   if ((rc = t2_finish_out(ctx, cells_out, dout, (size_t)n_symbols * t->n_out * 8))) return rc;
   if (sro && (rc = t2_finish_out(ctx, sro, dsro, (size_t)n_symbols * 4))) return rc;
   if (phase && (rc = t2_finish_out(ctx, phase, dph, (size_t)n_symbols * 4))) return rc;

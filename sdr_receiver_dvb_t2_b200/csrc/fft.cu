@@ -13,7 +13,7 @@
 // samples straight from global memory, does a radix-16 DFT (two radix-4 levels, constants folded), and one
 // shared-memory exchange hands the data to the second register stage (radix-A in pass A, radix-16 in pass B),
 // whose results are stored straight to global memory.
-#include "ctx.h"
+#include "stages.h"
 #include <cmath>
 #include <cstdlib>
 #include <vector>

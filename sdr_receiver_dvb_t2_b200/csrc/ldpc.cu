@@ -28,7 +28,7 @@
 //     them level by level (ldpc_schedule.cpp), everything else is one parallel step per layer.
 //   * lock-step groups of 32 (reference batch semantics) are 32 co-resident CTAs that exchange their
 //     parity verdict through one global word per iteration; groups are claimed from an atomic queue.
-#include "ctx.h"
+#include "stages.h"
 #include "ldpc_schedule.h"
 #include <cstring>
 #include <cstdlib>
@@ -850,6 +850,24 @@ extern "C" int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, 
   if (iterations && (rc = t2_finish_out(ctx, iterations, d_it, 4 * (size_t)n_cw))) return rc;
   if (d_post && (rc = t2_finish_out(ctx, post_out, d_post, (size_t)n_cw * s.N))) return rc;
   return T2B200_OK;
+}
+
+// device-level decode for the frame pipeline: everything resident, asynchronous
+int t2_ldpc_device(t2b200_ctx* ctx, int code, const int8_t* d_llr, int n_cw, uint8_t* d_bits, int32_t* d_trials,
+                   int32_t* d_iters, int max_trials, unsigned flags)
+{
+  LdpcDeviceCode* d = nullptr;
+  int rc = get_code(ctx, code, &d);
+  if (rc) return rc;
+  int k_out = d->s.K;
+  if (flags & T2B200_LDPC_BCH_DESCRAMBLE) {
+    k_out = t2_ldpc_k_bch(code);
+    if (!k_out) { ctx->err = "code has no BCH geometry"; return T2B200_ERR_ARG; }
+    if ((rc = ensure_prbs(ctx))) return rc;
+  }
+  if (n_cw == 0) return T2B200_OK;
+  if ((rc = ensure_group_sync(ctx, ldpc_sync_rows(d, ctx->sm_count, n_cw, flags), ctx->stream))) return rc;
+  return ldpc_launch(ctx, d, d_llr, n_cw, d_bits, d_trials, d_iters, nullptr, max_trials, flags, k_out, 0, ctx->stream);
 }
 
 // ---- K6 stand-alone -------------------------------------------------------------------------

@@ -1,0 +1,20 @@
+// Device-level entry points of the stages (all pointers device memory, everything asynchronous on ctx->stream):
+// what the C-ABI functions call after staging host buffers, and what the frame pipeline (frames.cu) chains directly.
+#pragma once
+#include "ctx.h"
+
+struct TiBlockDesc { long long in_off, out_off; int n_fec; };           // cell offsets of one TI block
+struct DemapBlockDesc { long long cell_off; int n_cells; int first_fec; };
+
+int t2_fft_device(t2b200_ctx* ctx, int n, const float2* d_in, int batch, float2* d_out, float2* d_tmp);
+int t2_equalize_device(t2b200_ctx* ctx, int kind, int n_symbols, int per_frame, const int* d_idx, const float2* d_freq,
+                       long long in_frame, long long in_sym, float2* d_out, long long out_frame, long long out_sym,
+                       float* d_sro, float* d_phase, long long fb_frame);
+int t2_ti_device(t2b200_ctx* ctx, int plp, const float2* d_in, float2* d_out, const TiBlockDesc* d_desc, int n_ti_blocks,
+                 int max_cells);
+int t2_ti_geometry(t2b200_ctx* ctx, int plp, int* cells_per_fec, int* n_fec_max);
+int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_ti_blocks, int max_cells,
+                    long long total_cells, int max_fec, int mod, int rotation, int fec_type, int code_rate, int8_t* d_llr,
+                    float* d_prec, float* d_snr, const float* d_prec_in);
+int t2_ldpc_device(t2b200_ctx* ctx, int code, const int8_t* d_llr, int n_cw, uint8_t* d_bits, int32_t* d_trials,
+                   int32_t* d_iters, int max_trials, unsigned flags);

@@ -29,8 +29,14 @@ SYMBOLS = [
     't2b200_ldpc_decode', 't2b200_bch_descramble',
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
     't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
-    't2b200_ts_reset', 't2b200_ts_packetize',
+    't2b200_ts_reset', 't2b200_ts_packetize', 't2b200_frames_configure', 't2b200_frames_decode',
 ]
+
+
+class FrameCfg(C.Structure):
+    """t2b200_frame_cfg"""
+    _fields_ = [(n, C.c_int) for n in ('fft_size', 'len_frame', 'n_p2', 'l_fc', 'c_p2', 'c_data', 'n_fc', 'first_cell',
+                                       'plp', 'mod', 'rotation', 'fec_type', 'code_rate', 'n_blocks', 'ti_len')]
 
 
 class T2Error(RuntimeError):
@@ -76,6 +82,8 @@ def lib():
     L.t2b200_fft.argtypes = [vp, i32, vp, i32, vp]
     L.t2b200_ts_reset.argtypes = [vp, i32]
     L.t2b200_ts_packetize.argtypes = [vp, i32, vp, i32, i32, vp, C.c_size_t, vp, vp, C.POINTER(C.c_longlong)]
+    L.t2b200_frames_configure.argtypes = [vp, C.POINTER(FrameCfg)]
+    L.t2b200_frames_decode.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, u32]
     _lib = L
     return L
 
@@ -232,6 +240,32 @@ class Engine:
         self._chk(self.L.t2b200_ts_packetize(self.h, plp, _ptr(bbframes), n, k_bch, _ptr(ts), cap, _ptr(dl), _ptr(st),
                                              C.byref(total)))
         return ts[:total.value], dl, st
+
+    # ---- whole frames in one call ----
+    def frames_configure(self, **kw):
+        cfg = FrameCfg(**kw)
+        self._frame_cfg = cfg
+        self._chk(self.L.t2b200_frames_configure(self.h, C.byref(cfg)))
+
+    def frames_decode(self, iq, flags=LDPC_GROUP32 | LDPC_BCH_DESCRAMBLE, max_trials=25, want_status=True, out=None):
+        """iq complex64[F][len_frame][fft_size] (numpy / pinned / torch cuda) -> dict(bits, trials_left, sro, phase, snr);
+        outputs live where iq lives (torch cuda in -> torch cuda out, nothing waits for the GPU)"""
+        c = self._frame_cfg
+        F = iq.shape[0]
+        n_cw = F * c.n_blocks
+        code = self.ldpc_code_id(c.fec_type, c.code_rate)
+        N, K, KB = self.ldpc_geometry(code)
+        k_out = KB if flags & LDPC_BCH_DESCRAMBLE else K
+        row = k_out // 8 if flags & LDPC_PACK_BITS else k_out
+        bits = out if out is not None else _like(iq, (n_cw, row), np.uint8)
+        r = {'bits': bits, 'trials_left': None, 'sro': None, 'phase': None, 'snr': None}
+        if want_status:
+            r['trials_left'] = _like(iq, (n_cw,), np.int32)
+            r['sro'], r['phase'] = _like(iq, (F, c.len_frame), np.float32), _like(iq, (F, c.len_frame), np.float32)
+            r['snr'] = _like(iq, (F * c.ti_len,), np.float32)
+        self._chk(self.L.t2b200_frames_decode(self.h, _ptr(iq), F, _ptr(bits), _ptr(r['trials_left']), _ptr(r['sro']),
+                                              _ptr(r['phase']), _ptr(r['snr']), max_trials, flags))
+        return r
 
     # ---- K1 ----
     def fft(self, x, out=None):

@@ -146,3 +146,24 @@ def test_config5_multi_plp_r34_pooled_fec(engine):
     bits = r['bits'].cpu().numpy()
     assert (r['trials_left'].cpu().numpy() >= 0).all()
     assert np.array_equal(bits[:nb[0]], f['bb']) and np.array_equal(bits[nb[0]:], bb1)
+
+
+def test_fused_frames_call_equals_the_staged_chain(engine):
+    """t2b200_frames_decode (one C call, everything chained on the device) gives exactly what the per-stage calls give:
+    bits, trial counts, both feedback floats of every symbol, SNR -- config 4 geometry, device and host buffers"""
+    import torch
+    t = tables('c16')
+    m = Modulator(t, mod=2, cod=1, fec_normal=False, n_blocks=96, ti_len=3, seed=9)
+    frames = [m.frame(noise_cn_db=15.5) for _ in range(3)]
+    time = np.stack([f['time'] for f in frames])
+    ch = FrameChain(engine, t, mod=2, cod=1, fec_type=0, n_blocks=96, ti_len=3)
+    a = ch.decode_frames(torch.from_numpy(time).cuda())
+    b = ch.decode_frames_fused(torch.from_numpy(time).cuda())
+    engine.sync()
+    assert np.array_equal(a['bits'].cpu().numpy(), b['bits'].cpu().numpy())
+    assert np.array_equal(a['trials_left'].cpu().numpy(), b['trials_left'].cpu().numpy())
+    assert np.array_equal(a['sro'], b['sro'].cpu().numpy()) and np.array_equal(a['phase'], b['phase'].cpu().numpy())
+    assert np.array_equal(a['snr'], b['snr'].cpu().numpy())
+    assert np.array_equal(b['bits'].cpu().numpy(), np.concatenate([f['bb'] for f in frames]))
+    c = ch.decode_frames_fused(time)                             # pageable host buffers in and out
+    assert np.array_equal(c['bits'], b['bits'].cpu().numpy()) and np.array_equal(c['sro'], a['sro'])
