@@ -30,13 +30,19 @@ int main(int argc, char** argv)
   for (int s = 0; s < nd; ++s) { map_rows[s] = data_map.data() + (size_t)s * m.k_total; ref_rows[s] = data_ref.data() + (size_t)s * m.k_total; }
 
   FILE* out = fopen(argv[2], "wb");
-  int n_frames = 0;
+  FILE* ts = argc > 3 ? fopen(argv[3], "wb") : nullptr;       // optional: the datagrams of the bb_de_header mirror, back to back
+  int n_frames = 0, n_datagrams = 0;
   try {
     t2b200::context ctx(0);
     t2b200::fast_fourier_transform fft(ctx);
     t2b200::p2_symbol_equalizer p2(ctx);
     t2b200::data_symbol data(ctx);
-    t2b200::fec_chain fec(ctx, [&](int, int len, uint8_t* bits) { fwrite(bits, 1, len, out); ++n_frames; });
+    t2b200::bb_de_header deheader(ctx, [&](const uint8_t* d, int len) { if (ts) fwrite(d, 1, len, ts); ++n_datagrams; });
+    deheader.set_out(plp.id);
+    t2b200::fec_chain fec(ctx, [&](int id, int len, uint8_t* bits) {          // emit bit_descramble -> deheader->execute
+      fwrite(bits, 1, len, out); ++n_frames;
+      deheader.execute(id, len, bits);
+    });
     t2b200::complex* in_fft = fft.init(m.fft_size);
     p2.init(m, p2_map.data(), p2_ref.data(), he_p.data(), ho_p.data(), amps[2]);
     data.init(m, map_rows.data(), ref_rows.data(), he_d.data(), ho_d.data(), amps[0], amps[1]);
@@ -48,8 +54,9 @@ int main(int argc, char** argv)
       if (l == 0) fec.l1_dyn_execute(num_blocks, m.c_p2, p2.execute(0, cell, sro, ph));
       else fec.execute(m.c_data, data.execute(l, cell, sro, ph));
     }
-  } catch (const std::exception& e) { std::fprintf(stderr, "facade_check: %s\n", e.what()); fclose(out); return 1; }
+  } catch (const std::exception& e) { std::fprintf(stderr, "facade_check: %s\n", e.what()); fclose(out); if (ts) fclose(ts); return 1; }
   fclose(out);
-  std::printf("bbframes %d\n", n_frames);
+  if (ts) fclose(ts);
+  std::printf("bbframes %d datagrams %d\n", n_frames, n_datagrams);
   return 0;
 }

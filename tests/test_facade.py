@@ -41,7 +41,7 @@ def test_facade_decodes_config4_frame():
     m = Modulator(t, mod=2, cod=1, fec_normal=False, n_blocks=64, ti_len=2, seed=9)
     fr = m.frame(noise_cn_db=15.0)
     with tempfile.TemporaryDirectory() as d:
-        fin, fout = os.path.join(d, 'in.bin'), os.path.join(d, 'out.bin')
+        fin, fout, fts = os.path.join(d, 'in.bin'), os.path.join(d, 'out.bin'), os.path.join(d, 'ts.bin')
         with open(fin, 'wb') as f:
             hdr = [p['fft_size'], p['k_total'], p['l_nulls'], p['n_p2'], p['n_data'], p['len_frame'], p['l_fc'], p['c_p2'], p['c_data'],
                    p['n_fc'], 0, 1, 2, 1, 0, 32, 2, 0, 360, 64]
@@ -54,8 +54,14 @@ def test_facade_decodes_config4_frame():
             for k in ('h_even_data', 'h_odd_data', 'h_even_p2', 'h_odd_p2'):
                 t[k].astype(np.int32).tofile(f)
             fr['time'].astype(np.complex64).tofile(f)
-        r = subprocess.run([b, fin, fout], capture_output=True, text=True, timeout=300)
+        r = subprocess.run([b, fin, fout, fts], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         assert 'bbframes 64' in r.stdout
         got = np.fromfile(fout, np.uint8).reshape(64, -1)
+        ts = np.fromfile(fts, np.uint8)
     assert np.array_equal(got, fr['bb'])
+    # ... and the bb_de_header mirror turned them into the TS the reference's bb_de_header makes of them (oracle port)
+    from oracle import pyoracle as O
+    port = O.PortTs()
+    assert 'datagrams 64' in r.stdout
+    assert np.array_equal(ts, np.concatenate([port.feed(b) for b in fr['bb']]))
