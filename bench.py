@@ -240,8 +240,8 @@ def run_t2b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL prints its version banner on stdout: keep stdout to the one JSON line
+        # NCCL prints its version banner / debug lines on stdout: send them to stderr, stdout carries the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
