@@ -240,9 +240,18 @@ def run_t2b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner / debug lines on stdout: send them to stderr, stdout carries the one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on the C stdout while the communicator comes up: point fd 1 at stderr for that
+        # moment, stdout carries the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if dist is not None:
