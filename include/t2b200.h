@@ -13,6 +13,10 @@
  * call that received a host OUTPUT pointer returns, that buffer is filled.  t2b200_sync() drains
  * the stream.  There is no CPU fallback: without a usable GPU every compute call fails with
  * T2B200_ERR_CUDA.
+ *
+ * Threads: a context is used by one host thread at a time; use one context (and stream) per thread -- they share the GPU
+ * (bench.py runs two).  Kernels of different contexts overlap: the LDPC decoder leaves room on every SM for the streaming
+ * stages of another context.
  */
 #ifndef T2B200_H
 #define T2B200_H

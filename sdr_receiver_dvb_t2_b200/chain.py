@@ -79,8 +79,13 @@ class FrameChain:
         return _T()
 
     def stage_ms(self):
-        """mean device milliseconds per stage from the collected events"""
-        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.events or {}).items()}
+        """median device milliseconds per stage from the collected events (a stage that had to wait for an allocation once
+        does not move it)"""
+        out = {}
+        for k, v in (self.events or {}).items():
+            ms = sorted(a.elapsed_time(b) for a, b in v)
+            out[k] = ms[len(ms) // 2]
+        return out
 
     def demodulate(self, time):
         """time: torch complex64 cuda [F][len_frame][fft_size] -> PLP cell stream [F][n_blocks*cpf] (arrival order),
