@@ -61,19 +61,40 @@ def ordered_sum(t, CH=64, E=4):
             sbf=frombits((Es<<23)|(Sb&0x7fffff))
             s=np.float32(sbf+t[base+k]); base+=k+1
     return s,passes
-rng=np.random.default_rng(1)
+
+
 def serial(t):
-    s=np.float32(0)
-    for x in t: s=np.float32(s+x)
+    s = np.float32(0)
+    for x in t:
+        s = np.float32(s + x)
     return s
-for trial in range(300):
-    n=int(rng.integers(1,3000))
-    kind=trial%5
-    if kind==0: t=(rng.standard_normal(n)**2).astype(np.float32)
-    elif kind==1: t=(rng.integers(0,64,n)/np.float32(8)).astype(np.float32)      # many ties
-    elif kind==2: t=(rng.integers(0,4,n)*np.float32(2.0**-int(rng.integers(0,30)))).astype(np.float32)
-    elif kind==3: t=(10.0**rng.uniform(-12,6,n)).astype(np.float32)
-    else: t=np.where(rng.random(n)<0.3,0,rng.integers(1,5,n)*np.float32(0.5)).astype(np.float32); t[rng.integers(0,n)]=np.float32(3e7)
-    a=serial(t); b,p=ordered_sum(t)
-    assert fbits(a)==fbits(b),(trial,kind,n,a,b)
-print('model ok')
+
+
+def random_terms(kind, n, rng):
+    """non-negative float32 terms of different characters: squares of normals, many exact ties, tiny + one huge, ..."""
+    if kind == 0:
+        return (rng.standard_normal(n) ** 2).astype(np.float32)
+    if kind == 1:
+        return (rng.integers(0, 64, n) / np.float32(8)).astype(np.float32)                     # many ties
+    if kind == 2:
+        return (rng.integers(0, 4, n) * np.float32(2.0 ** -int(rng.integers(0, 30)))).astype(np.float32)
+    if kind == 3:
+        return (10.0 ** rng.uniform(-12, 6, n)).astype(np.float32)
+    t = np.where(rng.random(n) < 0.3, 0, rng.integers(1, 5, n) * np.float32(0.5)).astype(np.float32)
+    t[rng.integers(0, n)] = np.float32(3e7)
+    return t
+
+
+def check(trials=300, seed=1, chunk=64, per_thread=4):
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        n = int(rng.integers(1, 3000))
+        t = random_terms(trial % 5, n, rng)
+        a = serial(t)
+        b, _ = ordered_sum(t, CH=chunk, E=per_thread)
+        assert fbits(a) == fbits(b), (trial, trial % 5, n, a, b)
+    return trials
+
+
+if __name__ == '__main__':
+    print('model ok:', check(), 'trials')
