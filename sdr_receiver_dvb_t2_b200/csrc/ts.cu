@@ -20,7 +20,13 @@ namespace {
 
 constexpr int PKT = 188;
 
-struct TsHdr { int status, dfl, syncd; };              // status: 0 HEM ok, 1 header CRC, 2 SYNCD == 65535, 3 normal mode
+struct TsHdr {                                         // status: 0 HEM ok, 1 header CRC, 2 SYNCD == 65535, 3 normal mode
+  int status, dfl, syncd;
+  // what a frame does when it is entered with a held-back tail (the usual case: its packet phase after the head is 0, so
+  // everything behind the head depends on the frame alone) -- computed by the parallel parse kernel, divisions included
+  int main_n, main_out;                                // data bytes / output bytes (with sync bytes) of the main run
+  int ntail, tail_sync, end_packet, end_buffer;        // held-back bytes, sync position inside them, state afterwards
+};
 struct TsDesc {
   long long out_off; int out_len;
   int carry_len, carry_src, carry_bit, carry_sync;     // carry_src: frame index, -1 = state buffer of the previous call
@@ -41,6 +47,37 @@ __device__ __forceinline__ unsigned field(const uint8_t* b, int n)
   return v;
 }
 
+// main run + held-back tail of a frame whose data field (behind SYNCD) has `dfl` bits left and whose packet index is
+// idx_packet when the main run starts (bb_de_header.cpp:384-428)
+struct TsBody { int M, T, phase, ntail, tail_sync, end_packet, end_buffer, split; };
+__device__ __forceinline__ TsBody ts_body(int dfl, int idx_packet)
+{
+  TsBody b = {0, 0, 0, 0, -1, idx_packet, 0, 0};
+  if (dfl >= PKT * 8) {
+    const int M = (dfl - PKT * 8) / 8 + 1;
+    const int phase = idx_packet == PKT ? 0 : idx_packet;
+    int T;
+    if (phase == 0) T = M + (M + PKT - 2) / (PKT - 1);
+    else if (M <= PKT - phase) T = M;
+    else T = M + (M - (PKT - phase) + PKT - 2) / (PKT - 1);
+    b.M = M; b.T = T; b.phase = phase;
+    dfl -= 8 * M;
+    idx_packet = (phase + T) % PKT;
+    if (idx_packet == 0) idx_packet = PKT;
+  }
+  if (dfl > 0) {                                         // held back for the next frame (bb_de_header.cpp:386-402)
+    b.split = 1;
+    const int ntail = dfl / 8;
+    b.ntail = ntail;
+    if (idx_packet == PKT) { if (ntail > 0) b.tail_sync = 0; }
+    else if (idx_packet != 0 && PKT - idx_packet < ntail) b.tail_sync = PKT - idx_packet;
+    if (b.tail_sync >= 0) idx_packet = 1 + (ntail - b.tail_sync); else idx_packet += ntail;
+    b.end_buffer = ntail + (b.tail_sync >= 0 ? 1 : 0);
+  }
+  b.end_packet = idx_packet;
+  return b;
+}
+
 __global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames, int k_bch, TsHdr* __restrict__ hdr)
 {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,6 +94,9 @@ __global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames
   h.syncd = (int)field(b + 56, 16);
   h.status = reg == 0xABu ? 0 : reg == 0u ? 3 : 1;
   if (h.status == 0 && h.syncd == 65535) h.status = 2;
+  const TsBody body = ts_body(h.dfl - h.syncd, PKT);     // entered with a tail: the head completes a packet first
+  h.main_n = body.M; h.main_out = body.T; h.ntail = body.split ? body.ntail : -1; h.tail_sync = body.tail_sync;
+  h.end_packet = body.end_packet; h.end_buffer = body.end_buffer;
   hdr[f] = h;
 }
 
@@ -82,12 +122,12 @@ __global__ void __launch_bounds__(32) ts_scan_kernel(const TsHdr* __restrict__ h
         d.out_off = off; d.out_len = 0; d.carry_len = 0; d.carry_src = -1; d.carry_bit = 0; d.carry_sync = -1;
         d.head_n = 0; d.head_f0 = 0; d.main_bit = 0; d.main_n = 0; d.main_phase = 0;
         if (h.status == 0) {
-          int in_bit = 80, dfl = h.dfl;
+          int in_bit = 80;
+          TsBody b;
           if (split) {
-            split = 0;
             d.carry_src = tail_src; d.carry_bit = tail_bit; d.carry_sync = tail_sync;
             d.carry_len = idx_buffer;
-            const int missing = PKT - idx_packet, sb = h.syncd / 8;
+            const int missing = PKT - idx_packet, sb = h.syncd >> 3;
             if (missing <= sb) {
               d.head_n = missing;
               in_bit += missing == sb ? missing * 8 : h.syncd;
@@ -95,33 +135,22 @@ __global__ void __launch_bounds__(32) ts_scan_kernel(const TsHdr* __restrict__ h
               d.head_n = sb; d.head_f0 = missing - sb;
               in_bit += sb * 8;
             }
-            idx_packet = PKT;
+            // behind the head the packet index is 188: the parse kernel has done the rest
+            b.M = h.main_n; b.T = h.main_out; b.phase = 0; b.split = h.ntail >= 0; b.ntail = max(h.ntail, 0);
+            b.tail_sync = h.tail_sync; b.end_packet = h.end_packet; b.end_buffer = h.end_buffer;
           } else {
             in_bit += h.syncd;
+            b = ts_body(h.dfl - h.syncd, idx_packet);        // rare: first frame, or the previous one left no tail
           }
-          dfl -= h.syncd;
-          int T = 0;
-          if (dfl >= PKT * 8) {
-            const int M = (dfl - PKT * 8) / 8 + 1;
-            const int phase = idx_packet == PKT ? 0 : idx_packet;
-            if (phase == 0) T = M + (M + PKT - 2) / (PKT - 1);
-            else if (M <= PKT - phase) T = M;
-            else T = M + (M - (PKT - phase) + PKT - 2) / (PKT - 1);
-            d.main_bit = in_bit; d.main_n = M; d.main_phase = phase;
-            in_bit += 8 * M; dfl -= 8 * M;
-            idx_packet = (phase + T) % PKT;
-            if (idx_packet == 0) idx_packet = PKT;
+          d.main_bit = in_bit; d.main_n = b.M; d.main_phase = b.phase;
+          in_bit += 8 * b.M;
+          idx_packet = b.end_packet;
+          split = b.split;
+          if (b.split) {
+            tail_src = f; tail_bit = in_bit; tail_ndata = b.ntail; tail_sync = b.tail_sync;
+            idx_buffer = b.end_buffer;
           }
-          if (dfl > 0) {                                     // held back for the next frame (bb_de_header.cpp:386-402)
-            split = 1;
-            const int ntail = dfl / 8;
-            tail_src = f; tail_bit = in_bit; tail_ndata = ntail; tail_sync = -1;
-            if (idx_packet == PKT) { if (ntail > 0) tail_sync = 0; }
-            else if (idx_packet != 0 && PKT - idx_packet < ntail) tail_sync = PKT - idx_packet;
-            if (tail_sync >= 0) idx_packet = 1 + (ntail - tail_sync); else idx_packet += ntail;
-            idx_buffer = ntail + (tail_sync >= 0 ? 1 : 0);
-          }
-          d.out_len = d.carry_len + d.head_n + d.head_f0 + T;
+          d.out_len = d.carry_len + d.head_n + d.head_f0 + b.T;
         }
         sd[i] = d;
         off += d.out_len;
