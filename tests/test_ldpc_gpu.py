@@ -110,3 +110,22 @@ def test_device_pointers_and_large_batch_properties(engine):
     tl = r['trials_left'].cpu().numpy()
     assert (tl >= 0).all()
     assert np.array_equal(bits, info)
+
+
+def test_host_buffer_pipeline_equals_device_path(engine):
+    """more than 512 codewords in HOST memory take the chunked H2D | decode | D2H pipeline (two chunks here, the second
+    ragged): same bits, trial counts and iteration counts as one launch on device-resident buffers"""
+    import torch
+    code = 7
+    n = 512 + 3 * 32 + 9
+    llr, info = O.make_llr(code, n, 2.6, seed=41)
+    flags = E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE
+    h = engine.ldpc_decode(code, llr, flags=flags)                       # numpy in, numpy out: pipelined path
+    d = engine.ldpc_decode(code, torch.from_numpy(llr).cuda(), flags=flags)
+    engine.sync()
+    # lock-step groups are formed inside each 512-codeword chunk, i.e. at the same codeword boundaries as in one launch
+    assert np.array_equal(h['bits'], d['bits'].cpu().numpy())
+    assert np.array_equal(h['trials_left'], d['trials_left'].cpu().numpy())
+    assert np.array_equal(h['iterations'], d['iterations'].cpu().numpy())
+    N, K, KB = engine.ldpc_geometry(code)
+    assert np.array_equal(h['bits'][h['trials_left'] >= 0], O.bch_strip_descramble(info, K, KB)[h['trials_left'] >= 0])
