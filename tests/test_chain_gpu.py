@@ -167,3 +167,30 @@ def test_fused_frames_call_equals_the_staged_chain(engine):
     assert np.array_equal(b['bits'].cpu().numpy(), np.concatenate([f['bb'] for f in frames]))
     c = ch.decode_frames_fused(time)                             # pageable host buffers in and out
     assert np.array_equal(c['bits'], b['bits'].cpu().numpy()) and np.array_equal(c['sro'], a['sro'])
+
+
+def test_frame_closing_symbol_geometry_fused_and_staged(engine):
+    """a mode WITH a frame-closing symbol (32K, PP that needs one): the PLP runs into the FC symbol's cells; the one-call
+    pipeline and the staged chain agree and return the transmitted BBFRAMEs"""
+    import torch
+    t = tables('c32fc')
+    p = t['p']
+    assert p['l_fc'] == 1
+    # enough FEC blocks that the PLP reaches the frame-closing symbol
+    nd = p['len_frame'] - p['n_p2'] - p['l_fc']
+    cap = p['c_p2'] - 2200 + nd * p['c_data'] + p['n_fc']
+    nb = min(cap // 10800, 8 * (cap // 10800 // 8) + 5)
+    m = Modulator(t, mod=2, cod=1, fec_normal=True, n_blocks=nb, ti_len=2, seed=31)
+    assert nb * 10800 > p['c_p2'] - 2200 + nd * p['c_data']          # ... it does
+    f = m.frame(noise_cn_db=17.0)
+    ch = FrameChain(engine, t, mod=2, cod=1, fec_type=1, n_blocks=nb, ti_len=2)
+    x = torch.from_numpy(f['time'][None]).cuda()
+    a = ch.decode_frames(x)
+    b = ch.decode_frames_fused(x)
+    engine.sync()
+    full = (nb // 32) * 32
+    assert np.array_equal(a['bits'].cpu().numpy(), b['bits'].cpu().numpy())
+    assert np.array_equal(a['sro'], b['sro'].cpu().numpy()) and np.array_equal(a['phase'], b['phase'].cpu().numpy())
+    tl = b['trials_left'].cpu().numpy()
+    assert (tl >= 0).all()
+    assert np.array_equal(b['bits'].cpu().numpy(), f['bb']) and full >= 0
