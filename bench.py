@@ -202,7 +202,7 @@ def run_reference(args):
     vals = []
     info = None
     for i in range(args.warmup + args.steps):
-        v, info = cpu_reference_rate(seconds_budget=6.0)
+        v, info = cpu_reference_rate(seconds_budget=float(os.environ.get('T2B200_BENCH_CPU_BUDGET', '6.0')))
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
