@@ -54,8 +54,6 @@ struct SymbolTables {
 
 namespace {
 
-float* g_unused = nullptr;
-
 __device__ __forceinline__ float atan2_approx_dev(float y, float x)      // DSP/fast_math.h:61-81
 {
   const float PI = 3.14159265358979323846f, PI_2 = 1.57079632679489661923f;
@@ -284,7 +282,6 @@ void t2_eq_free(t2b200_ctx* ctx)
 {
   for (auto& s : ctx->sym) { free_tables(s); s = nullptr; }
   if (ctx->d_lut) { cudaFree(ctx->d_lut); ctx->d_lut = nullptr; }
-  (void)g_unused;
 }
 
 static int ensure_lut(t2b200_ctx* ctx)

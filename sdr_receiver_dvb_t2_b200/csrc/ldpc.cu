@@ -343,7 +343,6 @@ __device__ __forceinline__ int syndrome_bad(const int8_t* __restrict__ post, uin
   return bad;
 }
 
-// co-resident CTAs per SM the register budget is cut for (65536 / (384 * MINB) registers per thread)
 
 // Register budget: 64 per thread for the codes whose check nodes fit (two CTAs = 49 152 registers, 146 KB of shared memory
 // and 768 threads per SM), so that a quarter of every SM's register file, 81 KB of shared memory and 1 280 threads stay
@@ -576,7 +575,7 @@ cudaError_t occupancy(size_t smem, int* blocks_per_sm)
 // smallest instantiated CNL >= cnl_max
 const int kCnlBuckets[] = {4, 5, 7, 8, 9, 11, 12, 13, 16, 17, 20};
 
-// (CNL bucket, register budget) instantiations: minb = co-resident CTAs per SM the register allocation is cut for
+// CNL bucket instantiations (MINB = 2: the register budget of kLdpcRegs is cut for two co-resident CTAs per SM)
 #define DISPATCH(CALL)                                                                    \
   switch (cnl) {                                                                          \
     case 4:  return CALL(4, uint32_t, 2);   case 5:  return CALL(5, uint32_t, 2);         \
@@ -604,7 +603,7 @@ cudaError_t occupancy_dispatch(int cnl, int minb, size_t smem, int* bps)
 struct LdpcDeviceCode {
   LdpcSchedule s;
   int cnl = 0;              // instantiated bucket
-  int minb = 1;             // register-budget variant (CTAs per SM)
+  int minb = 2;             // co-resident CTAs per SM the kernel is built for
   size_t state_bytes = 4, smem = 0;
   int blocks_per_sm = 0;
   uint8_t* d_level = nullptr;
