@@ -379,7 +379,9 @@ __global__ void __maxnreg__(kLdpcRegs<CNL>) ldpc_decode_kernel(const __grid_cons
       unsigned* w = p.gqueue + 1 + (size_t)slot * (n_groups + 1) + round;
       int gg;
       if (lane == 0) {
-        gg = (int)atomicAdd(p.gqueue, 1u);
+        // last group first: a trailing partial group costs a full group's time, so it should not be the one left over
+        const int claim = (int)atomicAdd(p.gqueue, 1u);
+        gg = claim < n_groups ? n_groups - 1 - claim : n_groups;
         if (GL > 1) { __threadfence(); atomicExch(w, (unsigned)gg + 1u); }
       } else {
         unsigned v, polls = 0;
