@@ -125,6 +125,10 @@ int t2b200_bch_descramble(t2b200_ctx* ctx, int code, const uint8_t* bits_in, int
  * (llr_demapper.cpp:110-130, constants llr_demapper.h:64-78): address_out int32[64800 | 16200].        */
 int t2b200_cell_permutation(int n_fec_blocks, int cells_per_fec, int32_t* perm_out);
 int t2b200_demap_address_table(int fec_type, int mod, int code_rate, int32_t* address_out);
+/* frequency de-interleaver tables of address_freq_deinterleaver (address_freq_deinterleaver.cpp:28-209; EN 302 755 8.5):
+ * h_even_out / h_odd_out int32[n_cells] for a symbol kind with n_cells cells (c_p2, c_data or n_fc); fft_size 16384 or
+ * 32768.  The drop-in may hand the reference's own tables to t2b200_eq_configure instead.                               */
+int t2b200_freq_deinterleaver_table(int fft_size, int n_cells, int32_t* h_even_out, int32_t* h_odd_out);
 
 /* Replaces time_deinterleaver::start for one PLP (time_deinterleaver.cpp:38-145): geometry from
  * (fec_type, mod), permutation for plp_num_blocks_max FEC blocks.  permutation == NULL builds it

@@ -421,6 +421,15 @@ extern "C" int t2b200_demap_address_table(int fec_type, int mod, int code_rate, 
   return T2B200_OK;
 }
 
+extern "C" int t2b200_freq_deinterleaver_table(int fft_size, int n_cells, int32_t* h_even_out, int32_t* h_odd_out)
+{
+  std::vector<int32_t> e, o;
+  if (!h_even_out || !h_odd_out || !t2_freq_deinterleaver_tables(fft_size, n_cells, e, o)) return T2B200_ERR_ARG;
+  std::copy(e.begin(), e.end(), h_even_out);
+  std::copy(o.begin(), o.end(), h_odd_out);
+  return T2B200_OK;
+}
+
 extern "C" int t2b200_ti_configure(t2b200_ctx* ctx, int plp, int fec_type, int mod, int n_fec_blocks_max,
                                    const int32_t* permutation)
 {

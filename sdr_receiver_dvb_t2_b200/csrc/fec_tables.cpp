@@ -86,3 +86,45 @@ bool t2_demap_address_table(int fec_type, int mod, int code_rate, std::vector<in
   for (int i = 0; i < n; ++i) address[i] = twist[(i / ncols) * ncols + dm[i % ncols]];
   return true;
 }
+
+// ---- frequency de-interleaver ----------------------------------------------------------------------------------
+// The interleaver permutes the cells of a symbol by H(q): a shift register R' of Nr - 1 bits (Nr = log2 FFT size) steps
+// through a maximal-length sequence, a fixed wire permutation (different for even and odd symbols below 32K) turns R'_i
+// into R_i, the toggling top bit (i mod 2) is put in front, and values outside the symbol are skipped.  The receiver
+// needs the inverse mapping; in 32K the even-symbol permutation IS the inverse of the odd one
+// (address_freq_deinterleaver.cpp:149-155,185-196), so there h_even is the odd forward table itself.
+bool t2_freq_deinterleaver_tables(int fft_size, int n_cells, std::vector<int32_t>& h_even, std::vector<int32_t>& h_odd)
+{
+  static const int perm16_even[13] = {9, 7, 6, 10, 12, 5, 1, 11, 0, 2, 3, 4, 8};       // EN 302 755 table 74 (16K)
+  static const int perm16_odd[13] = {6, 8, 10, 12, 2, 0, 4, 1, 11, 3, 5, 9, 7};
+  static const int perm32[14] = {7, 13, 3, 4, 9, 2, 12, 11, 1, 8, 10, 0, 5, 6};        // (32K)
+  static const int taps16[6] = {0, 1, 4, 5, 9, 11}, taps32[4] = {0, 1, 2, 12};
+  const int *pe, *po, *taps; int ntaps, nbits;
+  if (fft_size == 16384) { pe = perm16_even; po = perm16_odd; taps = taps16; ntaps = 6; nbits = 13; }
+  else if (fft_size == 32768) { pe = perm32; po = perm32; taps = taps32; ntaps = 4; nbits = 14; }
+  else return false;
+  if (n_cells <= 0 || n_cells > fft_size) return false;
+  std::vector<int32_t> fwd_even, fwd_odd;                       // H(q) of the transmitter, even / odd symbols
+  fwd_even.reserve(n_cells); fwd_odd.reserve(n_cells);
+  unsigned reg = 0;
+  for (int i = 0; i < fft_size; ++i) {
+    if (i < 2) reg = 0;
+    else if (i == 2) reg = 1;
+    else {
+      unsigned fb = 0;
+      for (int k = 0; k < ntaps; ++k) fb ^= (reg >> taps[k]) & 1u;
+      reg = ((reg & ((1u << nbits) - 1u)) >> 1) | (fb << (nbits - 1));
+    }
+    unsigned e = 0, o = 0;
+    for (int n = 0; n < nbits; ++n) { e |= ((reg >> n) & 1u) << pe[n]; o |= ((reg >> n) & 1u) << po[n]; }
+    const unsigned top = (unsigned)(i & 1) * (unsigned)(fft_size / 2);
+    if ((int)(e + top) < n_cells) fwd_even.push_back((int32_t)(e + top));
+    if ((int)(o + top) < n_cells) fwd_odd.push_back((int32_t)(o + top));
+  }
+  if ((int)fwd_even.size() != n_cells || (int)fwd_odd.size() != n_cells) return false;
+  h_even.assign(n_cells, 0); h_odd.assign(n_cells, 0);
+  for (int i = 0; i < n_cells; ++i) h_odd[fwd_odd[i]] = i;
+  if (fft_size == 32768) h_even = fwd_odd;                      // inverse of the inverse
+  else for (int i = 0; i < n_cells; ++i) h_even[fwd_even[i]] = i;
+  return true;
+}

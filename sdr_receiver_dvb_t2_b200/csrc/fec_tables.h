@@ -18,3 +18,8 @@ int t2_bits_per_cell(int mod);
 // address[n] for the n-th soft bit the demapper produces inside a FEC frame (cell-major, per cell the
 // order L0(I),L0(Q),L1(I),L1(Q),...): index into the de-interleaved FECFRAME.  Empty for QPSK (identity).
 bool t2_demap_address_table(int fec_type, int mod, int code_rate, std::vector<int32_t>& address);
+
+// Frequency de-interleaver address tables of the receiver (EN 302 755 clause 8.5; address_freq_deinterleaver.cpp:28-209):
+// h_even / h_odd [n_cells] such that the d-th data cell of a symbol (ascending carrier order) is cell h[d] of the
+// interleaving frame.  16K and 32K (the FFT sizes with one P2 symbol, the ones the reference receives).
+bool t2_freq_deinterleaver_tables(int fft_size, int n_cells, std::vector<int32_t>& h_even, std::vector<int32_t>& h_odd);

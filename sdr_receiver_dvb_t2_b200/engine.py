@@ -27,7 +27,7 @@ SYMBOLS = [
     't2b200_version', 't2b200_launch_count', 't2b200_set_option',
     't2b200_ldpc_code_id', 't2b200_ldpc_n', 't2b200_ldpc_k', 't2b200_ldpc_k_bch',
     't2b200_ldpc_decode', 't2b200_bch_descramble',
-    't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
+    't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_freq_deinterleaver_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
     't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
     't2b200_ts_reset', 't2b200_ts_packetize', 't2b200_frames_configure', 't2b200_frames_decode',
 ]
@@ -74,6 +74,7 @@ def lib():
     L.t2b200_bch_descramble.argtypes = [vp, i32, vp, i32, vp]
     L.t2b200_cell_permutation.argtypes = [i32, i32, vp]
     L.t2b200_demap_address_table.argtypes = [i32, i32, i32, vp]
+    L.t2b200_freq_deinterleaver_table.argtypes = [i32, i32, vp, vp]
     L.t2b200_ti_configure.argtypes = [vp, i32, i32, i32, i32, vp]
     L.t2b200_ti_deinterleave.argtypes = [vp, i32, vp, i32, vp, vp]
     L.t2b200_demap.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]
@@ -311,3 +312,12 @@ def demap_address_table(fec_type, mod, code_rate):
     if rc != OK:
         raise T2Error('t2b200_demap_address_table rc=%d' % rc)
     return out
+
+
+def freq_deinterleaver_table(fft_size, n_cells):
+    """(h_even, h_odd) int32[n_cells] of address_freq_deinterleaver for a symbol kind with n_cells cells"""
+    e, o = np.zeros(n_cells, np.int32), np.zeros(n_cells, np.int32)
+    rc = lib().t2b200_freq_deinterleaver_table(fft_size, n_cells, e.ctypes.data, o.ctypes.data)
+    if rc != OK:
+        raise T2Error('t2b200_freq_deinterleaver_table rc=%d' % rc)
+    return e, o
