@@ -227,7 +227,6 @@ def run_t2b200(args):
     import sdr_receiver_dvb_t2_b200 as t2
     from sdr_receiver_dvb_t2_b200 import engine as E
     from sdr_receiver_dvb_t2_b200.chain import FrameChain
-    from tools.make_golden_tables import load as load_tables
     from tools.modulator import Modulator
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -267,7 +266,8 @@ def run_t2b200(args):
     eng.set_option(E.OPT_DEMAP_SATURATE, 1)
     plain = int(os.environ.get('T2B200_BENCH_PLAIN_LAUNCH', '0'))
     eng.set_option(E.OPT_LDPC_PLAIN_LAUNCH, plain)          # experiment: measured no gain over the cooperative launch (237.7k vs 242.1k cw/s)
-    tables = load_tables(os.path.join(ROOT, 'tests', 'golden', 'tables_c32.npz'))
+    # init-time tables of the mode (carrier maps, pilot references, frequency de-interleaver): built natively (csrc/pilots.cpp)
+    tables = E.mode_tables(E.mode_init('32K', True, 7, '1/128', 59))
     p = tables['p']
     L, N = p['len_frame'], p['fft_size']
     F = FRAMES_PER_STEP

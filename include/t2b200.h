@@ -186,6 +186,32 @@ int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int first_symb
 int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx_symbol,
                     const float* freq, float* cells_out, float* sro, float* phase);
 
+/* ---- a2: transmission-mode parameters and pilot tables, built natively ------------------------ */
+/* The subset of dvbt2_parameters (dvbt2_definition.h:215-260) the hot path needs, for SISO 16K / 32K.  Enum values are
+ * the reference's: fft_mode 4 = 16K, 5 = 32K (dvbt2_definition.h:121-131); carrier_mode 0 normal / 1 extended;
+ * pilot_pattern 0..7 = PP1..PP8; guard_interval_mode 0..6 = 1/32 1/16 1/8 1/4 1/128 19/128 19/256; papr_mode 0..3.    */
+typedef struct {
+  int fft_mode, carrier_mode, pilot_pattern, guard_interval_mode, papr_mode;
+  int fft_size, k_total, k_ext, k_offset, l_nulls, guard_interval_size;
+  int n_p2, c_p2, c_data, n_fc, c_fc, l_fc;
+  int n_data, len_frame;          /* n_data = symbols behind P2 including the frame-closing one; len_frame = n_p2 + n_data */
+  int dx, dy;                     /* scattered-pilot spacing of the pilot pattern                                       */
+  float amp_p2, amp_sp, amp_cp;   /* pilot boosts (pilot_generator.cpp:376-507)                                         */
+} t2b200_mode;
+/* Replaces dvbt2_p2_parameters_init + dvbt2_bwt_ext_parameters_init + dvbt2_data_parameters_init
+ * (dvbt2_definition.cpp:20-159,161-648).  T2B200_ERR_ARG for combinations EN 302 755 does not define (c_data == 0).     */
+int t2b200_mode_init(int fft_mode, int carrier_mode, int pilot_pattern, int guard_interval_mode, int n_data,
+                     int papr_mode, t2b200_mode* out);
+/* Replaces pilot_generator::p2_generator / data_generator (pilot_generator.cpp:69-132): the carrier-type map
+ * (dvbt2_definition.h:103-113) and the BPSK pilot reference (+-amplitude, 0 on data carriers) of one symbol kind.
+ *   kind T2B200_SYM_P2 / _FC: carrier_map int32[k_total], pilot_refer float[k_total]
+ *   kind T2B200_SYM_DATA:     [len_frame - l_fc - n_p2][k_total] each, one row per data symbol                         */
+int t2b200_pilot_tables(const t2b200_mode* mode, int kind, int32_t* carrier_map, float* pilot_refer);
+/* t2b200_eq_configure for P2, data and frame-closing symbols of a mode from natively built pilot and frequency
+ * de-interleaver tables: what p2_symbol::init / data_symbol::init / fc_symbol::init set up (p2_symbol.cpp:43-76,
+ * data_symbol.cpp:39-106, fc_symbol.cpp:37-80) without the reference's pilot_generator / address_freq_deinterleaver.  */
+int t2b200_eq_configure_mode(t2b200_ctx* ctx, const t2b200_mode* mode);
+
 /* ---- K1: OFDM FFT --------------------------------------------------------------------------- */
 /* Replaces fast_fourier_transform::init + execute (DSP/fast_fourier_transform.h:54-70) for a batch of
  * symbols: out[b] = halves-swapped, unnormalised forward DFT (FFTW_FORWARD sign) of in[b].

@@ -154,9 +154,10 @@ int ref_rx_init(int fft_mode, int carrier_mode, int pilot_pattern, int guard_int
   r->p2->init(d, r->pilot, r->fq);
   // what l1_pre_info writes back (p2_symbol.cpp:493-499)
   if (d.carrier_mode != carrier_mode) {
+    // p2_symbol::init always falls back to extended carriers (it calls dvbt2_p2_parameters_init, dvbt2_definition.cpp:89),
+    // so the reference's P2 tables exist for the extended mode only; the data / frame-closing side follows L1-pre.
     d.carrier_mode = carrier_mode;
     dvbt2_bwt_ext_parameters_init(d);
-    r->p2->init(d, r->pilot, r->fq);          // the reference would see the new k_total on its next init
   }
   d.guard_interval_mode = guard_interval_mode; d.papr_mode = papr_mode; d.pilot_pattern = pilot_pattern; d.n_data = n_data;
   r->data = make_zeroed<data_symbol>();

@@ -30,6 +30,7 @@ SYMBOLS = [
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_freq_deinterleaver_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
     't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
     't2b200_ts_reset', 't2b200_ts_packetize', 't2b200_frames_configure', 't2b200_frames_decode',
+    't2b200_mode_init', 't2b200_pilot_tables', 't2b200_eq_configure_mode',
 ]
 
 
@@ -37,6 +38,18 @@ class FrameCfg(C.Structure):
     """t2b200_frame_cfg"""
     _fields_ = [(n, C.c_int) for n in ('fft_size', 'len_frame', 'n_p2', 'l_fc', 'c_p2', 'c_data', 'n_fc', 'first_cell',
                                        'plp', 'mod', 'rotation', 'fec_type', 'code_rate', 'n_blocks', 'ti_len')]
+
+
+class Mode(C.Structure):
+    """t2b200_mode"""
+    _fields_ = [(n, C.c_int) for n in ('fft_mode', 'carrier_mode', 'pilot_pattern', 'guard_interval_mode', 'papr_mode',
+                                       'fft_size', 'k_total', 'k_ext', 'k_offset', 'l_nulls', 'guard_interval_size',
+                                       'n_p2', 'c_p2', 'c_data', 'n_fc', 'c_fc', 'l_fc', 'n_data', 'len_frame', 'dx', 'dy')] + \
+               [(n, C.c_float) for n in ('amp_p2', 'amp_sp', 'amp_cp')]
+
+
+FFT_MODE = {'16K': 4, '32K': 5}
+GI_MODE = {'1/32': 0, '1/16': 1, '1/8': 2, '1/4': 3, '1/128': 4, '19/128': 5, '19/256': 6}
 
 
 class T2Error(RuntimeError):
@@ -85,6 +98,9 @@ def lib():
     L.t2b200_ts_packetize.argtypes = [vp, i32, vp, i32, i32, vp, C.c_size_t, vp, vp, C.POINTER(C.c_longlong)]
     L.t2b200_frames_configure.argtypes = [vp, C.POINTER(FrameCfg)]
     L.t2b200_frames_decode.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, u32]
+    L.t2b200_mode_init.argtypes = [i32] * 6 + [C.POINTER(Mode)]
+    L.t2b200_pilot_tables.argtypes = [C.POINTER(Mode), i32, vp, vp]
+    L.t2b200_eq_configure_mode.argtypes = [vp, C.POINTER(Mode)]
     _lib = L
     return L
 
@@ -296,6 +312,44 @@ class Engine:
         sro, ph = _like(freq, (n,), np.float32), _like(freq, (n,), np.float32)
         self._chk(self.L.t2b200_equalize(self.h, kind, n, _ptr(idx), _ptr(freq), _ptr(cells), _ptr(sro), _ptr(ph)))
         return cells, sro, ph
+
+
+def mode_init(fft='32K', carrier_ext=True, pp=7, gi='1/128', n_data=59, papr=0):
+    """t2b200_mode_init -> Mode (dvbt2_parameters of one SISO transmission mode, built natively)"""
+    m = Mode()
+    rc = lib().t2b200_mode_init(FFT_MODE[fft], 1 if carrier_ext else 0, pp - 1, GI_MODE[gi], n_data, papr, C.byref(m))
+    if rc != OK:
+        raise T2Error('t2b200_mode_init rc=%d (combination not defined)' % rc)
+    return m
+
+
+def mode_tables(m):
+    """The init-time tables of a mode, built natively (t2b200_pilot_tables + t2b200_freq_deinterleaver_table), in the
+    layout oracle RefRx.tables() / tools.make_golden_tables.load() use: dict with 'p' (parameters), *_map, *_ref,
+    h_even_* / h_odd_*, amp_*."""
+    L = lib()
+    k = m.k_total
+    nd = m.len_frame - m.l_fc - m.n_p2
+    t = {'p': {n: int(getattr(m, n)) for n in ('fft_size', 'k_total', 'l_nulls', 'c_p2', 'c_data', 'n_fc', 'c_fc', 'n_data',
+                                               'len_frame', 'l_fc', 'n_p2', 'guard_interval_size', 'k_ext')}}
+    t['amp_p2'], t['amp_sp'], t['amp_cp'] = float(m.amp_p2), float(m.amp_sp), float(m.amp_cp)
+
+    def tab(kind, rows):
+        cm, pr = np.zeros((rows, k), np.int32), np.zeros((rows, k), np.float32)
+        rc = L.t2b200_pilot_tables(C.byref(m), kind, cm.ctypes.data, pr.ctypes.data)
+        if rc != OK:
+            raise T2Error('t2b200_pilot_tables rc=%d' % rc)
+        return cm, pr
+    t['data_map'], t['data_ref'] = tab(1, nd)
+    cm, pr = tab(0, 1)
+    t['p2_map'], t['p2_ref'] = cm[0], pr[0]
+    if m.l_fc:
+        cm, pr = tab(2, 1)
+        t['fc_map'], t['fc_ref'] = cm[0], pr[0]
+    for name, n in (('p2', m.c_p2), ('data', m.c_data), ('fc', m.n_fc)):
+        if n:
+            t['h_even_' + name], t['h_odd_' + name] = freq_deinterleaver_table(m.fft_size, n)
+    return t
 
 
 def cell_permutation(n_fec_blocks, cells_per_fec):
