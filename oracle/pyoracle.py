@@ -183,6 +183,12 @@ def ref_chain():
             f.restype = C.c_longlong
         L.ref_demod_new.argtypes = [C.c_float, C.c_int]
         L.ref_demod_feed.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_demod_params.argtypes = [_i32p]
+        L.ref_tap_fft_arm.argtypes = [C.c_int]
+        for n in ('fft_in', 'fft_info'):
+            f = getattr(L, 'ref_tap_' + n)
+            f.argtypes = [C.c_void_p, C.c_longlong]
+            f.restype = C.c_longlong
         _ref_chain = L
     return _ref_chain
 
@@ -396,3 +402,36 @@ class PortTs:
         out = np.zeros(len(bits) // 8 + 2 * 188 + 64, np.uint8)
         n = self.L.port_ts_frame(self.state.ctypes.data, padded.ctypes.data, len(bits), out.ctypes.data)
         return None if n < 0 else out[:n].copy()
+
+
+class RefDemod:
+    """The reference's whole receiver, dvbt2_demodulator::execute (dvbt2_demodulator.cpp:145-254) down to the TS sink, fed
+    with int16 I/Q in front-end sized chunks.  One instance per process (the stages keep static state).  Besides the
+    taps of RefFec it records the FFT input window of every OFDM symbol (`in_fft`, dvbt2_demodulator.cpp:332)."""
+
+    def __init__(self, sample_rate=64e6 / 7, need_plp=0, tap_fft=True):
+        self.L = ref_chain()
+        self.L.ref_demod_new(float(sample_rate), need_plp)
+        self.L.ref_tap_fft_arm(1 if tap_fft else 0)
+        self.status = []
+
+    def feed(self, i16, q16, chunk=1 << 16):
+        i16 = np.ascontiguousarray(i16, np.int16)
+        q16 = np.ascontiguousarray(q16, np.int16)
+        for a in range(0, len(i16), chunk):
+            n = min(chunk, len(i16) - a)
+            self.status.append(self.L.ref_demod_feed(n, i16[a:a + n].ctypes.data, q16[a:a + n].ctypes.data))
+
+    def params(self):
+        out = np.zeros(16, np.int32)
+        self.L.ref_demod_params(out)
+        return dict(zip(PARAM_NAMES + ['pilot_pattern', 'l1_post_size', 'num_plp'], [int(x) for x in out]))
+
+    def taps(self):
+        L = self.L
+        t = {'ti_sizes': _tap(L, 'ti_sizes', np.int32), 'bb_bits': _tap(L, 'bb_bits', np.uint8),
+             'bb_len': _tap(L, 'bb_len', np.int32), 'snr': _tap(L, 'snr', np.float32), 'ts': _tap(L, 'ts', np.uint8),
+             'ts_datagrams': _tap(L, 'ts_datagrams', np.int32), 'fft_info': _tap(L, 'fft_info', np.int32).reshape(-1, 3)}
+        x = _tap(L, 'fft_in', np.complex64)
+        t['fft_in'] = x.reshape(len(t['fft_info']), -1) if len(t['fft_info']) else x
+        return t

@@ -13,6 +13,10 @@
 #include <complex>
 #include <vector>
 #include <new>
+#include <dlfcn.h>
+#include <execinfo.h>
+#include <csignal>
+#include <unistd.h>
 
 #define private public          // the harness pokes at stage objects; the sources stay untouched
 #define protected public
@@ -329,10 +333,49 @@ void ref_tap_clear() { g_taps.clear(); OracleTsSink::get().bytes.clear(); Oracle
 // full receiver: dvbt2_demodulator::execute on int16 I/Q chunks (dvbt2_demodulator.cpp:145-254)
 static dvbt2_demodulator* g_demod = nullptr;
 static signal_estimate g_sig;
+
+// Tap on the FFT input of every OFDM symbol (the `in_fft` window of dvbt2_demodulator.cpp:332): the reference calls
+// fftwf_execute from an inline header function, so the call is interposed here (this library precedes libfftw3f in its
+// own lookup scope) and forwarded with dlsym(RTLD_NEXT).  One record per symbol: kind (SYMBOL_TYPE_*), symbol index,
+// whether the FEC chain was already running, then fft_size samples.
+struct FftTap { bool armed = false; std::vector<std::complex<float>> in; std::vector<int> info; };
+static FftTap g_fft_tap;
+void fftwf_execute(const fftwf_plan p)
+{
+  static void (*real)(const fftwf_plan) = reinterpret_cast<void (*)(const fftwf_plan)>(dlsym(RTLD_NEXT, "fftwf_execute"));
+  if (g_fft_tap.armed && g_demod && g_demod->in_fft && p == g_demod->fft->plan) {
+    const int n = g_demod->dvbt2.fft_size;
+    g_fft_tap.in.insert(g_fft_tap.in.end(), g_demod->in_fft, g_demod->in_fft + n);
+    g_fft_tap.info.push_back(g_demod->next_symbol_type);
+    g_fft_tap.info.push_back(g_demod->next_symbol_type == SYMBOL_TYPE_P2 ? 0 : g_demod->idx_symbol);
+    g_fft_tap.info.push_back((g_demod->deint_start ? 1 : 0) | (g_demod->demodulator_init ? 2 : 0));
+  }
+  real(p);
+}
+void ref_tap_fft_arm(int on) { g_fft_tap.armed = on != 0; if (!on) { g_fft_tap.in.clear(); g_fft_tap.info.clear(); } }
+TAP_GETTER(ref_tap_fft_in, g_fft_tap.in, std::complex<float>)
+TAP_GETTER(ref_tap_fft_info, g_fft_tap.info, int)
+void ref_tap_fft_clear() { g_fft_tap.in.clear(); g_fft_tap.info.clear(); }
+// mode parameters the demodulator derived from P1 + L1-pre (dvbt2_parameters) and the L1 of the last P2
+void ref_demod_params(int* out)
+{
+  const dvbt2_parameters& d = g_demod->dvbt2;
+  int v[16] = {d.fft_size, d.k_total, d.l_nulls, d.c_p2, d.c_data, d.n_fc, d.c_fc, d.n_data, d.len_frame, d.l_fc, d.n_p2,
+               d.guard_interval_size, d.k_ext, d.pilot_pattern, g_demod->l1_pre.l1_post_size, g_demod->l1_post.num_plp};
+  std::memcpy(out, v, sizeof(v));
+}
+static void segv_backtrace(int sig)
+{
+  void* bt[64];
+  const int n = backtrace(bt, 64);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(128 + sig);
+}
 int ref_demod_new(float sample_rate, int need_plp)
 {
+  if (getenv("ORACLE_BACKTRACE")) signal(SIGSEGV, segv_backtrace);
   g_demod = make_zeroed<dvbt2_demodulator>(id_sdrplay, sample_rate);
-  g_taps.clear(); OracleTsSink::get().bytes.clear();
+  g_taps.clear(); OracleTsSink::get().bytes.clear(); OracleTsSink::get().datagram_len.clear();
   bb_de_header* bb = g_demod->deinterleaver->qam->decoder->decoder->deheader;
   bb->set_out(bb_de_header::out_network, 7654, QString("x"), need_plp);
   return 0;

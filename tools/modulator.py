@@ -189,7 +189,7 @@ class Modulator:
         return bb, cw, cells, np.concatenate(stream)
 
     # ---- one T2 frame ----
-    def frame(self, noise_cn_db=None, scale=200.0, extra_streams=()):
+    def frame(self, noise_cn_db=None, scale=200.0, extra_streams=(), l1_cells=None):
         """-> dict(time complex64[len_frame][fft_size], bb bits [n_blocks][K_bch], cells ...).
         extra_streams: cell streams of further (type-1, contiguous) PLPs placed right behind this one."""
         p, t = self.p, self.t
@@ -199,7 +199,8 @@ class Modulator:
         plps = np.concatenate([stream] + list(extra_streams))
         assert len(plps) <= cap, 'PLPs do not fit the frame'
         dummy = qam_map(self.rng.integers(0, 2, (cap - len(plps), self.bpc), dtype=np.uint8), self.mod)
-        l1 = (1.0 - 2.0 * self.rng.integers(0, 2, self.p2_start)).astype(np.complex128)
+        l1 = (1.0 - 2.0 * self.rng.integers(0, 2, self.p2_start)).astype(np.complex128) if l1_cells is None else l1_cells
+        assert len(l1) == self.p2_start
         allc = np.concatenate([l1, plps, dummy])
         syms = []
         # P2 (idx_symbol 0 -> h_odd), data symbols (parity of idx), frame closing
@@ -230,3 +231,174 @@ class Modulator:
             time = time + sig * (self.rng.standard_normal(time.shape) + 1j * self.rng.standard_normal(time.shape))
         return {'time': time.astype(np.complex64), 'bb': bb, 'cw': cw, 'cells': cells, 'stream': stream,
                 'blocks': list(self.blocks)}
+
+
+# =============================================================================================
+# Whole-signal transmitter: P1 preamble + L1-pre / L1-post signalling + guard intervals -> the int16 I/Q stream a device
+# front-end hands to dvbt2_demodulator::execute (dvbt2_demodulator.cpp:145).  Test-only, like everything in this file.
+P1_ACTIVE = [
+    44, 45, 47, 51, 54, 59, 62, 64, 65, 66, 70, 75, 78, 80, 81, 82, 84, 85, 87, 88, 89, 90, 94, 96, 97, 98, 102, 107, 110, 112,
+    113, 114, 116, 117, 119, 120, 121, 122, 124, 125, 127, 131, 132, 133, 135, 136, 137, 138, 142, 144, 145, 146, 148, 149, 151,
+    152, 153, 154, 158, 160, 161, 162, 166, 171, 172, 173, 175, 179, 182, 187, 190, 192, 193, 194, 198, 203, 206, 208, 209, 210,
+    212, 213, 215, 216, 217, 218, 222, 224, 225, 226, 230, 235, 238, 240, 241, 242, 244, 245, 247, 248, 249, 250, 252, 253, 255,
+    259, 260, 261, 263, 264, 265, 266, 270, 272, 273, 274, 276, 277, 279, 280, 281, 282, 286, 288, 289, 290, 294, 299, 300, 301,
+    303, 307, 310, 315, 318, 320, 321, 322, 326, 331, 334, 336, 337, 338, 340, 341, 343, 344, 345, 346, 350, 352, 353, 354, 358,
+    363, 364, 365, 367, 371, 374, 379, 382, 384, 385, 386, 390, 395, 396, 397, 399, 403, 406, 411, 412, 413, 415, 419, 420, 421,
+    423, 424, 425, 426, 428, 429, 431, 435, 438, 443, 446, 448, 449, 450, 454, 459, 462, 464, 465, 466, 468, 469, 471, 472, 473,
+    474, 478, 480, 481, 482, 486, 491, 494, 496, 497, 498, 500, 501, 503, 504, 505, 506, 508, 509, 511, 515, 516, 517, 519, 520,
+    521, 522, 526, 528, 529, 530, 532, 533, 535, 536, 537, 538, 542, 544, 545, 546, 550, 555, 558, 560, 561, 562, 564, 565, 567,
+    568, 569, 570, 572, 573, 575, 579, 580, 581, 583, 584, 585, 586, 588, 589, 591, 595, 598, 603, 604, 605, 607, 611, 612, 613,
+    615, 616, 617, 618, 622, 624, 625, 626, 628, 629, 631, 632, 633, 634, 636, 637, 639, 643, 644, 645, 647, 648, 649, 650, 654,
+    656, 657, 658, 660, 661, 663, 664, 665, 666, 670, 672, 673, 674, 678, 683, 684, 689, 692, 696, 698, 699, 701, 702, 703, 704,
+    706, 707, 708, 712, 714, 715, 717, 718, 719, 720, 722, 723, 725, 726, 727, 729, 733, 734, 735, 736, 738, 739, 740, 744, 746,
+    747, 748, 753, 756, 760, 762, 763, 765, 766, 767, 768, 770, 771, 772, 776, 778, 779, 780, 785, 788, 792, 794, 795, 796, 801,
+    805, 806, 807, 809]                                  # EN 302 755 table 61 (p1_symbol.h:60-110)
+# EN 302 755 table 60: the S1 (3 bit -> 64 chip) and S2 (4 bit -> 256 chip) modulation signalling sequences, hex
+P1_S1 = ['124721741D482E7B', '47127421481D7B2E', '217412472E7B1D48', '742147127B2E481D',
+         '1D482E7B12472174', '481D7B2E47127421', '2E7B1D4821741247', '7B2E481D74214712']
+P1_S2 = ['121D4748212E747B1D1248472E217B7412E247B721D174841DED48B82EDE7B8B',
+         '4748121D747B212E48471D127B742E2147B712E2748421D148B81DED7B8B2EDE',
+         '212E747B121D47482E217B741D12484721D1748412E247B72EDE7B8B1DED48B8',
+         '747B212E4748121D7B742E2148471D12748421D147B712E27B8B2EDE48B81DED',
+         '1D1248472E217B74121D4748212E747B1DED48B82EDE7B8B12E247B721D17484',
+         '48471D127B742E214748121D747B212E48B81DED7B8B2EDE47B712E2748421D1',
+         '2E217B741D124847212E747B121D47482EDE7B8B1DED48B821D1748412E247B7',
+         '7B742E2148471D12747B212E4748121D7B8B2EDE48B81DED748421D147B712E2',
+         '12E247B721D174841DED48B82EDE7B8B121D4748212E747B1D1248472E217B74',
+         '47B712E2748421D148B81DED7B8B2EDE4748121D747B212E48471D127B742E21',
+         '21D1748412E247B72EDE7B8B1DED48B8212E747B121D47482E217B741D124847',
+         '748421D147B712E27B8B2EDE48B81DED747B212E4748121D7B742E2148471D12',
+         '1DED48B82EDE7B8B12E247B721D174841D1248472E217B74121D4748212E747B',
+         '48B81DED7B8B2EDE47B712E2748421D148471D127B742E214748121D747B212E',
+         '2EDE7B8B1DED48B821D1748412E247B72E217B741D124847212E747B121D4748',
+         '7B8B2EDE48B81DED748421D147B712E27B742E2148471D12747B212E4748121D']
+
+
+def _hex_bits(h):
+    return np.array([(int(c, 16) >> (3 - k)) & 1 for c in h for k in range(4)], np.uint8)
+
+
+def p1_symbol(s1, s2):
+    """EN 302 755 9.8: 2048 samples C | A | B, unit mean power."""
+    mss = np.concatenate([_hex_bits(P1_S1[s1]), _hex_bits(P1_S2[s2]), _hex_bits(P1_S1[s1])])
+    dif = np.cumprod(1 - 2 * mss.astype(np.int64))                 # DBPSK, reference symbol +1
+    sr, scr = 0x4e46, np.zeros(384, np.int64)                      # PRBS of 9.8.2.3 as p1_symbol.cpp:46-55 runs it
+    for i in range(384):
+        b = (sr ^ (sr >> 1)) & 1
+        scr[i] = -1 if b else 1
+        sr >>= 1
+        if b:
+            sr |= 0x4000
+    spec = np.zeros(1024, np.complex128)
+    spec[(np.array(P1_ACTIVE) - 426) % 1024] = dif * scr
+    a = np.fft.ifft(spec) * 1024 / np.sqrt(384)
+    n = np.arange(2048)
+    sh = np.exp(2j * np.pi * n / 1024)
+    return np.concatenate([a[:542] * sh[:542], a, a[542:] * sh[1566:]])
+
+
+def crc32_bits(bits):
+    """CRC-32 (0x04C11DB7, all-ones start, no final inversion) over a bit array, as p2_symbol.cpp:308-318 checks it"""
+    crc = 0xffffffff
+    for b in bits:
+        fb = int(b) ^ ((crc >> 31) & 1)
+        crc = (crc << 1) & 0xffffffff
+        if fb:
+            crc ^= 0x04C11DB7
+    return crc
+
+
+def _field(v, n):
+    return [(int(v) >> (n - 1 - k)) & 1 for k in range(n)]
+
+
+def l1_pre_bits(m, l1_post_mod, l1_post_size, l1_post_info_size, s2_field1):
+    """EN 302 755 7.2.2: the 168 signalling bits + CRC-32 (all p2_symbol::l1_pre_info reads, p2_symbol.cpp:301-500)"""
+    f = []
+    for v, n in ((0, 8), (m.carrier_mode, 1), (0, 3), (s2_field1, 3), (0, 1), (0, 1), (m.guard_interval_mode, 3), (m.papr_mode, 4),
+                 (l1_post_mod, 4), (0, 2), (0, 2), (l1_post_size, 18), (l1_post_info_size, 18), (m.pilot_pattern, 4), (0, 8),
+                 (0, 16), (0x3085, 16), (0x8001, 16), (2, 8), (m.n_data, 12), (0, 3), (0, 1), (1, 3), (0, 3), (0, 4), (0, 1),
+                 (0, 1), (0, 4)):
+        f += _field(v, n)
+    assert len(f) == 168
+    return np.array(f + _field(crc32_bits(f), 32), np.uint8)
+
+
+def l1_post_bits(plps, frame_idx):
+    """EN 302 755 7.2.3: configurable + dynamic L1-post for NUM_RF = 1, no FEF, no auxiliary streams, + CRC-32, with the
+    field offsets p2_symbol::l1_post_info and its parsers use (p2_symbol.cpp:671-1005).
+    plps: dicts(id, cod, mod, rot, fec, blocks_max, ti_len, ti_type, start, num_blocks)"""
+    f = _field(0, 15) + _field(len(plps), 8) + _field(0, 4) + _field(0, 8)                 # SUB_SLICES, NUM_PLP, NUM_AUX, AUX_RFU
+    f += _field(0, 3) + _field(666000000, 32)                                              # RF_IDX, FREQUENCY
+    for p in plps:
+        for v, n in ((p['id'], 8), (1, 3), (3, 5), (0, 1), (0, 3), (0, 8), (p['id'], 8), (p['cod'], 3), (p['mod'], 3),
+                     (p['rot'], 1), (p['fec'], 2), (p['blocks_max'], 10), (1, 8), (p['ti_len'], 8), (p['ti_type'], 1),
+                     (0, 1), (0, 1), (0, 11), (1, 2), (0, 1), (0, 1)):
+            f += _field(v, n)
+    f += _field(0, 32)                                                                     # FEF_LENGTH_MSB, RESERVED_2
+    assert len(f) == 70 + 89 * len(plps) + 32
+    f += _field(frame_idx, 8) + _field(0, 22) + _field(0, 22) + _field(0, 8) + _field(0, 3) + _field(0, 8)
+    for p in plps:
+        f += _field(p['id'], 8) + _field(p['start'], 22) + _field(p['num_blocks'], 10) + _field(0, 8)
+    f += _field(0, 8)
+    return np.array(f + _field(crc32_bits(f), 32), np.uint8)
+
+
+class Transmitter:
+    """T2 frames of one PLP as the int16 I/Q sample stream of an 8 MHz channel sampled at 64/7 MHz: P1, P2 carrying real
+    L1-pre / L1-post signalling (QPSK L1-post; only the systematic bits + CRC are meaningful, which is all the reference
+    reads -- it never runs the L1 LDPC / BCH), data symbols (+ frame closing), guard intervals.
+    m: engine.Mode; the carrier / pilot tables are the natively built ones (engine.mode_tables)."""
+
+    def __init__(self, m, mod, cod, fec_normal, n_blocks, ti_len, rotation=True, seed=1, rms=3500.0):
+        from sdr_receiver_dvb_t2_b200 import engine as E
+        self.m = m
+        self.tables = E.mode_tables(m)
+        self.l1_post_mod = 1                                         # QPSK (BPSK would overflow the reference's bit buffers, p2_symbol.cpp:383-386)
+        self.plp = dict(id=0, cod=cod, mod=mod, rot=int(rotation), fec=int(fec_normal), blocks_max=n_blocks, ti_len=ti_len,
+                        ti_type=0, start=0, num_blocks=n_blocks)
+        self.info_size = len(l1_post_bits([self.plp], 0)) - 32
+        self.l1_post_size = 750                                      # cells: EN 302 755 7.3.1.2 for K_sig = 350, QPSK, one P2 symbol
+        assert self.info_size + 32 <= 2 * self.l1_post_size
+        self.mod = Modulator(self.tables, mod, cod, fec_normal, n_blocks, ti_len, rotation=rotation,
+                             l1_post_size=self.l1_post_size, seed=seed)
+        self.rng = np.random.default_rng(seed + 7777)
+        self.rms = rms
+        self.s2 = {16384: 4, 32768: 5}[m.fft_size] << 1              # S2 field 1 (FFT size), field 2 = 0 (not mixed)
+        self.p1 = p1_symbol(0, self.s2)                              # S1 = 000: T2 SISO
+        self.frame_idx = 0
+        self._scale = None
+
+    def l1_cells(self):
+        pre = l1_pre_bits(self.m, self.l1_post_mod, self.l1_post_size, self.info_size, self.s2 >> 1)
+        pre = np.concatenate([pre, self.rng.integers(0, 2, 1840 - len(pre), dtype=np.uint8)])      # BCH / LDPC parity: never read
+        post = l1_post_bits([self.plp], self.frame_idx & 0xff)
+        post = np.concatenate([post, self.rng.integers(0, 2, 2 * self.l1_post_size - len(post), dtype=np.uint8)])
+        qp = ((1.0 - 2.0 * post[0::2]) + 1j * (1.0 - 2.0 * post[1::2])) / np.sqrt(2.0)
+        return np.concatenate([(1.0 - 2.0 * pre).astype(np.complex128), qp])
+
+    def frame(self):
+        """-> (samples complex128 [2048 + len_frame * (N + GI)], unit-ish power; modulator frame dict)"""
+        f = self.mod.frame(noise_cn_db=None, scale=1.0, l1_cells=self.l1_cells())
+        self.frame_idx += 1
+        N, gi = self.m.fft_size, self.m.guard_interval_size
+        t = f['time'].astype(np.complex128) * N / np.sqrt(self.m.k_total)          # ~unit power per sample
+        sym = np.concatenate([t[:, N - gi:], t], axis=1).reshape(-1)
+        return np.concatenate([self.p1, sym]), f
+
+    def stream(self, n_frames, cn_db=None, lead=4096):
+        """-> (I int16, Q int16, list of modulator frame dicts).  `lead` noise-only samples in front."""
+        parts, frames = [], []
+        for _ in range(n_frames):
+            s, f = self.frame()
+            parts.append(s)
+            frames.append(f)
+        x = np.concatenate([np.zeros(lead, np.complex128)] + parts + [np.zeros(lead, np.complex128)])
+        p_sig = np.mean(np.abs(np.concatenate(parts)) ** 2)
+        if cn_db is not None:
+            sig = np.sqrt(p_sig * 10 ** (-cn_db / 10) / 2)
+            x = x + sig * (self.rng.standard_normal(len(x)) + 1j * self.rng.standard_normal(len(x)))
+        x *= self.rms * np.sqrt(2.0) / np.sqrt(p_sig)
+        i16 = np.clip(np.rint(x.real), -32768, 32767).astype(np.int16)
+        q16 = np.clip(np.rint(x.imag), -32768, 32767).astype(np.int16)
+        return i16, q16, frames
