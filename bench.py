@@ -101,97 +101,157 @@ def synth_llr(torch, n, device, seed):
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_rate(seconds_budget=12.0, sample=None):
-    """Reference CPU LDPC decoder (oracle/_ref when built, else the C port) on all host threads.
-    Returns (codewords/s, info dict)."""
+# The reference arm / CPU baseline: the UNMODIFIED reference stages (oracle/_ref/libref_chain.so, compiled from the
+# reference's own sources) over the SAME workload as the GPU arm -- C32 T2 frames from the same modulator at the same C/N:
+# FFTW FFT -> p2_symbol / data_symbol::execute -> time_deinterleaver -> llr_demapper -> ldpc_decoder -> bch_decoder, one
+# receiver per host core (the reference keeps static state: one instance per PROCESS), every core its own frames.
+# Like the GPU arm, the LDPC stage decodes LLRs made with the saturating cast (the reference's own wrapping cast never
+# converges on 256-QAM): the stock demapper still runs and is timed, its wrapped output is dropped, and the stock
+# ldpc_decoder + bch_decoder get the saturated LLRs of the same cells (made once, outside the timed region, by the oracle
+# port's demapper).  `stock_cast` reports the fully stock path (25 trials, every batch dropped) next to it.
+_W = {}
+
+
+def workload_config(world):
+    """`config` of the JSON line: identical in both arms (the driver compares them)"""
+    return {'workload': '8MHz 32K ext PP7 GI1/128 SISO, 1 PLP 256-QAM rotated r2/3 64800, TI 67/67/68: whole hot path '
+                        'FFT -> equalise/freq-deint -> time/cell-deint -> demap -> LDPC(group-of-32, <=25 trials) -> '
+                        'BCH strip + BB descramble, replay mode',
+            'frames_per_step_per_gpu': FRAMES_PER_STEP, 'codewords_per_step_per_gpu': FRAMES_PER_STEP * FEC_PER_FRAME,
+            'cn_db': CN_DB, 'demap_cast': 'saturate (T2B200_OPT_DEMAP_SATURATE; the reference wraps and never converges on 256-QAM)',
+            'l2': 'input IQ 315 MB per step > 126 MB L2, 3 batches rotated', 'parallelism': 'shard%d' % world}
+
+
+def _refchain_init(seed_base, counter):
     import numpy as np
     from oracle import pyoracle as O
-    kind = 'reference' if O.have_ref() else 'port'
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    rate = CODE_K / CODE_N
-    sigma = (1.0 / (2.0 * rate * 10 ** (EBN0_DB / 10.0))) ** 0.5
-    rng = np.random.default_rng(7)
-
-    def make_group():
-        y = 1.0 + sigma * rng.standard_normal((32, CODE_N), dtype=np.float32)
-        return np.clip(np.rint(2.0 * (2.0 / (sigma * sigma)) * y), -128, 127).astype(np.int8)
-
-    if kind == 'reference':
-        L = O.ref_ldpc()
-        import ctypes as C
-
-        def worker(groups, res, idx):
-            dec = L.ref_ldpc_new(CODE_ID)
-            bits = np.empty((32, CODE_K), np.uint8)
-            n = 0
-            for g in groups:
-                L.ref_ldpc_decode32(dec, CODE_ID, g, bits.ctypes.data_as(C.c_void_p), None, 25)
-                n += 32
-            res[idx] = n
-    else:
-        def worker(groups, res, idx):
-            n = 0
-            for g in groups:
-                O.port_ldpc_decode(CODE_ID, g, 25)
-                n += 32
-            res[idx] = n
-
-    # calibrate on one group, then size the sample to the budget
-    g0 = make_group() if sample is None else np.ascontiguousarray(sample[:32])
-    t = time.perf_counter()
-    res = [0]
-    worker([g0], res, 0)
-    t1 = time.perf_counter() - t
-    # threads share the cores' SIMD units / caches: assume no better than t1 per group per thread
-    per_thread = max(1, min(1024, int(seconds_budget / max(t1, 1e-3))))
-    if sample is not None and len(sample) >= 32:          # LLRs of the GPU run's own demapper: same iteration statistics
-        distinct = [np.ascontiguousarray(sample[32 * i:32 * i + 32]) for i in range(min(4, len(sample) // 32))]
-        while len(distinct) < 4:
-            distinct.append(distinct[0])
-    else:
-        distinct = [make_group() for _ in range(4)]
-    groups = [[distinct[(i + k) % 4] for k in range(per_thread)] for i in range(ncpu)]
-    res = [0] * ncpu
-    th = [threading.Thread(target=worker, args=(groups[i], res, i)) for i in range(ncpu)]
-    t = time.perf_counter()
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
-    dt = time.perf_counter() - t
-    total = sum(res)
-    return total / dt, {'kind': kind, 'cores': ncpu,
-                        'sample': '%d groups of 32 codewords (N=64800 r2/3, Eb/N0 %.1f dB) per thread on %d threads, %.1f s'
-                                  % (per_thread, EBN0_DB, ncpu, dt)}
-
-
-def cpu_reference_front_stages(frame_time):
-    """Single-core time of the reference's OTHER stages (FFTW FFT, equaliser, TI + demapper; oracle/_ref/libref_chain.so,
-    compiled from the unmodified sources) on one C32 T2 frame: context for the LDPC-only CPU number, which leaves them out.
-    Returns ms per frame per stage, or None when the compiled reference is not on this box."""
-    import numpy as np
-    from oracle import pyoracle as O
-    if not O.have_ref('libref_chain.so'):
-        return None
+    from sdr_receiver_dvb_t2_b200 import engine as E            # host-side table builders only (no GPU in this process)
+    from tools.modulator import Modulator
+    with counter.get_lock():
+        idx = counter.value
+        counter.value += 1
+    tables = E.mode_tables(E.mode_init('32K', True, 7, '1/128', 59))
+    mod = Modulator(tables, mod=3, cod=2, fec_normal=True, n_blocks=FEC_PER_FRAME, ti_len=3, seed=seed_base + idx)
+    frame = mod.frame(noise_cn_db=CN_DB)['time']
     rx = O.RefRx('32K', True, 7, '1/128', 59)
-    L = frame_time.shape[0]
-    t0 = time.perf_counter()
-    freq = [rx.fft(frame_time[i]) for i in range(L)]
-    t_fft = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    cells = [rx.p2_symbol(freq[0])[0]] + [rx.data_symbol(i, freq[i])[0] for i in range(1, L)]
-    t_eq = time.perf_counter() - t0
     fec = O.RefFec(rx, [dict(id=0, cod=2, mod=3, rot=1, fec=1, blocks_max=68, ti_len=3, ti_type=0)], 360)
-    fec.chain(after_ti=True, after_demap=False, after_ldpc=False, after_bch=False)
-    t0 = time.perf_counter()
+    # converging LLRs of this frame for the LDPC stage (not timed): the reference's own cells -> port TI + saturating demap
+    L = frame.shape[0]
+    cells = [rx.p2_symbol(rx.fft(frame[0]))[0]] + [rx.data_symbol(i, rx.fft(frame[i]))[0] for i in range(1, L)]
+    stream = np.concatenate(cells)[mod.p2_start:mod.p2_start + mod.nb * mod.cpf]
+    ti = O.port_ti_blocks(stream, mod.blocks, mod.cpf, O.port_cell_permutation(max(mod.blocks), mod.cpf), [0, 0.0])
+    llrs, off = [], 0
+    for nf in mod.blocks:
+        llrs.append(O.port_demap(ti[off:off + nf * mod.cpf], 3, 1, True, 2, saturate=True)[0])
+        off += nf * mod.cpf
+    _W.update(rx=rx, fec=fec, frame=frame, llr=np.concatenate(llrs), carry=0, idx=idx)
+
+
+def _refchain_step(mode):
+    """one T2 frame through the stock stages; mode 'sat': LDPC on the saturated LLRs, 'stock': on the demapper's own output"""
+    import numpy as np
+    rx, fec, frame, llr = _W['rx'], _W['fec'], _W['frame'], _W['llr']
+    L = frame.shape[0]
+    t = [time.perf_counter()]
+    freq = [rx.fft(frame[i]) for i in range(L)]
+    t.append(time.perf_counter())
+    cells = [rx.p2_symbol(freq[0])[0]] + [rx.data_symbol(i, freq[i])[0] for i in range(1, L)]
+    t.append(time.perf_counter())
+    fec.chain(after_ti=True, after_demap=False, after_ldpc=True, after_bch=False)
     fec.feed_p2([0], [FEC_PER_FRAME], cells[0])
     for c in cells[1:]:
         fec.feed(c)
-    t_fec = time.perf_counter() - t0
-    return {'fft_ms': 1e3 * t_fft, 'equalize_ms': 1e3 * t_eq, 'ti_demap_ms': 1e3 * t_fec, 'frames': 1,
-            'codewords_per_frame': FEC_PER_FRAME,
-            'note': 'one core, one C32 frame (60 symbols, 202 FECFRAMEs) through the compiled reference stages; the LDPC '
-                    'number above does not include them'}
+    t.append(time.perf_counter())
+    if mode == 'sat':
+        have = _W['carry'] + FEC_PER_FRAME          # the demapper hands over whole batches of 32 and carries the rest
+        groups = have // 32
+        _W['carry'] = have - 32 * groups
+        for g in range(groups):
+            fec.ldpc_batch(llr[32 * (g % 6):32 * (g % 6) + 32])
+    else:
+        # the batches the stock demapper just emitted (wrapped cast).  They are handed to ldpc_decoder::execute from here:
+        # chained inside the reference, a batch that straddles two TI blocks (67 / 67 / 68 FEC blocks) reads its PLP ids from
+        # a dead stack array (llr_demapper.cpp:540,747) and crashes this harness
+        own = fec.taps()['llr'].reshape(-1, 32, CODE_N)
+        groups = own.shape[0]
+        for g in range(groups):
+            fec.ldpc_batch(own[g])
+    n_cw = 32 * groups
+    t.append(time.perf_counter())
+    fec.clear()
+    return n_cw, [t[i + 1] - t[i] for i in range(4)]
+
+
+def reference_chain_rate(steps, warmup, mode='sat', procs=None):
+    """-> (codewords/s over all host cores, info dict).  One process per core, each pushes one C32 frame per step through
+    the compiled reference stages; a step ends when the slowest core is done."""
+    import multiprocessing as mp
+    from oracle import pyoracle as O
+    if not O.have_ref('libref_chain.so'):
+        raise RuntimeError('oracle/_ref/libref_chain.so is not on this box')
+    ncpu = procs or (len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    from concurrent.futures import ProcessPoolExecutor           # (a dead worker raises BrokenProcessPool instead of hanging)
+    ctx = mp.get_context('spawn')
+    counter = ctx.Value('i', 0)
+    with ProcessPoolExecutor(ncpu, mp_context=ctx, initializer=_refchain_init, initargs=(1000, counter)) as pool:
+        def step(m):
+            return list(pool.map(_refchain_step, [m] * ncpu, chunksize=1, timeout=600))
+        for _ in range(max(1, warmup)):                                           # every worker is up (and warm)
+            step(mode)
+        n_cw, wall, stage = 0, 0.0, [0.0] * 4
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            res = step(mode)
+            wall += time.perf_counter() - t0
+            n_cw += sum(r[0] for r in res)
+            for r in res:
+                for k in range(4):
+                    stage[k] += r[1][k]
+        stock = None
+        if mode == 'sat':                      # the stock cast once: wrapped LLRs, 25 trials per batch, everything dropped
+            t0 = time.perf_counter()
+            res = step('stock')
+            stock = sum(r[0] for r in res) / (time.perf_counter() - t0)
+    per = steps * ncpu
+    info = {'kind': 'reference', 'cores': ncpu,
+            'sample': '%d steps x %d processes x 1 C32 T2 frame (60 symbols, 202 FECFRAMEs 256-QAM r2/3 at %.1f dB) through the compiled '
+                      'reference stages FFTW -> p2/data_symbol -> time_deinterleaver -> llr_demapper -> ldpc_decoder -> bch_decoder, %.1f s'
+                      % (steps, ncpu, CN_DB, wall),
+            'ms_per_frame_per_core': {'fft': 1e3 * stage[0] / per, 'equalize': 1e3 * stage[1] / per, 'ti_demap': 1e3 * stage[2] / per,
+                                      'ldpc_bch': 1e3 * stage[3] / per},
+            'ldpc_input': 'saturating-cast LLRs of the same cells (as the GPU arm); the stock demapper runs and is timed'}
+    if stock is not None:
+        info['stock_cast'] = {'value': stock, 'unit': 'codewords/s',
+                              'note': 'fully stock path once: the wrapping cast never converges on 256-QAM, every batch runs 25 trials and is dropped'}
+    return n_cw / wall, info
+
+
+def _e2e_1core_worker(q):
+    """BASELINE.md 3.1: the reference's whole receiver (dvbt2_demodulator::execute -> ... -> bb_de_header) on ONE core, on the
+    synthetic int16 I/Q of tests/e2e_helpers.py 'c32e' (32K 64-QAM r3/5 64800: a mode it decodes)"""
+    from oracle import pyoracle as O
+    from tests import e2e_helpers as H
+    i16, q16, _, tx = H.make_stream('c32e')
+    rx = O.RefDemod(tap_fft=False)
+    t0 = time.perf_counter()
+    rx.feed(i16, q16)
+    dt = time.perf_counter() - t0
+    t = rx.taps()
+    q.put({'seconds': dt, 'samples': int(len(i16)), 'bbframes': int(len(t['bb_len'])), 'ts_bytes': int(len(t['ts']))})
+
+
+def reference_e2e_1core():
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    p = ctx.Process(target=_e2e_1core_worker, args=(q,))
+    p.start()
+    r = q.get(timeout=300)
+    p.join()
+    r.update(config='32K ext PP4 GI1/32, 64-QAM r3/5 64800, 7 T2 frames of int16 I/Q at 64/7 MHz incl. acquisition (3 frames decoded)',
+             msamples_per_s=r['samples'] / r['seconds'] / 1e6, realtime_multiple=r['samples'] / r['seconds'] / (64e6 / 7),
+             note='dvbt2_demodulator::execute -> bb_de_header, one core, synchronous signal glue (BASELINE.md 3.1)')
+    return r
 
 
 def run_reference(args):
@@ -199,20 +259,19 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        v, info = cpu_reference_rate(seconds_budget=float(os.environ.get('T2B200_BENCH_CPU_BUDGET', '6.0')))
-        if i >= args.warmup:
-            vals.append(v)
-    v = sum(vals) / len(vals)
+    # each step: one T2 frame per host core (a bounded sample of the GPU arm's 20-frame step)
+    v, info = reference_chain_rate(args.steps, args.warmup)
+    try:
+        info['e2e_1core'] = reference_e2e_1core()
+    except Exception as e:
+        info['e2e_1core'] = 'failed: %s' % e
+    cw_step = FRAMES_PER_STEP * FEC_PER_FRAME
     line = {
         'impl': 'reference', 'metric': 'ldpc_codewords_per_s', 'value': v, 'unit': 'codewords/s',
         'ts_mbit_s': ts_mbit(v), 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * BATCH / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'int8', 'data': 'synthetic',
-        'config': {'workload': '8MHz 32K 256-QAM r2/3 FEC path: LDPC 64800 r2/3 group-of-32 + BCH strip/descramble',
-                   'batch_codewords': BATCH, 'note': 'each step is a bounded sample of the batch on all host threads'},
+        'ms_per_step': 1e3 * cw_step / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 demod + int8 FEC', 'data': 'synthetic',
+        'config': workload_config(args.gpus),
         'cpu_baseline': dict(info, value=v, unit='codewords/s'),
         'e2e': {'value': v, 'unit': 'codewords/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.perf_counter() - t0,
@@ -289,7 +348,6 @@ def run_t2b200(args):
         stream.synchronize()
         mean_iters = float(r['iterations'].float().mean().item())
         frac_ok = float((r['trials_left'] >= 0).float().mean().item())
-        sample_llr = None
 
         # Two chains on two streams take alternate steps: the lock-step LDPC kernel holds 128 of the 148 SMs (4 groups
         # of 32 co-resident CTAs), so the other chain's streaming stages (and its latency-bound ordered sum) run on
@@ -354,7 +412,6 @@ def run_t2b200(args):
         k1.record(stream)
         stream.synchronize()
         ldpc_ms = k0.elapsed_time(k1) / 5
-        sample_llr = llr[:256].cpu().numpy()
         # the same decode with per-codeword exit (no lock-step groups): for information, not the reference's batch semantics
         nflags = E.LDPC_BCH_DESCRAMBLE
         eng.ldpc_decode(CODE_ID, llr, flags=nflags, out=out_bits, want_status=False)
@@ -496,14 +553,15 @@ def run_t2b200(args):
         except Exception:
             pass
         try:
-            v, info = cpu_reference_rate(seconds_budget=12.0, sample=sample_llr)
+            # the reference's own stages over the same workload on all host cores (bounded: 3 steps of one frame per core)
+            v, info = reference_chain_rate(steps=3, warmup=1)
             cpu = dict(info, value=v, unit='codewords/s')
             try:
-                cpu['other_stages_1core'] = cpu_reference_front_stages(clean[0])
+                cpu['e2e_1core'] = reference_e2e_1core()
             except Exception as e:
-                cpu['other_stages_1core'] = 'failed: %s' % e
+                cpu['e2e_1core'] = 'failed: %s' % e
         except Exception as e:  # the baseline is reported, never required for the GPU number
-            cpu = {'value': None, 'unit': 'codewords/s', 'cores': 0, 'kind': 'port', 'sample': 'failed: %s' % e}
+            cpu = {'value': None, 'unit': 'codewords/s', 'cores': 0, 'kind': 'reference', 'sample': 'failed: %s' % e}
         # algorithmic bytes per frame of every stage and the HBM fraction each reaches
         per_frame = {
             'fft': L * 16 * N,
@@ -520,14 +578,9 @@ def run_t2b200(args):
             't2_frames_per_s': value / FEC_PER_FRAME, 'realtime_multiple': value / 931.0,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 demod + int8 FEC', 'data': 'synthetic',
-            'config': {'workload': '8MHz 32K ext PP7 GI1/128 SISO, 1 PLP 256-QAM rotated r2/3 64800, TI 67/67/68: whole hot path '
-                                   'FFT -> equalise/freq-deint -> time/cell-deint -> demap -> LDPC(group-of-32, <=25 trials) -> '
-                                   'BCH strip + BB descramble, replay mode',
-                       'frames_per_step_per_gpu': F, 'codewords_per_step_per_gpu': cw_step, 'cn_db': CN_DB,
-                       'demap_cast': 'saturate (T2B200_OPT_DEMAP_SATURATE; the reference wraps and never converges on 256-QAM)',
-                       'mean_ldpc_iterations': mean_iters, 'converged_fraction': frac_ok,
-                       'l2': 'input IQ 315 MB per step > 126 MB L2, 3 batches rotated', 'parallelism': 'shard%d' % world,
-                       'overlap': 'two contexts on two streams take alternate steps (t2b200_frames_decode, device buffers)'},
+            'config': workload_config(world),
+            'workload_stats': {'mean_ldpc_iterations': mean_iters, 'converged_fraction': frac_ok,
+                               'overlap': 'two contexts on two streams take alternate steps (t2b200_frames_decode, device buffers)'},
             'e2e': {'value': e2e_value, 'unit': 'codewords/s', 'ts_mbit_s': ts_mbit(e2e_value),
                     'h2d_bytes_per_step': F * L * N * 8, 'd2h_bytes_per_step': cw_step * CODE_KBCH,
                     'steps': e2e_steps, 'api': 't2b200_frames_decode with host pointers: pinned host IQ in, pinned host BBFRAME bits (byte per bit) out, '

@@ -160,9 +160,16 @@ static float slice(int mod, float x, float a)
   return x < -(a * 2.0f) ? -(a * 3.0f) : -a;
 }
 
+/* Restates the PRODUCT option T2B200_OPT_DEMAP_SATURATE (include/t2b200.h), not a reference behaviour: clamp the LLR to
+ * [-128, 127] instead of the reference's wrapping cast.  Off by default; bench.py turns it on to give the reference's LDPC
+ * decoder the same (decodable) LLRs the GPU arm decodes, tests use it to check the option bit for bit. */
+static int g_demap_saturate = 0;
+void port_set_demap_saturate(int on) { g_demap_saturate = on != 0; }
+
 /* (int8_t)(float) the way x86-64 gcc does it: cvttss2si r32 (0x80000000 if out of range), low byte */
 static int8_t cast_i8(float r)
 {
+  if (g_demap_saturate) return (int8_t)fminf(fmaxf(r, -128.0f), 127.0f);
   if (!(fabsf(r) < 2147483648.0f)) return 0;
   return (int8_t)((int32_t)r & 0xff);
 }

@@ -174,6 +174,7 @@ def ref_chain():
         L.ref_fec_feed_p2.argtypes = [_i32p, _i32p, C.c_int, C.c_void_p]
         L.ref_fec_feed.argtypes = [C.c_int, C.c_void_p]
         L.ref_demap.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_ldpc_batch.argtypes = [C.c_int, C.c_void_p, C.c_int]
         L.ref_bb_deheader.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.ref_ti_permutation.argtypes = [C.c_int, _i32p, C.c_int]
         L.ref_demap_address.argtypes = [C.c_int, C.c_int, C.c_int, _i32p]
@@ -300,6 +301,12 @@ class RefFec:
         bits = np.concatenate([np.ascontiguousarray(bits, np.uint8), np.zeros(4096, np.uint8)])
         self.L.ref_bb_deheader(plp, n, bits.ctypes.data)
 
+    def ldpc_batch(self, llr32, plp=0):
+        """32 FECFRAMEs of int8 LLRs through the reference's ldpc_decoder::execute and the stages chained behind it"""
+        llr32 = np.ascontiguousarray(llr32, np.int8)
+        assert llr32.shape[0] == 32
+        self.L.ref_ldpc_batch(plp, llr32.ctypes.data, llr32.shape[1])
+
     def permutation(self, plp=0):
         out = np.zeros(1 << 22, np.int32)
         n = self.L.ref_ti_permutation(plp, out, len(out))
@@ -349,8 +356,10 @@ def port_demap_address(fec_normal, mod, code_rate):
     return out
 
 
-def port_demap(cells, mod, rotation, fec_normal, code_rate, precision_in=0.0):
-    """one TI block; returns (llr int8[n_fec][N], snr, precision, derotated cells)"""
+def port_demap(cells, mod, rotation, fec_normal, code_rate, precision_in=0.0, saturate=False):
+    """one TI block; returns (llr int8[n_fec][N], snr, precision, derotated cells).  saturate: the PRODUCT's
+    T2B200_OPT_DEMAP_SATURATE cast instead of the reference's wrapping one"""
+    port().port_set_demap_saturate(int(saturate))
     cells = np.ascontiguousarray(cells, np.complex64).copy()
     nb = 64800 if fec_normal else 16200
     cpf = nb // (2 * (mod + 1))

@@ -281,6 +281,15 @@ void ref_fec_feed_p2(const int* dyn_start, const int* dyn_num_blocks, int n_cell
 }
 void ref_fec_feed(int n_cells, float* cells) { g_rx->ti->execute(n_cells, reinterpret_cast<complex*>(cells)); }
 
+// ldpc_decoder::execute (ldpc_decoder.cpp:157-301) on one batch of 32 FECFRAMEs of plp, then whatever is chained behind it
+// (bch_decoder::execute, bb_de_header::execute): the stock FEC back half on caller-supplied LLRs
+void ref_ldpc_batch(int plp, int8_t* llr32, int fec_size)
+{
+  int idx[32];
+  for (int i = 0; i < 32; ++i) idx[i] = plp;
+  g_rx->ti->qam->decoder->execute(idx, g_rx->l1_post, 32 * fec_size, llr32);
+}
+
 // stand-alone stage entry points (stage objects of the same instance)
 void ref_demap(int n_cells, float* cells, int plp) { g_rx->ti->qam->execute(n_cells, reinterpret_cast<complex*>(cells), plp, g_rx->l1_post); }
 

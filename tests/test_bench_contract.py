@@ -28,6 +28,13 @@ def test_reference_arm_line():
     assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     assert 'workload' in d['config']
+    # same-config arms: both print the config of bench.workload_config (the driver compares them), and the reference arm is
+    # the whole stock chain over C32 frames, not the LDPC stage alone
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d['config'] == bench.workload_config(1)
+    assert set(d['cpu_baseline']['ms_per_frame_per_core']) == {'fft', 'equalize', 'ti_demap', 'ldpc_bch'}
+    assert d['cpu_baseline']['e2e_1core']['bbframes'] == 192
 
 
 def test_reference_arm_other_ranks_are_silent():

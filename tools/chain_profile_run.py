@@ -5,12 +5,10 @@ import numpy as np, torch
 import sdr_receiver_dvb_t2_b200 as t2
 from sdr_receiver_dvb_t2_b200 import engine as E
 from sdr_receiver_dvb_t2_b200.chain import FrameChain
-from tools.make_golden_tables import load as load_tables
 from tools.modulator import Modulator
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-tables = load_tables(os.path.join(root, 'tests', 'golden', 'tables_c32.npz'))
+tables = E.mode_tables(E.mode_init('32K', True, 7, '1/128', 59))
 eng = t2.Engine(0, stream=torch.cuda.current_stream().cuda_stream)
 eng.set_option(E.OPT_DEMAP_SATURATE, 1)
 mod = Modulator(tables, mod=3, cod=2, fec_normal=True, n_blocks=202, ti_len=3, seed=5)
