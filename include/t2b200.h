@@ -230,7 +230,9 @@ int t2b200_fft(t2b200_ctx* ctx, int n, const float* in, int batch, float* out);
  *   datagram_len  int32[n_frames] or NULL: bytes of each frame's datagram (0 for a dropped frame)
  *   status        int32[n_frames] or NULL: 0 ok; 1 header CRC-8 error (dropped, :108-113); 2 SYNCD == 65535 (dropped,
  *                 :160-163); 3 normal-mode frame: NOT handled here (the reference's normal-mode path reads its CRC bytes
- *                 outside DFL): the frame is skipped and must go to the host bb_de_header
+ *                 outside DFL): the frame is skipped and must go to the host bb_de_header; 4 the header announces a data
+ *                 field longer than the frame (80 + DFL > k_bch): dropped without touching the carried state -- the
+ *                 reference has no such check and would read past its buffer
  *   total_out     bytes written to ts_out, or NULL (then the call stays asynchronous for device buffers)
  * The packet phase and the held-back tail (< 188 bytes) persist per PLP between calls; t2b200_ts_reset clears them. */
 int t2b200_ts_reset(t2b200_ctx* ctx, int plp);

@@ -58,10 +58,14 @@ int t2_to_device(t2b200_ctx* ctx, int slot, const void* src, size_t bytes, const
   if (t2_is_device_ptr(src)) { *dptr = src; return T2B200_OK; }
   void* d; int rc;
   if ((rc = t2_dev_scratch(ctx, slot, bytes, &d))) return rc;
-  // pinned or pageable: cudaMemcpyAsync handles both (pageable is staged by the driver and the call
-  // returns once the source has been consumed, which is the contract of this ABI)
+  // Pageable memory is staged by the driver: cudaMemcpyAsync returns once the source has been consumed.  A PINNED source is
+  // read by the copy engine later, so the call waits for that copy (only the copy, not the kernels behind it): when an
+  // entry point returns, the caller may reuse every host buffer it passed in -- the contract of this ABI.
   T2_CUDA(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  (void)is_pinned_host;
+  if (is_pinned_host(src)) {
+    T2_CUDA(ctx, cudaEventRecord(ctx->ev_h2d, ctx->stream));
+    T2_CUDA(ctx, cudaEventSynchronize(ctx->ev_h2d));
+  }
   *dptr = d;
   return T2B200_OK;
 }
@@ -80,9 +84,21 @@ int t2_finish_out(t2b200_ctx* ctx, void* dst, const void* dptr, size_t bytes)
   return T2B200_OK;
 }
 
+// A kernel that had to give up a wait (ldpc.cu: lock-step lanes that never became co-resident) raises a flag in device
+// memory instead of trapping; every call that waits for the GPU anyway turns it into an error here.
+int t2_check_device_flag(t2b200_ctx* ctx)
+{
+  unsigned f = 0;
+  T2_CUDA(ctx, cudaMemcpy(&f, ctx->d_err_flag, sizeof(f), cudaMemcpyDeviceToHost));
+  if (!f) return T2B200_OK;
+  cudaMemset(ctx->d_err_flag, 0, sizeof(unsigned));
+  ctx->err = "LDPC decoder: a lock-step wait timed out (lanes of a group were not co-resident); results of that call are invalid";
+  return T2B200_ERR_CUDA;
+}
+
 extern "C" {
 
-const char* t2b200_version(void) { return "t2b200 0.1 (sm_100a)"; }
+const char* t2b200_version(void) { return "t2b200 0.2 (sm_100a)"; }
 
 int t2b200_create(int device, t2b200_ctx** out)
 {
@@ -101,6 +117,9 @@ int t2b200_create(int device, t2b200_ctx** out)
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return T2B200_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
+  if (cudaEventCreateWithFlags(&ctx->ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&ctx->d_err_flag, sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(ctx->d_err_flag, 0, sizeof(unsigned)) != cudaSuccess) { t2b200_destroy(ctx); return T2B200_ERR_CUDA; }
   *out = ctx;
   return T2B200_OK;
 }
@@ -118,6 +137,8 @@ void t2b200_destroy(t2b200_ctx* ctx)
   t2_frames_free(ctx);
   if (ctx->d_prbs) cudaFree(ctx->d_prbs);
   if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
+  if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
+  if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
   for (auto& s : ctx->dev) if (s.p) cudaFree(s.p);
   for (auto& s : ctx->pin) if (s.p) cudaFreeHost(s.p);
   if (ctx->s_in) {
@@ -140,7 +161,7 @@ int t2b200_sync(t2b200_ctx* ctx)
 {
   if (!ctx) return T2B200_ERR_ARG;
   T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return T2B200_OK;
+  return t2_check_device_flag(ctx);
 }
 
 int t2b200_set_option(t2b200_ctx* ctx, int option, int value)

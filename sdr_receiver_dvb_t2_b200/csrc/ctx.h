@@ -34,6 +34,8 @@ struct t2b200_ctx {
   float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes
   unsigned* d_group_sync = nullptr; size_t group_sync_cap = 0;
+  unsigned* d_err_flag = nullptr;             // raised by a kernel that gave up a lock-step wait (ldpc.cu)
+  cudaEvent_t ev_h2d = nullptr;               // completion of the last copy out of a pinned host source
   std::map<int, FftPlan*> fft;                // by log2 n
   SymbolTables* sym[3] = {nullptr, nullptr, nullptr};
   TiDemapState* ti = nullptr;
@@ -69,3 +71,5 @@ int t2_to_device(t2b200_ctx* ctx, int slot, const void* src, size_t bytes, const
 int t2_out_device(t2b200_ctx* ctx, int slot, void* dst, size_t bytes, void** dptr);
 // Copy a scratch-produced result back to a host dst and wait for it (no-op if dst was device memory)
 int t2_finish_out(t2b200_ctx* ctx, void* dst, const void* dptr, size_t bytes);
+// T2B200_ERR_CUDA (and ctx->err) if a kernel raised the device error flag since the last check; synchronous
+int t2_check_device_flag(t2b200_ctx* ctx);

@@ -229,10 +229,16 @@ __global__ void __launch_bounds__(kEqThreads) equalize_kernel(const EqParams p)
 }
 
 // carrier map + pilot references of ONE symbol -> plan (the reference's scan, run once on the host)
-bool build_plan(int kind, int k_total, const int32_t* map, const float* refer, const int32_t* h, float amp_main,
+bool build_plan(int kind, int k_total, int n_out, const int32_t* map, const float* refer, const int32_t* h, float amp_main,
                 float amp_cp, PlanHost& out, std::string& err)
 {
   const int half_total = k_total / 2;
+  {
+    // the de-interleaver tables hold n_out addresses: count the data cells before indexing them
+    int cells = 0;
+    for (int i = 1; i < k_total; ++i) cells += map[i] == DATA_CARRIER && !(i == half_total && kind == 0);
+    if (cells > n_out) { err = "carrier map holds more data cells than n_out"; return false; }
+  }
   out.pilots.clear(); out.cells.clear(); out.first.clear();
   out.pilots.push_back({0, 0, 0, refer[0], amp_main});            // carrier 0: always the first (edge) pilot
   out.first.push_back(0);
@@ -257,7 +263,7 @@ bool build_plan(int kind, int k_total, const int32_t* map, const float* refer, c
     const int n = (int)pending.size();
     if (n > 255) { err = "more than 255 data cells between two pilots"; return false; }
     for (int j = 0; j < n; ++j, ++d) {
-      if (h[d] < 0 || h[d] > 65535) { err = "de-interleaver address out of range"; return false; }
+      if (h[d] < 0 || h[d] >= n_out) { err = "de-interleaver address out of range"; return false; }
       out.cells.push_back(make_uint2((uint32_t)pending[j] | ((uint32_t)left << 16),
                                      (uint32_t)(j + 1) | ((uint32_t)n << 8) | ((uint32_t)h[d] << 16)));
     }
@@ -277,6 +283,14 @@ void free_tables(SymbolTables* t)
 }
 
 }  // namespace
+
+bool t2_eq_geometry(const t2b200_ctx* ctx, int kind, int* fft_size, int* n_out, int* n_symbols, int* first_symbol)
+{
+  const SymbolTables* t = (kind >= 0 && kind < 3) ? ctx->sym[kind] : nullptr;
+  if (!t) return false;
+  *fft_size = t->fft_size; *n_out = t->n_out; *n_symbols = t->n_symbols; *first_symbol = t->first_symbol;
+  return true;
+}
 
 void t2_eq_free(t2b200_ctx* ctx)
 {
@@ -325,7 +339,7 @@ extern "C" int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int
     for (int parity = 0; parity < 2; ++parity) {
       PlanHost ph;
       // idx_symbol even -> h_odd, odd -> h_even (data_symbol.cpp:148-149)
-      if (!build_plan(kind, k_total, carrier_map + (size_t)s * k_total, pilot_refer + (size_t)s * k_total,
+      if (!build_plan(kind, k_total, n_out, carrier_map + (size_t)s * k_total, pilot_refer + (size_t)s * k_total,
                       parity ? h_even : h_odd, amp_main, amp_cp, ph, ctx->err)) { delete t; return T2B200_ERR_ARG; }
       if ((int)ph.cells.size() > n_out) { ctx->err = "carrier map holds more data cells than n_out"; delete t; return T2B200_ERR_ARG; }
       (parity ? t->plan_odd : t->plan_even).push_back(intern(ph));

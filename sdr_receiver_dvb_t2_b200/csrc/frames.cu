@@ -50,6 +50,24 @@ extern "C" int t2b200_frames_configure(t2b200_ctx* ctx, const t2b200_frame_cfg* 
   if (!ctx->sym[T2B200_SYM_P2] || !ctx->sym[T2B200_SYM_DATA] || (c->l_fc && !ctx->sym[T2B200_SYM_FC])) {
     ctx->err = "t2b200_frames_configure: call t2b200_eq_configure for every symbol kind first"; return T2B200_ERR_STATE;
   }
+  {
+    // the equaliser takes its input / output strides from this configuration but l_nulls, the carrier maps and the
+    // de-interleaver addresses (up to n_out - 1) from the symbol tables: they must describe the same mode
+    const int n_data = c->len_frame - c->n_p2 - (c->l_fc ? 1 : 0);
+    const int want_out[3] = {c->c_p2, c->c_data, c->n_fc}, want_sym[3] = {c->n_p2, n_data, 1};
+    const int want_first[3] = {0, c->n_p2, c->len_frame - 1};
+    for (int kind = 0; kind < 3; ++kind) {
+      if (kind == T2B200_SYM_FC && !c->l_fc) continue;
+      if (kind == T2B200_SYM_DATA && n_data == 0) continue;
+      int fs, no, ns, first;
+      if (!t2_eq_geometry(ctx, kind, &fs, &no, &ns, &first) || fs != c->fft_size || no != want_out[kind] ||
+          ns < want_sym[kind] || first != want_first[kind]) {
+        ctx->err = "t2b200_frames_configure: frame geometry differs from what t2b200_eq_configure was given (fft_size, cells per "
+                   "symbol, symbols per frame)";
+        return T2B200_ERR_ARG;
+      }
+    }
+  }
   int cpf = 0, nmax = 0, rc;
   if ((rc = t2_ti_geometry(ctx, c->plp, &cpf, &nmax))) return rc;
   if (!ctx->frames) ctx->frames = new FramePipe();

@@ -18,3 +18,5 @@ int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_de
                     float* d_prec, float* d_snr, const float* d_prec_in);
 int t2_ldpc_device(t2b200_ctx* ctx, int code, const int8_t* d_llr, int n_cw, uint8_t* d_bits, int32_t* d_trials,
                    int32_t* d_iters, int max_trials, unsigned flags);
+// geometry the symbol tables of `kind` were configured with (t2b200_eq_configure); false when they are missing
+bool t2_eq_geometry(const t2b200_ctx* ctx, int kind, int* fft_size, int* n_out, int* n_symbols, int* first_symbol);

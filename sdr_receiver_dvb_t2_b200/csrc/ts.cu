@@ -20,7 +20,7 @@ namespace {
 
 constexpr int PKT = 188;
 
-struct TsHdr {                                         // status: 0 HEM ok, 1 header CRC, 2 SYNCD == 65535, 3 normal mode
+struct TsHdr {                                         // status: 0 HEM ok, 1 header CRC, 2 SYNCD == 65535, 3 normal mode, 4 DFL too long
   int status, dfl, syncd;
   // what a frame does when it is entered with a held-back tail (the usual case: its packet phase after the head is 0, so
   // everything behind the head depends on the frame alone) -- computed by the parallel parse kernel, divisions included
@@ -94,6 +94,10 @@ __global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames
   h.syncd = (int)field(b + 56, 16);
   h.status = reg == 0xABu ? 0 : reg == 0u ? 3 : 1;
   if (h.status == 0 && h.syncd == 65535) h.status = 2;
+  // A header whose CRC-8 passes by chance (or a crafted one) can announce a data field longer than the frame: the reference
+  // would walk off the end of its buffer (it has no such check); here the frame is dropped like a header CRC error, without
+  // touching the carried packet state.
+  if (h.status == 0 && 80 + h.dfl > k_bch) h.status = 4;
   const TsBody body = ts_body(h.dfl - h.syncd, PKT);     // entered with a tail: the head completes a packet first
   h.main_n = body.M; h.main_out = body.T; h.ntail = body.split ? body.ntail : -1; h.tail_sync = body.tail_sync;
   h.end_packet = body.end_packet; h.end_buffer = body.end_buffer;

@@ -62,3 +62,21 @@ def test_single_symbol_live_mode_calls(engine):
     whole = engine.fft(x)
     for i in range(3):
         assert np.array_equal(engine.fft(x[i:i + 1])[0], whole[i])
+
+
+def test_frame_pipeline_rejects_a_geometry_that_differs_from_the_symbol_tables(engine):
+    """t2b200_frames_configure cross-checks fft_size / cells per symbol / symbols per frame against what t2b200_eq_configure
+    stored (a mismatch would scatter cells across neighbouring symbols), and t2b200_frames_decode bounds max_trials"""
+    m = E.mode_init('16K', True, 7, '1/128', 10)
+    assert engine.L.t2b200_eq_configure_mode(engine.h, C.byref(m)) == E.OK
+    engine.ti_configure(0, 0, 2, 16)
+    good = dict(fft_size=m.fft_size, len_frame=m.len_frame, n_p2=1, l_fc=0, c_p2=m.c_p2, c_data=m.c_data, n_fc=0, first_cell=2200,
+                plp=0, mod=2, rotation=1, fec_type=0, code_rate=1, n_blocks=32, ti_len=2)
+    engine.frames_configure(**good)
+    for k, v in (('c_data', m.c_data - 2), ('c_p2', m.c_p2 + 6), ('fft_size', 32768), ('len_frame', m.len_frame + 3)):
+        with pytest.raises(E.T2Error):
+            engine.frames_configure(**dict(good, **{k: v}))
+    engine.frames_configure(**good)
+    iq = np.zeros((1, m.len_frame, m.fft_size), np.complex64)
+    out = np.zeros((32, 9552), np.uint8)
+    assert engine.L.t2b200_frames_decode(engine.h, iq.ctypes.data, 1, out.ctypes.data, None, None, None, None, 64, 3) == E.ERR_ARG

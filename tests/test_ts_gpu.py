@@ -81,3 +81,26 @@ def test_chain_bbframes_to_ts(engine):
     want = port_datagrams(f['bb'])
     assert (st == 0).all() and list(dl) == [len(d) for d in want]
     assert np.array_equal(ts.cpu().numpy(), np.concatenate(want))
+
+
+def test_oversize_dfl_is_dropped_without_touching_the_state(engine):
+    """a header with a valid CRC-8 that announces a data field longer than the frame (80 + DFL > k_bch): status 4, no
+    datagram, and the frames around it come out as if it had been a header-CRC drop (the reference has no such check and
+    would read past the frame)"""
+    from tests.ts_helpers import bbframes, header
+    frames, _ = bbframes(9552, 1180, 8, True, np.random.default_rng(5))
+    bad = frames.copy()
+    bad[3, :80] = header(65528, 0, True)                  # DFL = 65528 bits on a 9552-bit frame, CRC-8 correct
+    bad[7, :80] = header(9552 - 80 + 8, 0, True)          # the last frame of the batch: one byte too long
+    ref = frames.copy()
+    for f in (3, 7):
+        ref[f, 79] ^= 1
+        ref[f, 78] ^= 1                                   # the same frames with a broken header CRC instead
+    engine.ts_reset(0)
+    ts, dl, st = engine.ts_packetize(bad)
+    engine.ts_reset(0)
+    ts2, dl2, st2 = engine.ts_packetize(ref)
+    assert list(st) == [0, 0, 0, 4, 0, 0, 0, 4] and list(st2) == [0, 0, 0, 1, 0, 0, 0, 1]
+    assert dl[3] == 0 and dl[7] == 0 and list(dl) == list(dl2) and np.array_equal(ts, ts2)
+    want = port_datagrams(ref)
+    assert np.array_equal(ts, np.concatenate([d for d in want if d is not None]))
