@@ -84,19 +84,91 @@ def hbm_peak():
     return 6650.0, 'fallback'
 
 
-def synth_llr(torch, n, device, seed):
-    """int8 LLRs of the all-zero codeword (the code is linear) after BPSK + AWGN at EBN0_DB, quantised as
+def synth_llr(torch, n, device, seed, n_bits=CODE_N, k_bits=CODE_K, ebn0_db=EBN0_DB):
+    """int8 LLRs of the all-zero codeword (the code is linear) after BPSK + AWGN at ebn0_db, quantised as
     clip(round(2*llr)) -- SURVEY 8d config 3.  Generated on the device."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    rate = CODE_K / CODE_N
-    sigma = (1.0 / (2.0 * rate * 10 ** (EBN0_DB / 10.0))) ** 0.5
-    out = torch.empty((n, CODE_N), dtype=torch.int8, device=device)
+    rate = k_bits / n_bits
+    sigma = (1.0 / (2.0 * rate * 10 ** (ebn0_db / 10.0))) ** 0.5
+    out = torch.empty((n, n_bits), dtype=torch.int8, device=device)
     step = 512
     for i in range(0, n, step):
         m = min(step, n - i)
-        y = 1.0 + sigma * torch.randn((m, CODE_N), generator=g, device=device)
+        y = 1.0 + sigma * torch.randn((m, n_bits), generator=g, device=device)
         out[i:i + m] = torch.clamp(torch.round(2.0 * (2.0 / (sigma * sigma)) * y), -128, 127).to(torch.int8)
+    return out
+
+
+# BASELINE config 3: LDPC-only batched sweep, 64 800-bit FECFRAMEs, rates 1/2 .. 5/6 (code ids 0..5)
+SWEEP_EBN0 = {0: 1.4, 1: 2.5, 2: 2.9, 3: 3.4, 4: 3.9, 5: 4.3}
+SWEEP_RATES = {0: '1/2', 1: '3/5', 2: '2/3', 3: '3/4', 4: '4/5', 5: '5/6'}
+SWEEP_BATCHES = (32, 1024, 8192, 65536)
+
+
+def ldpc_sweep(torch, eng, E, dev, stream):
+    """codewords/s of t2b200_ldpc_decode (lock-step groups of 32, BCH strip + descramble fused) per rate and batch"""
+    out = {}
+    for code in range(6):
+        N, K, KB = eng.ldpc_geometry(code)
+        base = synth_llr(torch, 8192, dev, 40 + code, N, K, SWEEP_EBN0[code])
+        row = {}
+        for B in SWEEP_BATCHES:
+            llr = base[:B] if B <= 8192 else base.repeat(B // 8192, 1)
+            bits = torch.empty((B, KB), dtype=torch.uint8, device=dev)
+            flags = E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE
+            r = eng.ldpc_decode(code, llr, flags=flags, out=bits)
+            stream.synchronize()
+            reps = 3 if B <= 8192 else 1
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                eng.ldpc_decode(code, llr, flags=flags, out=bits, want_status=False)
+            b.record(stream)
+            stream.synchronize()
+            ms = a.elapsed_time(b) / reps
+            row[str(B)] = {'codewords_per_s': B / (ms * 1e-3), 'ms': ms, 'mean_iterations': float(r['iterations'].float().mean().item()),
+                           'converged': float((r['trials_left'] >= 0).float().mean().item())}
+            del llr, bits
+        out[SWEEP_RATES[code]] = dict(row, ebn0_db=SWEEP_EBN0[code])
+        del base
+    return out
+
+
+def ldpc_sweep_cpu(seconds_per_rate=2.0):
+    """the reference's own decoder (oracle/_ref/libref_ldpc.so: LDPCDecoder<SIMD<int8_t,32>>, one 32-codeword batch per call) on
+    all host threads, same LLR statistics: codewords/s per rate"""
+    import ctypes as C
+    import numpy as np
+    from oracle import pyoracle as O
+    if not O.have_ref():
+        return None
+    L = O.ref_ldpc()
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    out = {}
+    for code in range(6):
+        N, K = O.code_nk(code)
+        rate = K / N
+        sigma = (1.0 / (2.0 * rate * 10 ** (SWEEP_EBN0[code] / 10.0))) ** 0.5
+        rng = np.random.default_rng(40 + code)
+        y = 1.0 + sigma * rng.standard_normal((32, N), dtype=np.float32)
+        grp = np.clip(np.rint(2.0 * (2.0 / (sigma * sigma)) * y), -128, 127).astype(np.int8)
+        done = [0] * ncpu
+        stop = time.perf_counter() + seconds_per_rate
+
+        def worker(i):
+            dec = L.ref_ldpc_new(code)
+            bits = np.empty((32, K), np.uint8)
+            while time.perf_counter() < stop:
+                L.ref_ldpc_decode32(dec, code, grp, bits.ctypes.data_as(C.c_void_p), None, 25)
+                done[i] += 32
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(ncpu)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        out[SWEEP_RATES[code]] = {'codewords_per_s': sum(done) / (time.perf_counter() - t0), 'cores': ncpu}
     return out
 
 
@@ -442,6 +514,43 @@ def run_t2b200(args):
             ts_ok = 0.0
             print('ts_packetize failed: %s' % e, file=sys.stderr)
 
+        # ---- BASELINE configs 3 and 4 next to the headline (single-GPU runs only: they are not part of the scaling curve) ----
+        sweep, cfg4 = None, None
+        if world == 1 and not os.environ.get('T2B200_BENCH_SKIP_EXTRAS'):
+            try:
+                sweep = ldpc_sweep(torch, eng, E, dev, stream)
+            except Exception as e:
+                sweep = 'failed: %s' % e
+            try:
+                # config 4: 8 MHz 16K ext PP7 GI1/128, 64-QAM rotated r3/5, 16 200-bit FECFRAMEs (288 per frame, TI 96/96/96),
+                # whole hot path with the reference-exact wrapping cast (this mode decodes in the reference too)
+                t16 = E.mode_tables(E.mode_init('16K', True, 7, '1/128', 59))
+                m16 = Modulator(t16, mod=2, cod=1, fec_normal=False, n_blocks=288, ti_len=3, seed=300)
+                f16 = np.stack([m16.frame(noise_cn_db=16.0)['time'] for _ in range(2)])
+                eng4 = t2.Engine(local, stream=stream.cuda_stream)
+                ch4 = FrameChain(eng4, t16, mod=2, cod=1, fec_type=0, n_blocks=288, ti_len=3)
+                F4 = 40
+                x4 = torch.from_numpy(f16).to(dev)[torch.arange(F4, device=dev) % 2].contiguous()
+                x4 += torch.view_as_complex(1e-6 * torch.randn((F4, x4.shape[1], x4.shape[2], 2), device=dev))
+                r4 = ch4.decode_frames_fused(x4)
+                stream.synchronize()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                for _ in range(5):
+                    ch4.decode_frames_fused(x4, want_status=False)
+                c1.record(stream)
+                stream.synchronize()
+                ms4 = c0.elapsed_time(c1) / 5
+                cfg4 = {'workload': '8MHz 16K ext PP7 GI1/128, 64-QAM rotated r3/5 16200, 288 FEC blocks per frame, %d frames per step, '
+                                    'reference-exact cast' % F4,
+                        'codewords_per_s': F4 * 288 / (ms4 * 1e-3), 'ms_per_step': ms4, 'ts_mbit_s': F4 * 288 * (9552 - 80) * 188.0 / 187.0 / (ms4 * 1e-3) / 1e6,
+                        'converged_fraction': float((r4['trials_left'] >= 0).float().mean().item()),
+                        'realtime_multiple': (F4 / (ms4 * 1e-3)) / (1.0 / ((2048 + 60 * (16384 + 128)) * 7e-6 / 64))}
+                eng4.close()
+                del x4
+            except Exception as e:
+                cfg4 = 'failed: %s' % e
+
         # ---- SURVEY 8e scatter / gather variant (N > 1): rank 0 holds the LLRs of a pooled batch, every rank decodes a
         # shard of whole 32-codeword groups, bits return to rank 0 over NCCL point-to-point ----
         sg = None
@@ -489,17 +598,21 @@ def run_t2b200(args):
         with torch.cuda.stream(stream2):
             chain2 = FrameChain(eng2, tables, mod=3, cod=2, fec_type=1, n_blocks=FEC_PER_FRAME, ti_len=3)
         lanes = [(stream, chain), (stream2, chain2)]
-        h_in = [torch.empty((F, L, N), dtype=torch.complex64).pin_memory() for _ in range(2)]
+        # the form a device front-end delivers and a TS sink consumes: int16 I/Q in (rx_sdrplay.cpp:246; converted on the
+        # device while the FFT loads it), packed BBFRAME bits out (T2B200_LDPC_PACK_BITS)
+        gain = 3500.0 / float(bufs[0].abs().pow(2).mean().sqrt().item() / (2 ** 0.5))      # int16 rms ~3500 per rail
+        h_in = [torch.empty((F, L, N, 2), dtype=torch.int16).pin_memory() for _ in range(2)]
         for i in range(2):
-            h_in[i].copy_(bufs[i])
-        h_out = [torch.empty((F * FEC_PER_FRAME, CODE_KBCH), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            h_in[i].copy_(torch.view_as_real(bufs[i]).mul(gain).round().clamp(-32768, 32767).to(torch.int16))
+        e2e_flags = E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE | E.LDPC_PACK_BITS
+        h_out = [torch.empty((F * FEC_PER_FRAME, CODE_KBCH // 8), dtype=torch.uint8).pin_memory() for _ in range(2)]
         e2e_steps = max(4, min(args.steps, 8))
 
         # One host thread per lane calls t2b200_frames_decode with HOST pointers (pinned IQ in, pinned bits out): the call
         # copies in, runs the chain, copies out and returns when the host buffer is filled; the other lane's call overlaps it.
         def lane_worker(k, n):
             for _ in range(n):
-                lanes[k][1].decode_frames_fused(h_in[k], want_status=False, out=h_out[k])
+                lanes[k][1].decode_frames_fused(h_in[k], flags=e2e_flags, want_status=False, out=h_out[k], scale=1.0 / gain)
         per_lane = e2e_steps // 2
         e2e_steps = 2 * per_lane
         for k in range(2):
@@ -514,6 +627,11 @@ def run_t2b200(args):
             x.join()
         e2e_s = time.perf_counter() - t0
         barrier()
+        # the packed bits the host got back are the device path's bits of the same frames (int16 quantisation does not move a bit)
+        with torch.cuda.stream(stream):
+            ref_bits = chain.decode_frames_fused(bufs[0], want_status=False)['bits']
+            stream.synchronize()
+            e2e_ok = bool((torch.from_numpy(np.unpackbits(h_out[0].numpy(), axis=1)).to(dev) == ref_bits).all().item())
         eng2.close()
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -582,9 +700,11 @@ def run_t2b200(args):
             'workload_stats': {'mean_ldpc_iterations': mean_iters, 'converged_fraction': frac_ok,
                                'overlap': 'two contexts on two streams take alternate steps (t2b200_frames_decode, device buffers)'},
             'e2e': {'value': e2e_value, 'unit': 'codewords/s', 'ts_mbit_s': ts_mbit(e2e_value),
-                    'h2d_bytes_per_step': F * L * N * 8, 'd2h_bytes_per_step': cw_step * CODE_KBCH,
-                    'steps': e2e_steps, 'api': 't2b200_frames_decode with host pointers: pinned host IQ in, pinned host BBFRAME bits (byte per bit) out, '
-                           'one C call per step; two host threads (one context + stream each): one call\'s copies overlap the other\'s compute'},
+                    'h2d_bytes_per_step': F * L * N * 4, 'd2h_bytes_per_step': cw_step * CODE_KBCH // 8,
+                    'steps': e2e_steps, 'bits_ok': e2e_ok,
+                    'api': 't2b200_frames_decode_i16 with host pointers: pinned host int16 I/Q in (converted on the device), pinned host '
+                           'BBFRAME bits (packed) out, one C call per step; two host threads (one context + stream each): one call\'s '
+                           'copies overlap the other\'s compute'},
             'gpu_launches': int(launches),
             'stages': stages,
             'ldpc_only': {'value': cw_step / (ldpc_ms * 1e-3), 'unit': 'codewords/s', 'ms': ldpc_ms,
@@ -605,6 +725,15 @@ def run_t2b200(args):
             'cpu_baseline': cpu,
             'clocks': sampler.summary(),
         }
+        if sweep is not None:
+            line['extra'] = {'config3_ldpc_sweep': {'gpu': sweep, 'cpu_reference_all_cores': None,
+                                                    'note': 'BASELINE config 3: 64800-bit codes, lock-step groups of 32 (reference batch semantics), '
+                                                            'BCH strip + BB descramble fused, B codewords resident in HBM; all-zero codeword + BPSK/AWGN int8 LLRs'},
+                             'config4_16k_64qam_r35_short': cfg4}
+            try:
+                line['extra']['config3_ldpc_sweep']['cpu_reference_all_cores'] = ldpc_sweep_cpu()
+            except Exception as e:
+                line['extra']['config3_ldpc_sweep']['cpu_reference_all_cores'] = 'failed: %s' % e
         if sg:
             line['sharded_fec'] = {'value': sg[1] / (sg_ms * 1e-3), 'unit': 'codewords/s', 'ms': sg_ms, 'codewords': sg[1],
                                    'bits_match_single_gpu': sg[2],

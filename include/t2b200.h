@@ -215,7 +215,8 @@ int t2b200_eq_configure_mode(t2b200_ctx* ctx, const t2b200_mode* mode);
 /* ---- K1: OFDM FFT --------------------------------------------------------------------------- */
 /* Replaces fast_fourier_transform::init + execute (DSP/fast_fourier_transform.h:54-70) for a batch of
  * symbols: out[b] = halves-swapped, unnormalised forward DFT (FFTW_FORWARD sign) of in[b].
- *   n      4096, 8192, 16384 or 32768 (the reference runs 16K and 32K)
+ *   n      a power of two from 256 to 32768: 16K / 32K OFDM symbols (the modes the reference runs) and the 1K transform of
+ *          the P1 symbol (p1_symbol.cpp:34-35,114)
  *   in     complex<float>[batch][n]  the n samples after the guard interval (dvbt2_demodulator.cpp:332)
  *   out    complex<float>[batch][n]  carrier k of the active band sits at index l_nulls + k
  * FFTW is a binary-only dependency of the reference: agreement is to <= 1e-5 * max|X| (float64 DFT). */
@@ -258,6 +259,12 @@ int t2b200_frames_configure(t2b200_ctx* ctx, const t2b200_frame_cfg* cfg);
  *   feedback floats);  snr float[n_frames * ti_len] or NULL.  Device buffers keep the call asynchronous.                 */
 int t2b200_frames_decode(t2b200_ctx* ctx, const float* iq, int n_frames, uint8_t* bits_out, int32_t* trials_left,
                          float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags);
+/* The same with the FFT windows as the device front-ends deliver samples (rx_sdrplay.cpp:246: int16 I and Q), interleaved
+ *   iq   int16[n_frames][len_frame][fft_size][2]  (I, Q); sample = (I + jQ) * scale
+ * converted on the device while the FFT loads them -- the first step of dvbt2_demodulator::execute
+ * (dvbt2_demodulator.cpp:182-186, short_to_float = 2^-14 / 2^-12 / 2^-11 by device).  Half the bytes over PCIe and HBM. */
+int t2b200_frames_decode_i16(t2b200_ctx* ctx, const int16_t* iq, float scale, int n_frames, uint8_t* bits_out,
+                             int32_t* trials_left, float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags);
 
 #ifdef __cplusplus
 }

@@ -146,9 +146,11 @@ class FrameChain:
             r['llr'], r['ti'] = d['llr'], ti
         return r
 
-    def decode_frames_fused(self, time, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE, max_trials=25, want_status=True, out=None):
-        """the whole chain through t2b200_frames_decode (the engine keeps ONE frame configuration: the last chain built)"""
-        return self.eng.frames_decode(time, flags=flags, max_trials=max_trials, want_status=want_status, out=out)
+    def decode_frames_fused(self, time, flags=E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE, max_trials=25, want_status=True, out=None,
+                            scale=None):
+        """the whole chain through t2b200_frames_decode (the engine keeps ONE frame configuration: the last chain built);
+        scale given: `time` holds int16 (I, Q) pairs [F][len_frame][fft_size][2] (t2b200_frames_decode_i16)"""
+        return self.eng.frames_decode(time, flags=flags, max_trials=max_trials, want_status=want_status, out=out, scale=scale)
 
     def decode_frames(self, time, host_feedback=True, **kw):
         """host_feedback=False leaves sro / phase / snr / precision on the device: nothing in the call waits for the GPU"""

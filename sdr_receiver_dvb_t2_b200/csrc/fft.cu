@@ -95,19 +95,30 @@ template <int A> __device__ __forceinline__ void fft_small(float2 (&x)[8])
 // Thread (a = warp, c = lane) loads the 16 samples n1 = A*r + a of column n2_0 + c straight from global memory (a warp
 // reads 256 contiguous bytes per instruction), runs the radix-16 butterflies in registers, passes the results through one
 // shared-memory exchange to the radix-A stage (again in registers) and stores Y, inter-pass twiddle applied, as 256-byte rows.
-template <int A>
-__global__ void __launch_bounds__(32 * A) fft_pass_a(const float2* __restrict__ in, float2* __restrict__ tmp,
-                                                      const float2* __restrict__ wn, int n)
+// I16: the samples are the int16 I/Q pairs of a device front-end, converted on load with the reference's scale
+// (dvbt2_demodulator.cpp:182-186: real = I * short_to_float) -- 4 bytes per sample over HBM and PCIe instead of 8.
+template <int A, bool I16>
+__global__ void __launch_bounds__(32 * A) fft_pass_a(const void* __restrict__ in_any, float2* __restrict__ tmp,
+                                                      const float2* __restrict__ wn, int n, float scale)
 {
   constexpr int N1 = 16 * A;
   __shared__ float2 sm[16 * A * kColsA];
   const int c = threadIdx.x & 31, a = threadIdx.x >> 5;
   const int n2 = blockIdx.x * kColsA + c;
-  const float2* src = in + (size_t)blockIdx.y * n + n2;
   float2* dst = tmp + (size_t)blockIdx.y * n + n2;
   float2 x[16];
+  if (I16) {
+    const short2* src = static_cast<const short2*>(in_any) + (size_t)blockIdx.y * n + n2;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) x[r] = __ldg(src + (size_t)(A * r + a) * N2);
+    for (int r = 0; r < 16; ++r) {
+      const short2 v = __ldg(src + (size_t)(A * r + a) * N2);
+      x[r] = make_float2((float)v.x * scale, (float)v.y * scale);
+    }
+  } else {
+    const float2* src = static_cast<const float2*>(in_any) + (size_t)blockIdx.y * n + n2;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = __ldg(src + (size_t)(A * r + a) * N2);
+  }
   fft16(x);
   const int wstep1 = n / N1;                                       // W_N1^e = W_n^(e * n / N1)
 #pragma unroll
@@ -173,6 +184,37 @@ __global__ void __launch_bounds__(256) fft_pass_b(const float2* __restrict__ tmp
   }
 }
 
+// Small transforms (n = 256 .. 2048: the 1K FFT of the P1 symbol, p1_symbol.cpp:34-35,114): one CTA per transform, the
+// whole symbol in shared memory, radix-2 Stockham stages with twiddles W_n^m from the plan's table, half-swap on store.
+// One such transform per T2 frame is all the receiver does, so nothing here is tuned.
+__global__ void __launch_bounds__(256) fft_small_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                        const float2* __restrict__ wn, int n, int log2n)
+{
+  extern __shared__ float2 sm_small[];
+  float2* a = sm_small;
+  float2* b = sm_small + n;
+  const float2* src = in + (size_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = src[i];
+  __syncthreads();
+  // Stockham auto-sort, decimation in frequency: after stage s the sub-transform length is n >> (s + 1)
+  int l = n >> 1, m = 1;
+  for (int s = 0; s < log2n; ++s) {
+    for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+      const int j = t / m, k = t - j * m;                          // j < l, k < m
+      const float2 c0 = a[k + j * m], c1 = a[k + j * m + l * m];
+      const float2 w = wn[(j * m) & (n - 1)];                      // W_n^(j * m) = W_(2l)^j
+      b[k + 2 * j * m] = cadd(c0, c1);
+      b[k + 2 * j * m + m] = cmul(csub(c0, c1), w);
+    }
+    __syncthreads();
+    float2* t2 = a; a = b; b = t2;
+    l >>= 1; m <<= 1;
+  }
+  float2* dst = out + (size_t)blockIdx.x * n;
+  const int half = n >> 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[(i + half) & (n - 1)] = a[i];
+}
+
 }  // namespace
 
 void t2_fft_free(t2b200_ctx* ctx)
@@ -185,7 +227,7 @@ static int get_plan(t2b200_ctx* ctx, int n, FftPlan** out)
 {
   auto it = ctx->fft.find(n);
   if (it != ctx->fft.end()) { *out = it->second; return T2B200_OK; }
-  if (n < 4096 || n > 32768 || (n & (n - 1))) { ctx->err = "t2b200_fft: n must be a power of two in [4096, 32768]"; return T2B200_ERR_ARG; }
+  if (n < 256 || n > 32768 || (n & (n - 1))) { ctx->err = "t2b200_fft: n must be a power of two in [256, 32768]"; return T2B200_ERR_ARG; }
   FftPlan* p = new FftPlan();
   p->n = n; p->n1 = n / N2;
   std::vector<float2> wn(n), w256(N2);
@@ -201,24 +243,38 @@ static int get_plan(t2b200_ctx* ctx, int n, FftPlan** out)
   return T2B200_OK;
 }
 
-// device-resident batch: in, out, tmp all on the device
-int t2_fft_device(t2b200_ctx* ctx, int n, const float2* d_in, int batch, float2* d_out, float2* d_tmp)
+// device-resident batch: in, out, tmp all on the device.  d_in16 != nullptr: int16 I/Q input (scale applied on load)
+int t2_fft_device(t2b200_ctx* ctx, int n, const float2* d_in, int batch, float2* d_out, float2* d_tmp, const short2* d_in16,
+                  float scale)
 {
   FftPlan* p; int rc;
   if ((rc = get_plan(ctx, n, &p))) return rc;
+  if (n < 4096) {
+    if (d_in16) { ctx->err = "t2b200_fft: int16 input needs n >= 4096"; return T2B200_ERR_ARG; }
+    int log2n = 0;
+    while ((1 << log2n) < n) ++log2n;
+    fft_small_kernel<<<batch, 256, 2 * (size_t)n * sizeof(float2), ctx->stream>>>(d_in, d_out, p->d_wn, n, log2n);
+    T2_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return T2B200_OK;
+  }
   // walk the batch in chunks whose input + intermediate + output stay well inside the 126 MB L2
   const int chunk = std::max(1, (int)((48u << 20) / ((size_t)n * sizeof(float2) * 2)));
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int nb = std::min(chunk, batch - b0);
-    const float2* cin = d_in + (size_t)b0 * n;
+    const void* cin = d_in16 ? (const void*)(d_in16 + (size_t)b0 * n) : (const void*)(d_in + (size_t)b0 * n);
     float2* ctmp = d_tmp;
     const dim3 ga(N2 / kColsA, nb);
+#define T2_PASS_A(AA) \
+    if (d_in16) fft_pass_a<AA, true><<<ga, 32 * AA, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n, scale); \
+    else fft_pass_a<AA, false><<<ga, 32 * AA, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n, 1.0f)
     switch (p->n1 / 16) {
-      case 1: fft_pass_a<1><<<ga, 32, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
-      case 2: fft_pass_a<2><<<ga, 64, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
-      case 4: fft_pass_a<4><<<ga, 128, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
-      default: fft_pass_a<8><<<ga, 256, 0, ctx->stream>>>(cin, ctmp, p->d_wn, n); break;
+      case 1: T2_PASS_A(1); break;
+      case 2: T2_PASS_A(2); break;
+      case 4: T2_PASS_A(4); break;
+      default: T2_PASS_A(8); break;
     }
+#undef T2_PASS_A
     T2_CUDA(ctx, cudaGetLastError());
     fft_pass_b<<<dim3(p->n1 / kRowsB, nb), 256, 0, ctx->stream>>>(ctmp, d_out + (size_t)b0 * n, p->d_w256, n, p->n1);
     T2_CUDA(ctx, cudaGetLastError());
@@ -231,7 +287,7 @@ extern "C" int t2b200_fft(t2b200_ctx* ctx, int n, const float* in, int batch, fl
 {
   if (!ctx) return T2B200_ERR_ARG;
   if (!in || !out || batch < 0) { ctx->err = "t2b200_fft: bad argument"; return T2B200_ERR_ARG; }
-  if (n < 4096 || n > 32768 || (n & (n - 1))) { ctx->err = "t2b200_fft: n must be 4096, 8192, 16384 or 32768"; return T2B200_ERR_ARG; }
+  if (n < 256 || n > 32768 || (n & (n - 1))) { ctx->err = "t2b200_fft: n must be a power of two from 256 to 32768"; return T2B200_ERR_ARG; }
   if (batch == 0) return T2B200_OK;
   T2_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc; const void* din; void *dout, *dtmp;
@@ -240,6 +296,6 @@ extern "C" int t2b200_fft(t2b200_ctx* ctx, int n, const float* in, int batch, fl
   if ((rc = t2_out_device(ctx, 1, out, bytes, &dout))) return rc;
   const int chunk = std::max(1, (int)((48u << 20) / ((size_t)n * sizeof(float2) * 2)));
   if ((rc = t2_dev_scratch(ctx, 4, (size_t)std::min(chunk, batch) * n * sizeof(float2), &dtmp))) return rc;
-  if ((rc = t2_fft_device(ctx, n, (const float2*)din, batch, (float2*)dout, (float2*)dtmp))) return rc;
+  if ((rc = t2_fft_device(ctx, n, (const float2*)din, batch, (float2*)dout, (float2*)dtmp, nullptr, 1.0f))) return rc;
   return t2_finish_out(ctx, out, dout, bytes);
 }

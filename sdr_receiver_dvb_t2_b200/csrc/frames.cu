@@ -133,8 +133,24 @@ static int pipe_reserve(t2b200_ctx* ctx, FramePipe* p, int F, bool host_iq)
   return T2B200_OK;
 }
 
+static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale, int n_frames, uint8_t* bits_out,
+                         int32_t* trials_left, float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags);
+
 extern "C" int t2b200_frames_decode(t2b200_ctx* ctx, const float* iq, int n_frames, uint8_t* bits_out, int32_t* trials_left,
                                     float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags)
+{
+  return frames_decode(ctx, iq, false, 1.0f, n_frames, bits_out, trials_left, sro, phase, snr, max_trials, ldpc_flags);
+}
+
+extern "C" int t2b200_frames_decode_i16(t2b200_ctx* ctx, const int16_t* iq, float scale, int n_frames, uint8_t* bits_out,
+                                        int32_t* trials_left, float* sro, float* phase, float* snr, int max_trials,
+                                        unsigned ldpc_flags)
+{
+  return frames_decode(ctx, iq, true, scale, n_frames, bits_out, trials_left, sro, phase, snr, max_trials, ldpc_flags);
+}
+
+static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale, int n_frames, uint8_t* bits_out,
+                         int32_t* trials_left, float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags)
 {
   if (!ctx) return T2B200_ERR_ARG;
   FramePipe* p = ctx->frames;
@@ -147,13 +163,16 @@ extern "C" int t2b200_frames_decode(t2b200_ctx* ctx, const float* iq, int n_fram
   const bool host_iq = !t2_is_device_ptr(iq);
   int rc;
   if ((rc = pipe_reserve(ctx, p, F, host_iq))) return rc;
-  const float2* d_iq = reinterpret_cast<const float2*>(iq);
+  // the staging buffer is sized for float2 samples; int16 pairs use the first half of it
+  const void* d_iq = iq;
   if (host_iq) {
-    T2_CUDA(ctx, cudaMemcpyAsync(p->d_iq, iq, (size_t)F * L * N * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    T2_CUDA(ctx, cudaMemcpyAsync(p->d_iq, iq, (size_t)F * L * N * (i16 ? sizeof(short2) : sizeof(float2)), cudaMemcpyHostToDevice,
+                                 ctx->stream));
     d_iq = p->d_iq;
   }
-  // K1
-  if ((rc = t2_fft_device(ctx, N, d_iq, F * L, p->d_freq, p->d_tmp))) return rc;
+  // K1 (int16 samples are converted on load: the first slice of the front-end, dvbt2_demodulator.cpp:182-186)
+  if ((rc = t2_fft_device(ctx, N, i16 ? nullptr : static_cast<const float2*>(d_iq), F * L, p->d_freq, p->d_tmp,
+                          i16 ? static_cast<const short2*>(d_iq) : nullptr, scale))) return rc;
   // K2: every symbol kind writes its cells where the frame cell stream wants them
   float* d_sro = p->d_fb; float* d_ph = p->d_fb + (size_t)F * L;
   const long long frame_in = (long long)L * N;

@@ -31,8 +31,21 @@ template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b)
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
   return r;
 }
-T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }   // run-time selector, no sign mode
+// run-time selector (low 16 bits); the callers' nibbles never have bit 3 set where the result is used
+T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel)
+{
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
 T2_HD int mod360(int t) { return (int)__viaddmin_u32((unsigned)t, 0xfffffe98u, (unsigned)t); }    // t in [0, 720): t mod 360
+T2_HD uint32_t rotl(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+// the pair's posteriors by 32-bit shared-memory address (kept in a register from the load to the store of an edge)
+typedef uint32_t post_ref;
+T2_HD post_ref post_base(uint16_t* post) { return (uint32_t)__cvta_generic_to_shared(post); }
+T2_HD post_ref post_at(post_ref base, int a) { return base + 2u * (uint32_t)a; }
+T2_HD uint32_t post_ld(post_ref r) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(r) : "memory"); return v; }
+T2_HD void post_st(post_ref r, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r), "r"(v) : "memory"); }
 #else
 T2_HD int16_t lo16(uint32_t x) { return (int16_t)(x & 0xffffu); }
 T2_HD int16_t hi16(uint32_t x) { return (int16_t)(x >> 16); }
@@ -62,8 +75,14 @@ T2_HD uint32_t prmt_any(uint32_t a, uint32_t b, uint32_t sel)
   return r;
 }
 template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b) { return prmt_any(a, b, SEL); }
-T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel) { return prmt_any(a, b, sel & 0x7777u); }
+T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel) { return prmt_any(a, b, sel); }
 T2_HD int mod360(int t) { return t >= 360 ? t - 360 : t; }
+T2_HD uint32_t rotl(uint32_t x, int r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
+typedef uint16_t* post_ref;
+T2_HD post_ref post_base(uint16_t* post) { return post; }
+T2_HD post_ref post_at(post_ref base, int a) { return base + a; }
+T2_HD uint32_t post_ld(post_ref r) { return *r; }
+T2_HD void post_st(post_ref r, uint32_t v) { *r = (uint16_t)v; }
 #endif
 
 constexpr uint32_t kP127 = 0x007f007fu, kM128 = 0xff80ff80u, kOne2 = 0x00010001u, kIdleKey = 0x7fff7fffu;
@@ -73,7 +92,7 @@ T2_HD uint32_t sat8_add(uint32_t a, uint32_t b) { return vmax2(vaddmin(a, b, kP1
 T2_HD uint32_t abs2(uint32_t v) { return vaddmax(~v, kOne2, v); }                                   // max(-v, v)
 // two posteriors (one per codeword) as they sit in shared memory (low byte A, high byte B) -> sign-extended s16x2
 T2_HD uint32_t unpack_post(uint32_t raw16) { return prmt<0x9180u>(raw16, 0u); }
-T2_HD uint16_t pack_post(uint32_t v) { return (uint16_t)prmt<0x0020u>(v, 0u); }
+T2_HD uint32_t pack_post(uint32_t v) { return prmt<0x4420u>(v, 0u); }   // low bytes of the two halves, upper half zero
 T2_HD uint32_t pack4(int b0, int b1, int b2, int b3)
 {
   return ((uint32_t)b0 & 0xffu) | (((uint32_t)b1 & 0xffu) << 8) | (((uint32_t)b2 & 0xffu) << 16) | ((uint32_t)b3 << 24);
@@ -82,13 +101,16 @@ T2_HD uint32_t pack4(int b0, int b1, int b2, int b3)
 // Check-node word layout (per codeword).  The min-sum messages of a check node are fully determined by (m0, m1, arg-min
 // slot, output signs): message of slot c = sign_c * (c == arg-min ? m1 : m0).  One 2-bit code per slot (bit 0: sign
 // negative, bit 1: slot is the arg-min), one code per NIBBLE, so that a single PRMT looks the messages of four slots up in
-// a 4-entry byte table {+m0, -m0, +m1, -m1}.
+// a 4-entry byte table {+m0, -m0, +m1, -m1}.  The words of codeword B are kept ROTATED by 16 bits (halves swapped): one
+// rotate of (sx ^ input) then drops the output-sign bits of both codewords (bits 15 and 31) onto their nibbles at once.
 template <int CNL> struct CnLayout {
   static constexpr int SLOTS = CNL + 2;
   static constexpr int NW = (SLOTS + 7) / 8;                 // code words, 8 nibbles each
   static constexpr int TAIL = SLOTS - 8 * (NW - 1);          // nibbles in use in the last code word
   static constexpr bool MPACK = TAIL <= 5;                   // m0 | m1 (6 + 6 bits) share the last code word
   static constexpr int NS = NW + (MPACK ? 0 : 1);            // 32-bit words per check node and codeword
+  // bit position of slot's nibble in its code word; ROT = 0 for codeword A, 16 for codeword B
+  template <int ROT> static constexpr int nib(int slot) { return (4 * (slot & 7) + ROT) & 31; }
 };
 
 enum SlotMode { ALL_SLOTS, PREDICATED, BRANCHED };
@@ -100,32 +122,33 @@ struct CheckNodePair {
   using LY = CnLayout<CNL>;
   static constexpr int SLOTS = LY::SLOTS, NW = LY::NW, NG = (SLOTS + 3) / 4;
   uint32_t inp[SLOTS];      // vqsub(posterior, stored message), s16x2
-  int adr[SLOTS];
+  post_ref adr[SLOTS];      // where the edge's pair of posteriors lives
   uint32_t key0, key1;      // two smallest keys |v| * 32 + slot per half
   uint32_t sx;              // xor of the inputs: sign bits at 15 / 31
   uint32_t tinA, tinB;      // bytes {-clamp(+m0), -clamp(-m0), -clamp(+m1), -clamp(-m1)} of the PREVIOUS iteration
   uint32_t cwA[NW], cwB[NW];        // previous iteration's codes
   uint32_t ninA[NG], ninB[NG];      // minus stored message of slots 4g .. 4g+3, one byte each
   uint32_t ncwA[NW], ncwB[NW];      // codes being built
-  uint16_t* post;
+  post_ref post;
 
-  static T2_HD uint32_t table_in(uint32_t mw)
+  template <int ROT> static T2_HD uint32_t table_in(uint32_t mw)
   {
-    const int m0c = LY::MPACK ? (int)((mw >> 20) & 63u) : (int)(mw & 63u);
-    const int m1c = LY::MPACK ? (int)(mw >> 26) : (int)((mw >> 6) & 63u);
+    constexpr int P = (20 + ROT) & 31;                          // the minima sit behind the nibbles of the last code word
+    const int m0c = LY::MPACK ? (int)((mw >> P) & 63u) : (int)(mw & 63u);
+    const int m1c = LY::MPACK ? (int)((mw >> (P + 6)) & 63u) : (int)((mw >> 6) & 63u);
     return pack4(-(m0c < 31 ? m0c : 31), m0c, -(m1c < 31 ? m1c : 31), m1c);
   }
   T2_HD void begin(uint16_t* post_, const uint32_t (&wA)[LY::NS], const uint32_t (&wB)[LY::NS])
   {
-    post = post_;
-    tinA = table_in(wA[LY::NS - 1]);
-    tinB = table_in(wB[LY::NS - 1]);
+    post = post_base(post_);
+    tinA = table_in<0>(wA[LY::NS - 1]);
+    tinB = table_in<16>(wB[LY::NS - 1]);
 #pragma unroll
     for (int k = 0; k < NW; ++k) { cwA[k] = wA[k]; cwB[k] = wB[k]; ncwA[k] = 0; ncwB[k] = 0; }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       ninA[g] = prmt_rt(tinA, 0u, (g & 1) ? (cwA[g >> 1] >> 16) : cwA[g >> 1]);
-      ninB[g] = prmt_rt(tinB, 0u, (g & 1) ? (cwB[g >> 1] >> 16) : cwB[g >> 1]);
+      ninB[g] = prmt_rt(tinB, 0u, (g & 1) ? cwB[g >> 1] : (cwB[g >> 1] >> 16));
     }
     key0 = kIdleKey; key1 = kIdleKey; sx = 0;
   }
@@ -137,29 +160,34 @@ struct CheckNodePair {
   template <int SLOT> T2_HD uint32_t stored_neg() const { return pick<SLOT & 3>(ninA[SLOT >> 2], ninB[SLOT >> 2]); }
   T2_HD uint32_t stored_neg_rt(int slot) const
   {
-    const int sh4 = 4 * (slot & 7);
-    uint32_t ca = (cwA[0] >> sh4) & 3u, cb = (cwB[0] >> sh4) & 3u;
+    const int sh4 = 4 * (slot & 7), sh4b = (sh4 + 16) & 31;
+    uint32_t ca = (cwA[0] >> sh4) & 3u, cb = (cwB[0] >> sh4b) & 3u;
 #pragma unroll
     for (int k = 1; k < NW; ++k) {
-      const uint32_t xa = (cwA[k] >> sh4) & 3u, xb = (cwB[k] >> sh4) & 3u;
+      const uint32_t xa = (cwA[k] >> sh4) & 3u, xb = (cwB[k] >> sh4b) & 3u;
       ca = (slot >> 3) == k ? xa : ca;
       cb = (slot >> 3) == k ? xb : cb;
     }
     const int a = (int)(int8_t)(tinA >> (8 * ca)), b = (int)(int8_t)(tinB >> (8 * cb));
     return ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
   }
-  T2_HD void take(uint32_t v, int slot_const)
+  // `active` false: the slot does not take part (it is computed and discarded, branch-free, so that the loads of a layer
+  // still issue back to back)
+  T2_HD void take(uint32_t v, int slot_const, bool active = true)
   {
-    const uint32_t key = abs2(v) * 32u + (uint32_t)slot_const * kOne2;       // |v| <= 128: no carry between the halves
+    uint32_t key = abs2(v) * 32u + (uint32_t)slot_const * kOne2;             // |v| <= 128: no carry between the halves
+    key = active ? key : kIdleKey;
     key1 = vmin2(key1, vmax2(key0, key));
     key0 = vmin2(key0, key);
-    sx ^= v;
+    sx ^= active ? v : 0u;
   }
   template <int SLOT> T2_HD void edge_in(int a, bool active)
   {
-    const uint32_t pv = unpack_post(post[a]);
+    const post_ref r = post_at(post, a);
+    const uint32_t pv = unpack_post(post_ld(r));
     const uint32_t v = sat8_add(pv, stored_neg<SLOT>());                      // vqsub(posterior, stored message)
-    if (active) { inp[SLOT] = v; adr[SLOT] = a; take(v, SLOT); }
+    inp[SLOT] = v; adr[SLOT] = r;
+    take(v, SLOT, active);
   }
   // m0 / m1 (after vqabs and the unsigned vqsub of beta = 1: both monotone, so applied to the two minima only) and the
   // arg-min slot of everything seen so far, per half
@@ -172,12 +200,11 @@ struct CheckNodePair {
   }
   template <int SLOT> T2_HD void mark_sign(bool active)
   {
-    if (!active) return;
-    const uint32_t t = sx ^ inp[SLOT];                                        // sign of the product of the OTHER links
-    constexpr int pos = 4 * (SLOT & 7);
-    constexpr uint32_t bit = 1u << pos;
-    ncwA[SLOT >> 3] |= (pos <= 15 ? (t >> (15 - pos)) : (t << (pos - 15))) & bit;
-    ncwB[SLOT >> 3] |= (t >> (31 - pos)) & bit;
+    // sign of the product of the OTHER links: bit 15 (A) lands on its nibble, bit 31 (B) on the rotated one
+    constexpr int pos = LY::template nib<0>(SLOT), posb = LY::template nib<16>(SLOT);
+    const uint32_t u = active ? rotl(sx ^ inp[SLOT], (pos + 17) & 31) : 0u;
+    ncwA[SLOT >> 3] |= u & (1u << pos);
+    ncwB[SLOT >> 3] |= u & (1u << posb);
   }
   template <SlotMode MODE, int C>
   T2_HD void load_from(const uint16_t* eb, const uint16_t* es, int cnt, uint32_t mask, int j)
@@ -209,7 +236,7 @@ struct CheckNodePair {
   template <int SLOT> T2_HD void edge_out(const uint32_t (&noutA)[NG], const uint32_t (&noutB)[NG], bool active)
   {
     const uint32_t o = pick<SLOT & 3>(noutA[SLOT >> 2], noutB[SLOT >> 2]);     // other(mags[i], mins[0], mins[1]) with the sign
-    if (active) post[adr[SLOT]] = pack_post(sat8_add(inp[SLOT], o));           // vqadd
+    if (active) post_st(adr[SLOT], pack_post(sat8_add(inp[SLOT], o)));          // vqadd
   }
   template <SlotMode MODE, int C>
   T2_HD void out_from(const uint32_t (&noutA)[NG], const uint32_t (&noutB)[NG], int cnt, uint32_t mask)
@@ -225,22 +252,23 @@ struct CheckNodePair {
   {
     if constexpr (C < CNL) {
       if ((negA >> C) & 1u) ncwA[C >> 3] |= 1u << (4 * (C & 7));
-      if ((negB >> C) & 1u) ncwB[C >> 3] |= 1u << (4 * (C & 7));
+      if ((negB >> C) & 1u) ncwB[C >> 3] |= 1u << LY::template nib<16>(C);
       merge_shared<C + 1>(negA, negB);
     }
   }
+  template <int ROT>
   static T2_HD void finish_codes(uint32_t (&ncw)[NW], int idn, int m0, int m1, uint32_t (&nout)[NG], uint32_t (&w)[LY::NS])
   {
-    const uint32_t bit = 2u << (4 * (idn & 7));
+    const uint32_t bit = 2u << ((4 * (idn & 7) + ROT) & 31);
 #pragma unroll
     for (int k = 0; k < NW; ++k) ncw[k] |= (idn >> 3) == k ? bit : 0u;
     const uint32_t tout = pack4(m0, -m0, m1, -m1);
 #pragma unroll
-    for (int g = 0; g < NG; ++g) nout[g] = prmt_rt(tout, 0u, (g & 1) ? (ncw[g >> 1] >> 16) : ncw[g >> 1]);
+    for (int g = 0; g < NG; ++g) nout[g] = prmt_rt(tout, 0u, ((g & 1) != (ROT != 0)) ? (ncw[g >> 1] >> 16) : ncw[g >> 1]);
     const uint32_t mm = (uint32_t)(m0 < 32 ? m0 : 32) | ((uint32_t)(m1 < 32 ? m1 : 32) << 6);
 #pragma unroll
     for (int k = 0; k < NW; ++k) w[k] = ncw[k];
-    if (LY::MPACK) w[NW - 1] |= mm << 20; else w[LY::NS - 1] = mm;
+    if (LY::MPACK) w[NW - 1] |= mm << ((20 + ROT) & 31); else w[LY::NS - 1] = mm;
   }
   // Write the private edges back and finish the check-node words.  negA / negB: bit c set when shared slot c (already
   // written by shared_out) carried a negative output sign in codeword A / B.
@@ -254,8 +282,8 @@ struct CheckNodePair {
     mark_sign<CNL + 1>((i | j) != 0);
     if (MODE != ALL_SLOTS) merge_shared<0>(negA, negB);
     uint32_t noutA[NG], noutB[NG];
-    finish_codes(ncwA, (int)(idn & 0xffffu), (int)(m0 & 0xffffu), (int)(m1 & 0xffffu), noutA, wA);
-    finish_codes(ncwB, (int)(idn >> 16), (int)(m0 >> 16), (int)(m1 >> 16), noutB, wB);
+    finish_codes<0>(ncwA, (int)(idn & 0xffffu), (int)(m0 & 0xffffu), (int)(m1 & 0xffffu), noutA, wA);
+    finish_codes<16>(ncwB, (int)(idn >> 16), (int)(m0 >> 16), (int)(m1 >> 16), noutB, wB);
     out_from<MODE, 0>(noutA, noutB, cnt, mask);
     edge_out<CNL>(noutA, noutB, true);
     edge_out<CNL + 1>(noutA, noutB, (i | j) != 0);
@@ -263,12 +291,16 @@ struct CheckNodePair {
   // ---- shared-edge path: the slot number is a run-time (warp-uniform) value ----
   T2_HD uint32_t shared_in(int slot, int a, uint32_t nbl)
   {
-    const uint32_t v = sat8_add(unpack_post(post[a]), nbl);
+    const uint32_t v = sat8_add(unpack_post(post_ld(post_at(post, a))), nbl);
     take(v, slot);
     return v;
   }
   // returns bit 0 (A) / bit 16 (B) set when the output sign is negative
   T2_HD uint32_t shared_out(int slot, int a, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn)
+  {
+    return shared_out_at(slot, post_at(post, a), v, m0, m1, idn);
+  }
+  T2_HD uint32_t shared_out_at(int slot, post_ref where, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn)
   {
     const uint32_t t = sx ^ v;
     const int negA = (t >> 15) & 1u, negB = t >> 31;
@@ -277,7 +309,7 @@ struct CheckNodePair {
     if (negA) ma = -ma;
     if (negB) mb = -mb;
     const uint32_t o = ((uint32_t)ma & 0xffffu) | ((uint32_t)mb << 16);
-    post[a] = pack_post(sat8_add(v, o));
+    post_st(where, pack_post(sat8_add(v, o)));
     return (uint32_t)negA | ((uint32_t)negB << 16);
   }
   template <int C> T2_HD void shared_load_generic(const uint16_t* eb, const uint16_t* es, uint32_t mask, int j)
@@ -293,7 +325,7 @@ struct CheckNodePair {
   {
     if constexpr (C < CNL) {
       if ((mask >> C) & 1u) {
-        const uint32_t r = shared_out(C, adr[C], inp[C], m0, m1, idn);
+        const uint32_t r = shared_out_at(C, adr[C], inp[C], m0, m1, idn);
         negA |= (r & 1u) << C; negB |= (r >> 16) << C;
       }
       shared_store_generic<C + 1>(mask, m0, m1, idn, negA, negB);

@@ -6,7 +6,8 @@
 struct TiBlockDesc { long long in_off, out_off; int n_fec; };           // cell offsets of one TI block
 struct DemapBlockDesc { long long cell_off; int n_cells; int first_fec; };
 
-int t2_fft_device(t2b200_ctx* ctx, int n, const float2* d_in, int batch, float2* d_out, float2* d_tmp);
+int t2_fft_device(t2b200_ctx* ctx, int n, const float2* d_in, int batch, float2* d_out, float2* d_tmp,
+                  const short2* d_in16 = nullptr, float scale = 1.0f);
 int t2_equalize_device(t2b200_ctx* ctx, int kind, int n_symbols, int per_frame, const int* d_idx, const float2* d_freq,
                        long long in_frame, long long in_sym, float2* d_out, long long out_frame, long long out_sym,
                        float* d_sro, float* d_phase, long long fb_frame);

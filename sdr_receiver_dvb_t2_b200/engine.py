@@ -30,7 +30,7 @@ SYMBOLS = [
     't2b200_cell_permutation', 't2b200_demap_address_table', 't2b200_freq_deinterleaver_table', 't2b200_ti_configure', 't2b200_ti_deinterleave',
     't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
     't2b200_ts_reset', 't2b200_ts_packetize', 't2b200_frames_configure', 't2b200_frames_decode',
-    't2b200_mode_init', 't2b200_pilot_tables', 't2b200_eq_configure_mode',
+    't2b200_mode_init', 't2b200_pilot_tables', 't2b200_eq_configure_mode', 't2b200_frames_decode_i16',
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
     L.t2b200_ts_packetize.argtypes = [vp, i32, vp, i32, i32, vp, C.c_size_t, vp, vp, C.POINTER(C.c_longlong)]
     L.t2b200_frames_configure.argtypes = [vp, C.POINTER(FrameCfg)]
     L.t2b200_frames_decode.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, u32]
+    L.t2b200_frames_decode_i16.argtypes = [vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, i32, u32]
     L.t2b200_mode_init.argtypes = [i32] * 6 + [C.POINTER(Mode)]
     L.t2b200_pilot_tables.argtypes = [C.POINTER(Mode), i32, vp, vp]
     L.t2b200_eq_configure_mode.argtypes = [vp, C.POINTER(Mode)]
@@ -127,7 +128,7 @@ def _like(ref, shape, dtype_np):
     if _is_torch(ref):
         import torch
         td = {np.uint8: torch.uint8, np.int8: torch.int8, np.int32: torch.int32,
-              np.float32: torch.float32, np.complex64: torch.complex64}[dtype_np]
+              np.float32: torch.float32, np.complex64: torch.complex64, np.int16: torch.int16}[dtype_np]
         return torch.empty(shape, dtype=td, device=ref.device)
     return np.empty(shape, dtype_np)
 
@@ -264,9 +265,10 @@ class Engine:
         self._frame_cfg = cfg
         self._chk(self.L.t2b200_frames_configure(self.h, C.byref(cfg)))
 
-    def frames_decode(self, iq, flags=LDPC_GROUP32 | LDPC_BCH_DESCRAMBLE, max_trials=25, want_status=True, out=None):
+    def frames_decode(self, iq, flags=LDPC_GROUP32 | LDPC_BCH_DESCRAMBLE, max_trials=25, want_status=True, out=None, scale=None):
         """iq complex64[F][len_frame][fft_size] (numpy / pinned / torch cuda) -> dict(bits, trials_left, sro, phase, snr);
-        outputs live where iq lives (torch cuda in -> torch cuda out, nothing waits for the GPU)"""
+        outputs live where iq lives (torch cuda in -> torch cuda out, nothing waits for the GPU).
+        scale given: iq is int16[F][len_frame][fft_size][2] (I, Q pairs), sample = (I + jQ) * scale (t2b200_frames_decode_i16)"""
         c = self._frame_cfg
         F = iq.shape[0]
         n_cw = F * c.n_blocks
@@ -280,8 +282,12 @@ class Engine:
             r['trials_left'] = _like(iq, (n_cw,), np.int32)
             r['sro'], r['phase'] = _like(iq, (F, c.len_frame), np.float32), _like(iq, (F, c.len_frame), np.float32)
             r['snr'] = _like(iq, (F * c.ti_len,), np.float32)
-        self._chk(self.L.t2b200_frames_decode(self.h, _ptr(iq), F, _ptr(bits), _ptr(r['trials_left']), _ptr(r['sro']),
-                                              _ptr(r['phase']), _ptr(r['snr']), max_trials, flags))
+        if scale is not None:
+            self._chk(self.L.t2b200_frames_decode_i16(self.h, _ptr(iq), float(scale), F, _ptr(bits), _ptr(r['trials_left']),
+                                                      _ptr(r['sro']), _ptr(r['phase']), _ptr(r['snr']), max_trials, flags))
+        else:
+            self._chk(self.L.t2b200_frames_decode(self.h, _ptr(iq), F, _ptr(bits), _ptr(r['trials_left']), _ptr(r['sro']),
+                                                  _ptr(r['phase']), _ptr(r['snr']), max_trials, flags))
         return r
 
     # ---- K1 ----

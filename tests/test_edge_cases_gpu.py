@@ -27,7 +27,7 @@ def test_bad_arguments_are_rejected(engine):
     with pytest.raises(E.T2Error):
         engine.fft(x)                                                    # not a power of two
     with pytest.raises(E.T2Error):
-        engine.fft(np.zeros((1, 2048), np.complex64))                    # below 4K
+        engine.fft(np.zeros((1, 128), np.complex64))                     # below 256
     assert L.t2b200_fft(h, 4096, None, 1, None) == E.ERR_ARG
     assert L.t2b200_ldpc_decode(h, 2, None, 1, None, None, None, None, 25, 0) == E.ERR_ARG
     llr = np.zeros((1, 64800), np.int8)

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-@pytest.mark.parametrize('n', [32768, 16384, 8192, 4096])
+@pytest.mark.parametrize('n', [32768, 16384, 8192, 4096, 2048, 1024, 256])      # 1024: the P1 symbol (p1_symbol.cpp:34-35)
 def test_fft_matches_float64_dft(engine, n):
     rng = np.random.default_rng(n)
     x = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))).astype(np.complex64)
