@@ -444,3 +444,44 @@ class RefDemod:
         x = _tap(L, 'fft_in', np.complex64)
         t['fft_in'] = x.reshape(len(t['fft_info']), -1) if len(t['fft_info']) else x
         return t
+
+
+# ---- the drop-in proof: reference receiver front half + GPU stage classes (oracle/dropin_glue.cc) ----
+class DropinDemod:
+    """The reference's UNMODIFIED dvbt2_demodulator / p1_symbol / p2_symbol / bb_de_header compiled against the GPU stage
+    classes of sdr_receiver_dvb_t2_b200/host/dropin (oracle/_ref/libdropin_chain.so): int16 I/Q in, TS datagrams out.
+    Needs a GPU (the stage classes have no CPU fallback).  One instance per process."""
+
+    def __init__(self, sample_rate=64e6 / 7, need_plp=0):
+        L = C.CDLL(os.path.join(_HERE, '_ref', 'libdropin_chain.so'))
+        L.dropin_demod_new.argtypes = [C.c_float, C.c_int]
+        L.dropin_demod_feed.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.dropin_launches.restype = C.c_longlong
+        for n in ('ts', 'ts_datagrams', 'bb_bits', 'bb_len'):
+            f = getattr(L, 'dropin_tap_' + n)
+            f.argtypes = [C.c_void_p, C.c_longlong]
+            f.restype = C.c_longlong
+        self.L = L
+        L.dropin_demod_new(float(sample_rate), need_plp)
+        self.status = []
+
+    def feed(self, i16, q16, chunk=1 << 16):
+        i16 = np.ascontiguousarray(i16, np.int16)
+        q16 = np.ascontiguousarray(q16, np.int16)
+        for a in range(0, len(i16), chunk):
+            n = min(chunk, len(i16) - a)
+            self.status.append(self.L.dropin_demod_feed(n, i16[a:a + n].ctypes.data, q16[a:a + n].ctypes.data))
+
+    def taps(self):
+        def tap(name, dtype):
+            f = getattr(self.L, 'dropin_tap_' + name)
+            n = f(None, 0)
+            a = np.empty(n, dtype)
+            if n:
+                f(a.ctypes.data, n)
+            return a
+        t = {'ts': tap('ts', np.uint8), 'ts_datagrams': tap('ts_datagrams', np.int32), 'bb_bits': tap('bb_bits', np.uint8),
+             'bb_len': tap('bb_len', np.int32), 'launches': int(self.L.dropin_launches())}
+        n = len(t['bb_len'])
+        t['bb_bits'] = t['bb_bits'].reshape(n, -1) if n else t['bb_bits']
+        return t

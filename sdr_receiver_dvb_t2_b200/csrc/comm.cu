@@ -1,0 +1,216 @@
+// Multi-GPU FEC: FEC blocks are independent, so the LDPC / BCH stage of a pooled batch is sharded by codeword
+// across the GPUs of one box.  ONE exchange step each way -- the int8 LLRs of every rank's shard out from the demodulating
+// rank, the BBFRAME bits back -- as NCCL point-to-point transfers over NVLink / NVSwitch, issued from here (not from
+// Python): a side stream carries the transfers in chunks of <= 1024 codewords, double-buffered against the decode on the
+// context's stream, so a rank decodes chunk t-1 while chunk t arrives and the bits of chunk t-2 leave.
+//
+// NCCL is loaded at run time (dlopen "libnccl.so.2": in a torch process that is the NCCL torch itself uses), so
+// libt2b200.so has no link-time dependency on it and single-GPU users never touch it.
+#include "stages.h"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include <vector>
+
+struct CommState {
+  void* dl = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  cudaStream_t s_comm = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_in[2] = {}, ev_dec[2] = {};
+  int8_t* in_buf = nullptr; uint8_t* out_buf = nullptr; size_t in_cap = 0, out_cap = 0;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+namespace {
+
+constexpr int kChunk = 1024;          // codewords per transfer (32 lock-step groups)
+
+bool load_nccl(CommState* s, std::string& err)
+{
+  if (s->dl) return true;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    s->dl = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (s->dl) break;
+  }
+  if (!s->dl) { err = std::string("NCCL not found: ") + dlerror(); return false; }
+#define T2_SYM(field, sym)                                                       \
+  s->field = reinterpret_cast<decltype(s->field)>(dlsym(s->dl, sym));           \
+  if (!s->field) { err = std::string("NCCL symbol missing: ") + sym; return false; }
+  T2_SYM(GetUniqueId, "ncclGetUniqueId") T2_SYM(CommInitRank, "ncclCommInitRank") T2_SYM(CommDestroy, "ncclCommDestroy")
+  T2_SYM(Send, "ncclSend") T2_SYM(Recv, "ncclRecv") T2_SYM(GroupStart, "ncclGroupStart") T2_SYM(GroupEnd, "ncclGroupEnd")
+  T2_SYM(GetErrorString, "ncclGetErrorString")
+#undef T2_SYM
+  return true;
+}
+
+// contiguous shard of rank r: whole 32-codeword lock-step groups (the reference's batch, ldpc_decoder.h:28-32)
+void span_of(int n_cw, int r, int nranks, int* lo, int* hi)
+{
+  const int units = (n_cw + 31) / 32, base = units / nranks, extra = units % nranks;
+  const int lo_u = r * base + std::min(r, extra), hi_u = lo_u + base + (r < extra ? 1 : 0);
+  *lo = std::min(lo_u * 32, n_cw); *hi = std::min(hi_u * 32, n_cw);
+}
+
+CommState g_loader;                   // t2b200_comm_unique_id needs NCCL before any context has a communicator
+
+}  // namespace
+
+#define T2_NCCL(ctx, s, call)                                                                   \
+  do {                                                                                          \
+    ncclResult_t r__ = (call);                                                                  \
+    if (r__ != ncclSuccess) {                                                                   \
+      (ctx)->err = std::string(#call) + ": " + ((s)->GetErrorString ? (s)->GetErrorString(r__) : "NCCL error"); \
+      return T2B200_ERR_CUDA;                                                                   \
+    }                                                                                           \
+  } while (0)
+
+void t2_comm_free(t2b200_ctx* ctx)
+{
+  CommState* s = ctx->comm;
+  if (!s) return;
+  if (s->comm && s->CommDestroy) s->CommDestroy(s->comm);
+  if (s->s_comm) cudaStreamDestroy(s->s_comm);
+  for (cudaEvent_t e : {s->ev_start, s->ev_done, s->ev_in[0], s->ev_in[1], s->ev_dec[0], s->ev_dec[1]}) if (e) cudaEventDestroy(e);
+  cudaFree(s->in_buf); cudaFree(s->out_buf);
+  delete s;
+  ctx->comm = nullptr;
+}
+
+extern "C" int t2b200_comm_unique_id(void* id_out, size_t id_bytes)
+{
+  std::string err;
+  if (!id_out || id_bytes < sizeof(ncclUniqueId) || !load_nccl(&g_loader, err)) return T2B200_ERR_ARG;
+  ncclUniqueId id;
+  if (g_loader.GetUniqueId(&id) != ncclSuccess) return T2B200_ERR_CUDA;
+  memcpy(id_out, &id, sizeof(id));
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_comm_init(t2b200_ctx* ctx, int rank, int nranks, const void* unique_id, size_t id_bytes)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  if (rank < 0 || nranks < 1 || rank >= nranks || !unique_id || id_bytes < sizeof(ncclUniqueId)) {
+    ctx->err = "t2b200_comm_init: bad argument"; return T2B200_ERR_ARG;
+  }
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  t2_comm_free(ctx);
+  CommState* s = new CommState();
+  ctx->comm = s;
+  if (!load_nccl(s, ctx->err)) { t2_comm_free(ctx); return T2B200_ERR_STATE; }
+  s->rank = rank; s->nranks = nranks;
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  T2_NCCL(ctx, s, s->CommInitRank(&s->comm, nranks, id, rank));
+  T2_CUDA(ctx, cudaStreamCreateWithFlags(&s->s_comm, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&s->ev_start, &s->ev_done, &s->ev_in[0], &s->ev_in[1], &s->ev_dec[0], &s->ev_dec[1]})
+    T2_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_comm_destroy(t2b200_ctx* ctx)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  t2_comm_free(ctx);
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, const int8_t* llr, int n_cw, uint8_t* bits_out,
+                                          int max_trials, unsigned flags)
+{
+  if (!ctx) return T2B200_ERR_ARG;
+  CommState* s = ctx->comm;
+  if (!s || !s->comm) { ctx->err = "t2b200_ldpc_decode_sharded: call t2b200_comm_init first"; return T2B200_ERR_STATE; }
+  const int N = t2b200_ldpc_n(code), K = t2b200_ldpc_k(code);
+  if (!N || n_cw < 0 || root < 0 || root >= s->nranks || (flags & T2B200_LDPC_WANT_POST) || max_trials <= 0 || max_trials > 60) {
+    ctx->err = "t2b200_ldpc_decode_sharded: bad argument"; return T2B200_ERR_ARG;
+  }
+  const bool is_root = s->rank == root;
+  if (is_root && (!llr || !bits_out || !t2_is_device_ptr(llr) || !t2_is_device_ptr(bits_out))) {
+    ctx->err = "t2b200_ldpc_decode_sharded: the root's llr / bits_out must be device memory"; return T2B200_ERR_ARG;
+  }
+  if (n_cw == 0) return T2B200_OK;
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  int k_out = K;
+  if (flags & T2B200_LDPC_BCH_DESCRAMBLE) {
+    k_out = t2b200_ldpc_k_bch(code);
+    if (!k_out) { ctx->err = "code has no BCH geometry"; return T2B200_ERR_ARG; }
+  }
+  const size_t row = (flags & T2B200_LDPC_PACK_BITS) ? (size_t)k_out / 8 : (size_t)k_out;
+  std::vector<int> lo(s->nranks), hi(s->nranks);
+  int rounds = 0;
+  for (int r = 0; r < s->nranks; ++r) {
+    span_of(n_cw, r, s->nranks, &lo[r], &hi[r]);
+    if (r != root) rounds = std::max(rounds, (hi[r] - lo[r] + kChunk - 1) / kChunk);
+  }
+  auto chunk_n = [&](int r, int t) { return t < 0 ? 0 : std::max(0, std::min(kChunk, hi[r] - lo[r] - t * kChunk)); };
+  int rc;
+  // everything queued on the context's stream so far (the LLRs on the root, earlier users of the buffers) comes first
+  T2_CUDA(ctx, cudaEventRecord(s->ev_start, ctx->stream));
+  T2_CUDA(ctx, cudaStreamWaitEvent(s->s_comm, s->ev_start, 0));
+  if (is_root) {
+    // the root's own shard decodes on the context's stream while the side stream moves the other shards
+    const int mine = hi[root] - lo[root];
+    for (int t = 0; t < rounds + 2; ++t) {
+      bool any = false;
+      for (int r = 0; r < s->nranks && !any; ++r) any = r != root && (chunk_n(r, t) || chunk_n(r, t - 2));
+      if (!any) continue;
+      T2_NCCL(ctx, s, s->GroupStart());
+      for (int r = 0; r < s->nranks; ++r) {
+        if (r == root) continue;
+        if (const int n = chunk_n(r, t))
+          T2_NCCL(ctx, s, s->Send(llr + (size_t)(lo[r] + t * kChunk) * N, (size_t)n * N, ncclInt8, r, s->comm, s->s_comm));
+        if (const int n = chunk_n(r, t - 2))
+          T2_NCCL(ctx, s, s->Recv(bits_out + (size_t)(lo[r] + (t - 2) * kChunk) * row, (size_t)n * row, ncclUint8, r, s->comm, s->s_comm));
+      }
+      T2_NCCL(ctx, s, s->GroupEnd());
+    }
+    if (mine > 0 && (rc = t2_ldpc_device(ctx, code, llr + (size_t)lo[root] * N, mine, bits_out + (size_t)lo[root] * row, nullptr, nullptr,
+                                         max_trials, flags))) return rc;
+  } else {
+    const int r = s->rank;
+    if (s->in_cap < 2 * (size_t)kChunk * N) {
+      T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(s->in_buf); s->in_buf = nullptr; s->in_cap = 0;
+      T2_CUDA(ctx, cudaMalloc(&s->in_buf, 2 * (size_t)kChunk * N));
+      s->in_cap = 2 * (size_t)kChunk * N;
+    }
+    if (s->out_cap < 2 * (size_t)kChunk * row) {
+      T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(s->out_buf); s->out_buf = nullptr; s->out_cap = 0;
+      T2_CUDA(ctx, cudaMalloc(&s->out_buf, 2 * (size_t)kChunk * row));
+      s->out_cap = 2 * (size_t)kChunk * row;
+    }
+    for (int t = 0; t < rounds + 2; ++t) {
+      const int n_in = chunk_n(r, t), n_out = chunk_n(r, t - 2);
+      if (!n_in && !n_out) continue;
+      int8_t* in = s->in_buf + (size_t)(t & 1) * kChunk * N;
+      uint8_t* out = s->out_buf + (size_t)(t & 1) * kChunk * row;
+      // round t re-uses the buffers of round t - 2: its decode must be over (it is what the send below carries anyway)
+      if (t >= 2) T2_CUDA(ctx, cudaStreamWaitEvent(s->s_comm, s->ev_dec[t & 1], 0));
+      T2_NCCL(ctx, s, s->GroupStart());
+      if (n_in) T2_NCCL(ctx, s, s->Recv(in, (size_t)n_in * N, ncclInt8, root, s->comm, s->s_comm));
+      if (n_out) T2_NCCL(ctx, s, s->Send(out, (size_t)n_out * row, ncclUint8, root, s->comm, s->s_comm));
+      T2_NCCL(ctx, s, s->GroupEnd());
+      if (n_in) {
+        T2_CUDA(ctx, cudaEventRecord(s->ev_in[t & 1], s->s_comm));
+        T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_in[t & 1], 0));
+        if ((rc = t2_ldpc_device(ctx, code, in, n_in, out, nullptr, nullptr, max_trials, flags))) return rc;
+        T2_CUDA(ctx, cudaEventRecord(s->ev_dec[t & 1], ctx->stream));
+      }
+    }
+  }
+  // later work on the context's stream sees the gathered bits (root) / may re-use the buffers (others)
+  T2_CUDA(ctx, cudaEventRecord(s->ev_done, s->s_comm));
+  T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_done, 0));
+  return T2B200_OK;
+}
