@@ -76,12 +76,15 @@ const char* t2b200_version(void);
  * ~116, so the outer constellation levels always wrap and the reference's own LDPC stage cannot converge on
  * a clean AWGN signal (DESIGN.md "reference quirks").  1 = clamp to [-128,127] instead -- NOT bit-compatible
  * with the reference, provided so the engine is usable; parity tests run with 0.                         */
-enum { T2B200_OPT_DEMAP_SATURATE = 1, T2B200_OPT_LDPC_PLAIN_LAUNCH = 2 };
+enum { T2B200_OPT_DEMAP_SATURATE = 1, T2B200_OPT_LDPC_PLAIN_LAUNCH = 2, T2B200_OPT_BCH_CORRECT = 3 };
 /* T2B200_OPT_LDPC_PLAIN_LAUNCH (default 0): lock-step (GROUP32) decodes are launched cooperatively, which makes a decode
  * wait until the whole GPU is free.  1 = ordinary launch of the same grid: with TWO contexts on two streams taking turns
  * (bench.py, chain.py) the next decode starts on the SMs the previous one's last groups have left.  Do not run more than
  * two such decodes concurrently on one GPU: partially resident groups of a third could starve the second (the kernel
  * traps after a few seconds rather than hang).  Results are identical either way.                              */
+/* T2B200_OPT_BCH_CORRECT (default 0): the reference never decodes the BCH code ("TODO BCH decode", bch_decoder.cpp:136).
+ * 1 = t2b200_frames_decode corrects up to t bit errors per BBFRAME (t2b200_bch_decode) between the LDPC stage and the
+ * parity strip / descramble -- beyond the reference; off in every parity test.                                          */
 int t2b200_set_option(t2b200_ctx* ctx, int option, int value);
 /* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
 long long t2b200_launch_count(const t2b200_ctx* ctx);
@@ -116,6 +119,13 @@ int t2b200_ldpc_decode(t2b200_ctx* ctx, int code, const int8_t* llr, int n_codew
  * byte-per-bit LDPC output: out[w][i] = in[w][i] ^ prbs[i], i < K_bch.                          */
 int t2b200_bch_descramble(t2b200_ctx* ctx, int code, const uint8_t* bits_in, int n_words,
                           uint8_t* bits_out);
+
+/* N3, opt-in: true BCH decoding, which the reference leaves as a TODO (bch_decoder.cpp:136).  bits_inout:
+ * uint8[n_words][K_ldpc], one byte per bit (what t2b200_ldpc_decode emits without BCH_DESCRAMBLE): the K_ldpc = N_bch bits
+ * of each word are decoded in place -- shortened BCH over GF(2^16) / GF(2^14), t = t2b200_bch_t(code) (EN 302 755 6.1.1).
+ * corrected int32[n_words] or NULL: bit errors corrected (0 .. t), -1 = more than t errors, word left unchanged.         */
+int t2b200_bch_t(int code);
+int t2b200_bch_decode(t2b200_ctx* ctx, int code, uint8_t* bits_inout, int n_words, int32_t* corrected);
 
 /* ---- K3: time / cell de-interleaver + cyclic-Q-delay removal ------------------------------- */
 /* Host-side table builders (no GPU needed):
@@ -265,6 +275,24 @@ int t2b200_frames_decode(t2b200_ctx* ctx, const float* iq, int n_frames, uint8_t
  * (dvbt2_demodulator.cpp:182-186, short_to_float = 2^-14 / 2^-12 / 2^-11 by device).  Half the bytes over PCIe and HBM. */
 int t2b200_frames_decode_i16(t2b200_ctx* ctx, const int16_t* iq, float scale, int n_frames, uint8_t* bits_out,
                              int32_t* trials_left, float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags);
+
+/* ---- multi-GPU: the LDPC / BCH stage sharded by codeword over the GPUs of one box --------------------- */
+/* FEC blocks are independent, so one rank demodulates (it holds the int8 LLRs of a pooled batch), every rank decodes a
+ * contiguous shard of whole 32-codeword groups and the BBFRAME bits return to that rank: ONE exchange each way, NCCL
+ * send / recv over NVLink issued by the library on a side stream, in chunks of <= 1024 codewords double-buffered against
+ * the decode.  One context (= one GPU) per process; NCCL is loaded at run time (libnccl.so.2).
+ *   t2b200_comm_unique_id   rank 0 obtains the rendezvous id (ncclGetUniqueId, 128 bytes) and hands it to the other
+ *                           ranks by any means (the tests use torch.distributed, the reference has no such step)
+ *   t2b200_comm_init        every rank: joins the communicator
+ *   t2b200_ldpc_decode_sharded  collective, every rank calls it with the same code / n_cw / flags / root:
+ *     llr, bits_out  DEVICE memory on `root` (int8[n_cw][N] in, [n_cw][K_bch | K_ldpc] per flags out), ignored elsewhere
+ *     flags          as t2b200_ldpc_decode (GROUP32 | BCH_DESCRAMBLE | PACK_BITS); asynchronous on the context's stream */
+#define T2B200_COMM_ID_BYTES 128
+int t2b200_comm_unique_id(void* id_out, size_t id_bytes);
+int t2b200_comm_init(t2b200_ctx* ctx, int rank, int nranks, const void* unique_id, size_t id_bytes);
+int t2b200_comm_destroy(t2b200_ctx* ctx);
+int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, const int8_t* llr, int n_codewords, uint8_t* bits_out,
+                               int max_trials, unsigned flags);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,8 @@ void t2_eq_free(t2b200_ctx* ctx);
 void t2_ti_free(t2b200_ctx* ctx);
 void t2_ts_free(t2b200_ctx* ctx);
 void t2_frames_free(t2b200_ctx* ctx);
+void t2_comm_free(t2b200_ctx* ctx);
+void t2_bch_free(t2b200_ctx* ctx);
 
 bool t2_is_device_ptr(const void* p)
 {
@@ -135,6 +137,8 @@ void t2b200_destroy(t2b200_ctx* ctx)
   t2_ti_free(ctx);
   t2_ts_free(ctx);
   t2_frames_free(ctx);
+  t2_comm_free(ctx);
+  t2_bch_free(ctx);
   if (ctx->d_prbs) cudaFree(ctx->d_prbs);
   if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
   if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
@@ -169,6 +173,7 @@ int t2b200_set_option(t2b200_ctx* ctx, int option, int value)
   if (!ctx) return T2B200_ERR_ARG;
   if (option == T2B200_OPT_DEMAP_SATURATE) { ctx->opt_demap_saturate = value != 0; return T2B200_OK; }
   if (option == T2B200_OPT_LDPC_PLAIN_LAUNCH) { ctx->opt_ldpc_plain_launch = value != 0; return T2B200_OK; }
+  if (option == T2B200_OPT_BCH_CORRECT) { ctx->opt_bch_correct = value != 0; return T2B200_OK; }
   ctx->err = "t2b200_set_option: unknown option";
   return T2B200_ERR_ARG;
 }
@@ -184,3 +189,5 @@ __attribute__((weak)) void t2_eq_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_ti_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_ts_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_frames_free(t2b200_ctx*) {}
+__attribute__((weak)) void t2_comm_free(t2b200_ctx*) {}
+__attribute__((weak)) void t2_bch_free(t2b200_ctx*) {}

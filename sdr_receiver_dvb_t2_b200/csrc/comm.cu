@@ -158,8 +158,12 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
   T2_CUDA(ctx, cudaEventRecord(s->ev_start, ctx->stream));
   T2_CUDA(ctx, cudaStreamWaitEvent(s->s_comm, s->ev_start, 0));
   if (is_root) {
-    // the root's own shard decodes on the context's stream while the side stream moves the other shards
+    // The root's own shard decodes on the context's stream while the side stream moves the other shards.  The decode is
+    // queued FIRST: its 144 CTAs then hold their SMs and the few CTAs of NCCL's send / recv kernels (which sit waiting for
+    // the peers' results for milliseconds) take the SMs left over, instead of the decoder waiting behind them.
     const int mine = hi[root] - lo[root];
+    if (mine > 0 && (rc = t2_ldpc_device(ctx, code, llr + (size_t)lo[root] * N, mine, bits_out + (size_t)lo[root] * row, nullptr, nullptr,
+                                         max_trials, flags))) return rc;
     for (int t = 0; t < rounds + 2; ++t) {
       bool any = false;
       for (int r = 0; r < s->nranks && !any; ++r) any = r != root && (chunk_n(r, t) || chunk_n(r, t - 2));
@@ -174,8 +178,6 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
       }
       T2_NCCL(ctx, s, s->GroupEnd());
     }
-    if (mine > 0 && (rc = t2_ldpc_device(ctx, code, llr + (size_t)lo[root] * N, mine, bits_out + (size_t)lo[root] * row, nullptr, nullptr,
-                                         max_trials, flags))) return rc;
   } else {
     const int r = s->rank;
     if (s->in_cap < 2 * (size_t)kChunk * N) {

@@ -14,6 +14,8 @@ struct SymbolTables;     // equalizer.cu
 struct TiDemapState;     // demap.cu
 struct TsState;          // ts.cu
 struct FramePipe;        // frames.cu
+struct CommState;        // comm.cu
+struct BchState;         // bch.cu
 
 struct Scratch {
   void* p = nullptr; size_t cap = 0; bool pinned_host = false;
@@ -30,6 +32,7 @@ struct t2b200_ctx {
   long long launches = 0;
   int opt_demap_saturate = 0;                 // T2B200_OPT_DEMAP_SATURATE
   int opt_ldpc_plain_launch = 0;              // T2B200_OPT_LDPC_PLAIN_LAUNCH
+  int opt_bch_correct = 0;                    // T2B200_OPT_BCH_CORRECT
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id
   float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes
@@ -41,6 +44,8 @@ struct t2b200_ctx {
   TiDemapState* ti = nullptr;
   TsState* ts = nullptr;
   FramePipe* frames = nullptr;
+  BchState* bch = nullptr;                    // GF(2^16) / GF(2^14) tables of the opt-in BCH decoder
+  CommState* comm = nullptr;                  // NCCL communicator of the sharded FEC stage (t2b200_comm_init)
   // staging scratch, grown on demand
   Scratch dev[16];
   Scratch pin[8];

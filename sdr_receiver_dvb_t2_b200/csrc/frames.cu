@@ -18,6 +18,7 @@ struct FramePipe {
   TiBlockDesc* d_ti = nullptr; DemapBlockDesc* d_dm = nullptr;
   float2 *d_freq = nullptr, *d_tmp = nullptr, *d_cells = nullptr, *d_tib = nullptr, *d_iq = nullptr;
   int8_t* d_llr = nullptr; float* d_prec = nullptr; uint8_t* d_bits = nullptr; int32_t* d_trials = nullptr;
+  uint8_t* d_kldpc = nullptr;              // LDPC information words of the opt-in BCH correction
   float* d_fb = nullptr;                   // sro | phase, [frames][len_frame] each
   int max_cells = 0, max_fec = 0;
 };
@@ -25,6 +26,7 @@ struct FramePipe {
 static void pipe_free_buffers(FramePipe* p)
 {
   cudaFree(p->d_ti); cudaFree(p->d_dm); cudaFree(p->d_freq); cudaFree(p->d_tmp); cudaFree(p->d_cells); cudaFree(p->d_tib);
+  cudaFree(p->d_kldpc); p->d_kldpc = nullptr;
   cudaFree(p->d_iq); cudaFree(p->d_llr); cudaFree(p->d_prec); cudaFree(p->d_bits); cudaFree(p->d_trials); cudaFree(p->d_fb);
   p->d_ti = nullptr; p->d_dm = nullptr; p->d_freq = p->d_tmp = p->d_cells = p->d_tib = p->d_iq = nullptr;
   p->d_llr = nullptr; p->d_prec = nullptr; p->d_bits = nullptr; p->d_trials = nullptr; p->d_fb = nullptr;
@@ -198,7 +200,15 @@ static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale,
   uint8_t* d_bits = host_bits ? p->d_bits : bits_out;
   const bool host_tr = trials_left && !t2_is_device_ptr(trials_left);
   int32_t* d_tr = trials_left ? (host_tr ? p->d_trials : trials_left) : nullptr;
-  if ((rc = t2_ldpc_device(ctx, p->code, p->d_llr, n_cw, d_bits, d_tr, nullptr, max_trials > 0 ? max_trials : 25, ldpc_flags))) return rc;
+  if (ctx->opt_bch_correct && (ldpc_flags & T2B200_LDPC_BCH_DESCRAMBLE)) {
+    // opt-in N3: LDPC information words (K_ldpc = N_bch bits) -> BCH correction in place -> parity strip + descramble
+    if (ldpc_flags & T2B200_LDPC_PACK_BITS) { ctx->err = "t2b200_frames_decode: BCH correction needs byte-per-bit output"; return T2B200_ERR_ARG; }
+    if (!p->d_kldpc) T2_CUDA(ctx, cudaMalloc(&p->d_kldpc, (size_t)p->frames_cap * c.n_blocks * 54000));
+    if ((rc = t2_ldpc_device(ctx, p->code, p->d_llr, n_cw, p->d_kldpc, d_tr, nullptr, max_trials > 0 ? max_trials : 25,
+                             ldpc_flags & ~(unsigned)T2B200_LDPC_BCH_DESCRAMBLE))) return rc;
+    if ((rc = t2_bch_device(ctx, p->code, p->d_kldpc, t2b200_ldpc_k(p->code), n_cw, nullptr))) return rc;
+    if ((rc = t2_bch_descramble_device(ctx, p->code, p->d_kldpc, n_cw, d_bits))) return rc;
+  } else if ((rc = t2_ldpc_device(ctx, p->code, p->d_llr, n_cw, d_bits, d_tr, nullptr, max_trials > 0 ? max_trials : 25, ldpc_flags))) return rc;
   // results
   bool sync = false;
   auto give = [&](void* dst, const void* src, size_t bytes) -> int {

@@ -754,6 +754,22 @@ __global__ void bch_descramble_kernel(const uint8_t* __restrict__ in, uint8_t* _
   }
 }
 
+// device-level strip + descramble: d_in uint8[n_words][K_ldpc] -> d_out uint8[n_words][K_bch]
+int t2_bch_descramble_device(t2b200_ctx* ctx, int code, const uint8_t* d_in, int n_words, uint8_t* d_out)
+{
+  const int k_ldpc = t2b200_ldpc_k(code), k_bch = t2_ldpc_k_bch(code);
+  if (!k_bch) { ctx->err = "code has no BCH geometry"; return T2B200_ERR_ARG; }
+  int rc;
+  if ((rc = ensure_prbs(ctx))) return rc;
+  if (n_words == 0) return T2B200_OK;
+  size_t total = (size_t)n_words * (k_bch / 4);
+  int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 8);
+  bch_descramble_kernel<<<grid, 256, 0, ctx->stream>>>(d_in, d_out, ctx->d_prbs, n_words, k_ldpc, k_bch);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return T2B200_OK;
+}
+
 extern "C" int t2b200_bch_descramble(t2b200_ctx* ctx, int code, const uint8_t* bits_in, int n_words, uint8_t* bits_out)
 {
   if (!ctx) return T2B200_ERR_ARG;
@@ -762,14 +778,9 @@ extern "C" int t2b200_bch_descramble(t2b200_ctx* ctx, int code, const uint8_t* b
   if (n_words == 0) return T2B200_OK;
   T2_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure_prbs(ctx))) return rc;
   const void* d_in; void* d_out;
   if ((rc = t2_to_device(ctx, 0, bits_in, (size_t)n_words * k_ldpc, &d_in))) return rc;
   if ((rc = t2_out_device(ctx, 1, bits_out, (size_t)n_words * k_bch, &d_out))) return rc;
-  size_t total = (size_t)n_words * (k_bch / 4);
-  int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 8);
-  bch_descramble_kernel<<<grid, 256, 0, ctx->stream>>>((const uint8_t*)d_in, (uint8_t*)d_out, ctx->d_prbs, n_words, k_ldpc, k_bch);
-  T2_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
+  if ((rc = t2_bch_descramble_device(ctx, code, (const uint8_t*)d_in, n_words, (uint8_t*)d_out))) return rc;
   return t2_finish_out(ctx, bits_out, d_out, (size_t)n_words * k_bch);
 }

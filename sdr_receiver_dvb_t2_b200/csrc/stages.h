@@ -21,3 +21,6 @@ int t2_ldpc_device(t2b200_ctx* ctx, int code, const int8_t* d_llr, int n_cw, uin
                    int32_t* d_iters, int max_trials, unsigned flags);
 // geometry the symbol tables of `kind` were configured with (t2b200_eq_configure); false when they are missing
 bool t2_eq_geometry(const t2b200_ctx* ctx, int kind, int* fft_size, int* n_out, int* n_symbols, int* first_symbol);
+// opt-in BCH decoding in place: bits uint8[n_words][row_stride], one byte per bit, the first K_ldpc of a row are the BCH word
+int t2_bch_device(t2b200_ctx* ctx, int code, uint8_t* d_bits, int row_stride, int n_words, int32_t* d_corrected);
+int t2_bch_descramble_device(t2b200_ctx* ctx, int code, const uint8_t* d_in, int n_words, uint8_t* d_out);

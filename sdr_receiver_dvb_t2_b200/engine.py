@@ -20,6 +20,7 @@ MOD_QPSK, MOD_16QAM, MOD_64QAM, MOD_256QAM = range(4)
 FEC_SHORT, FEC_NORMAL = 0, 1
 OPT_DEMAP_SATURATE = 1
 OPT_LDPC_PLAIN_LAUNCH = 2
+OPT_BCH_CORRECT = 3
 
 # every symbol include/t2b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -31,6 +32,8 @@ SYMBOLS = [
     't2b200_demap', 't2b200_eq_configure', 't2b200_equalize', 't2b200_fft',
     't2b200_ts_reset', 't2b200_ts_packetize', 't2b200_frames_configure', 't2b200_frames_decode',
     't2b200_mode_init', 't2b200_pilot_tables', 't2b200_eq_configure_mode', 't2b200_frames_decode_i16',
+    't2b200_comm_unique_id', 't2b200_comm_init', 't2b200_comm_destroy', 't2b200_ldpc_decode_sharded',
+    't2b200_bch_t', 't2b200_bch_decode',
 ]
 
 
@@ -85,6 +88,8 @@ def lib():
     L.t2b200_launch_count.restype = C.c_longlong
     L.t2b200_ldpc_decode.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, u32]
     L.t2b200_bch_descramble.argtypes = [vp, i32, vp, i32, vp]
+    L.t2b200_bch_decode.argtypes = [vp, i32, vp, i32, vp]
+    L.t2b200_bch_t.argtypes = [i32]
     L.t2b200_cell_permutation.argtypes = [i32, i32, vp]
     L.t2b200_demap_address_table.argtypes = [i32, i32, i32, vp]
     L.t2b200_freq_deinterleaver_table.argtypes = [i32, i32, vp, vp]
@@ -99,6 +104,10 @@ def lib():
     L.t2b200_frames_configure.argtypes = [vp, C.POINTER(FrameCfg)]
     L.t2b200_frames_decode.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, u32]
     L.t2b200_frames_decode_i16.argtypes = [vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, i32, u32]
+    L.t2b200_comm_unique_id.argtypes = [vp, C.c_size_t]
+    L.t2b200_comm_init.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.t2b200_comm_destroy.argtypes = [vp]
+    L.t2b200_ldpc_decode_sharded.argtypes = [vp, i32, i32, vp, i32, vp, i32, u32]
     L.t2b200_mode_init.argtypes = [i32] * 6 + [C.POINTER(Mode)]
     L.t2b200_pilot_tables.argtypes = [C.POINTER(Mode), i32, vp, vp]
     L.t2b200_eq_configure_mode.argtypes = [vp, C.POINTER(Mode)]
@@ -208,6 +217,27 @@ class Engine:
         if post is not None:
             r['post'] = post
         return r
+
+    # ---- multi-GPU: the FEC stage sharded by codeword (t2b200_comm_*, t2b200_ldpc_decode_sharded) ----
+    def comm_init(self, rank, nranks, unique_id):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id(), the same on every rank"""
+        buf = (C.c_char * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._chk(self.L.t2b200_comm_init(self.h, rank, nranks, buf, COMM_ID_BYTES))
+
+    def comm_destroy(self):
+        self._chk(self.L.t2b200_comm_destroy(self.h))
+
+    def ldpc_decode_sharded(self, code, root, llr, n_cw, out=None, flags=LDPC_GROUP32 | LDPC_BCH_DESCRAMBLE, max_trials=25):
+        """collective: llr (torch cuda int8[n_cw][N]) and out live on `root`, the other ranks pass None"""
+        self._chk(self.L.t2b200_ldpc_decode_sharded(self.h, code, root, _ptr(llr), n_cw, _ptr(out), max_trials, flags))
+        return out
+
+    def bch_decode(self, code, bits):
+        """opt-in N3: bits uint8[n][K_ldpc] (byte per bit) corrected IN PLACE; returns int32[n] errors corrected (-1: > t)"""
+        n = bits.shape[0]
+        cor = _like(bits, (n,), np.int32)
+        self._chk(self.L.t2b200_bch_decode(self.h, code, _ptr(bits), n, _ptr(cor)))
+        return cor
 
     def bch_descramble(self, code, bits):
         N, K, KB = self.ldpc_geometry(code)
@@ -356,6 +386,18 @@ def mode_tables(m):
         if n:
             t['h_even_' + name], t['h_odd_' + name] = freq_deinterleaver_table(m.fft_size, n)
     return t
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """the NCCL rendezvous id (rank 0 calls this and distributes the bytes)"""
+    buf = (C.c_char * COMM_ID_BYTES)()
+    rc = lib().t2b200_comm_unique_id(buf, COMM_ID_BYTES)
+    if rc != OK:
+        raise T2Error('t2b200_comm_unique_id rc=%d (NCCL not loadable?)' % rc)
+    return bytes(buf)
 
 
 def cell_permutation(n_fec_blocks, cells_per_fec):

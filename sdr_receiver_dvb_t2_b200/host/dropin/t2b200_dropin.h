@@ -36,7 +36,7 @@ inline void check(int rc, const char* what)
 }  // namespace t2b200_dropin
 
 // Qt builds run moc over the stage headers (Q_OBJECT + signals) as they do for the reference's own; a build without moc
-// (the Qt-free shim of oracle/qtshim) defines T2B200_NO_MOC and gets empty bodies for the GUI-only signals.
+// (a Qt-free shim such as the one the parity tests use) defines T2B200_NO_MOC and gets empty bodies for the GUI-only signals.
 #ifdef T2B200_NO_MOC
 #define T2B200_SIGNAL_BODY {}
 #else

@@ -93,9 +93,79 @@ def crc8_bits(bits):
     return crc
 
 
-def make_bbframes(code, n, rng):
+_bch_gen = {}
+
+
+def bch_generator(short_frame, t):
+    """generator polynomial of the DVB-T2 outer code as a Python int (bit i = coefficient of x^i): product of the minimal
+    polynomials of alpha, alpha^3, ..., alpha^(2t-1), alpha a root of the primitive polynomial of EN 302 755 table 6a / 6b"""
+    key = (bool(short_frame), t)
+    if key not in _bch_gen:
+        m = 14 if short_frame else 16
+        prim = (1 << 14 | 1 << 5 | 1 << 3 | 1 << 1 | 1) if short_frame else (1 << 16 | 1 << 5 | 1 << 3 | 1 << 2 | 1)
+        n = (1 << m) - 1
+        ex, lg, x = [0] * (2 * n), [0] * (n + 1), 1
+        for i in range(n):
+            ex[i], lg[x] = x, i
+            x <<= 1
+            if x >> m:
+                x ^= prim
+        for i in range(n, 2 * n):
+            ex[i] = ex[i - n]
+        gen = 1
+        for i in range(1, t + 1):
+            e = (2 * i - 1) % n
+            conj, c = [], e
+            while c not in conj:
+                conj.append(c)
+                c = (c * 2) % n
+            poly = [1]
+            for c in conj:
+                a, new = ex[c], [0] * (len(poly) + 1)
+                for k, pk in enumerate(poly):
+                    new[k + 1] ^= pk
+                    if pk:
+                        new[k] ^= ex[lg[pk] + lg[a]]
+                poly = new
+            mp = sum((pk & 1) << k for k, pk in enumerate(poly))
+            prod, a, sh = 0, gen, 0                          # carry-less multiply gen * mp
+            while mp >> sh:
+                if (mp >> sh) & 1:
+                    prod ^= a << sh
+                sh += 1
+            gen = prod
+        _bch_gen[key] = (gen, m * t)
+    return _bch_gen[key]
+
+
+def bch_parity(bits, short_frame, t):
+    """bits uint8[k] (first bit = highest power) -> parity uint8[m*t]: remainder of x^(m t) * msg(x) modulo g(x), MSB first"""
+    gen, deg = bch_generator(short_frame, t)
+    mask = (1 << deg) - 1
+    table = []
+    for b in range(256):                                        # (b << deg) mod g, one message byte at a time
+        r = b << deg
+        for k in range(deg + 7, deg - 1, -1):
+            if (r >> k) & 1:
+                r ^= gen << (k - deg)
+        table.append(r & mask)
+    pad = (-len(bits)) % 8
+    by = np.packbits(np.concatenate([np.zeros(pad, np.uint8), np.asarray(bits, np.uint8)]))
+    reg = 0
+    for b in by.tolist():
+        reg = ((reg << 8) & mask) ^ table[(reg >> (deg - 8)) ^ b]
+    return np.array([(reg >> (deg - 1 - k)) & 1 for k in range(deg)], np.uint8)
+
+
+def bch_t(code):
+    return 10 if code in (2, 5) else 12
+
+
+def make_bbframes(code, n, rng, bch=False):
     """n BBFRAMEs of K_bch bits, high-efficiency mode, carrying 187-byte packets of random payload.
-    Returns (descrambled bits [n][K_bch] -- what the receiver must output --, scrambled+padded info [n][K_ldpc])."""
+    Returns (descrambled bits [n][K_bch] -- what the receiver must output --, scrambled+padded info [n][K_ldpc]).
+    bch: fill the BCH parity bits [K_bch, K_ldpc) (EN 302 755 6.1.1) instead of leaving them zero (the reference never reads
+    them, bch_decoder.cpp:136)."""
     N, K, _ = ldpc_tables()[code]
     kb = K_BCH[code]
     dfl = ((kb - 80) // 8) * 8
@@ -116,7 +186,10 @@ def make_bbframes(code, n, rng):
         syncd = (syncd - dfl) % (187 * 8)
     scr = frames ^ bb_prbs(kb)[None, :]
     info = np.zeros((n, K), np.uint8)
-    info[:, :kb] = scr                                           # BCH parity bits [K_bch, K_ldpc) left zero
+    info[:, :kb] = scr                                           # BCH parity bits [K_bch, K_ldpc) left zero unless asked for
+    if bch:
+        for i in range(n):
+            info[i, kb:] = bch_parity(scr[i], code >= 6, bch_t(code))
     return frames, info
 
 
@@ -136,9 +209,10 @@ def qam_map(bits, mod):
 class Modulator:
     """One PLP, type-1, in the geometry of a table fixture (tests/golden/tables_*.npz)."""
 
-    def __init__(self, tables, mod, cod, fec_normal, n_blocks, ti_len, rotation=True, l1_post_size=360, seed=1):
+    def __init__(self, tables, mod, cod, fec_normal, n_blocks, ti_len, rotation=True, l1_post_size=360, seed=1, bch=False):
         from sdr_receiver_dvb_t2_b200 import engine as E
         self.t, self.p = tables, tables['p']
+        self.bch = bch
         self.mod, self.cod, self.fec, self.nb, self.ti_len, self.rot = mod, cod, int(fec_normal), n_blocks, ti_len, rotation
         self.code = (0 if fec_normal else 6) + cod
         self.N = 64800 if fec_normal else 16200
@@ -179,7 +253,7 @@ class Modulator:
 
     # ---- one interleaving frame of this PLP: BBFRAMEs -> cells in arrival order ----
     def plp_stream(self):
-        bb, info = make_bbframes(self.code, self.nb, self.rng)
+        bb, info = make_bbframes(self.code, self.nb, self.rng, bch=self.bch)
         cw = ldpc_encode(self.code, info)
         cells = self.fec_cells(cw)
         stream, off = [], 0
