@@ -167,10 +167,10 @@ __device__ __forceinline__ int syndrome_bad(const uint16_t* __restrict__ post, u
 
 // Register budget: one CTA per SM for the 64 800-bit codes (MINB = 1: 128 registers, so that a quarter of the register file
 // stays free), two CTAs per SM for the 16 200-bit codes (MINB = 2: 80 registers).
-template <int MINB> constexpr int kLdpcRegs = MINB == 1 ? 128 : 80;
+template <int CNL, int MINB> constexpr int kLdpcRegs = MINB == 2 ? 80 : CNL >= 16 ? 160 : 128;   // (16+ slots need more than 128)
 
 template <int CNL, int MINB>
-__global__ void __launch_bounds__(kThreads) __maxnreg__(kLdpcRegs<MINB>) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
+__global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
 {
   using LY = CnLayout<CNL>;
   constexpr int NS = LY::NS;
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kLdpcRegs<MINB>) ldpc_de
   const int plane_words = (((p.N + 31) >> 5) + 3) & ~1;
   uint32_t* hbA = reinterpret_cast<uint32_t*>(smem + ((2 * p.N + 15) & ~15));
   uint32_t* hbB = hbA + plane_words;
+  uint32_t* walk = hbB + plane_words;                                       // [360][kWalkWords]: parked check-node state of the chain walk
   const int R = p.N - p.K;
   // Check-node words are private to the thread that owns check node (i, tid): they live in an L2-resident global scratch
   // (ld/st.cg, next layer's words prefetched a layer ahead).  2 x NS planes of R words per resident CTA.
@@ -355,27 +356,71 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kLdpcRegs<MINB>) ldpc_de
             cn.template load<PREDICATED>(eb, es, cnt, ~sh, i, tid, p.K, p.q);
           }
           if (__popc(sh) == 2) {
-            // one pair of shared edges (the common case): addresses and stored messages are prepared
-            // up front so that a level is just load -> min/sign merge -> store on two posteriors
+            // One pair of slots (cA, cB) reads the same bit-group (the common case).  Bit (j + es[cA]) mod 360 of check node j
+            // is bit (j' + es[cB]) mod 360 of check node j' = j + D, D = es[cA] - es[cB] (mod 360): the check nodes form runs
+            // j0, j0 + step, j0 + 2 step, ... (j0 < step = min(D, 360 - D)) in which each one hands ONE updated posterior
+            // to the next, and the last one of a run also shares a bit with the first one of another run.  Instead of one
+            // barrier per level of these dependency chains, the thread of a run's first check node WALKS its run: first
+            // every run head is done (they depend on nothing), then -- one barrier later -- each walker goes down its run with
+            // the handed-over posterior in a register; the other check nodes' private state is parked in shared memory.
             const int cA = __ffs(sh) - 1, cB = 31 - __clz(sh);
-            int aA = 0, aB = 0;
-            uint32_t sA = 0, sB = 0;
-            if (tid < 360) {
-              aA = mod360(tid + (int)es[cA]) + (int)eb[cA]; aB = mod360(tid + (int)es[cB]) + (int)eb[cB];
-              sA = cn.stored_neg_rt(cA); sB = cn.stored_neg_rt(cB);
+            int D = (int)es[cA] - (int)es[cB];
+            D += D < 0 ? 360 : 0;
+            const bool fwd = D <= 180;
+            const int step = fwd ? D : 360 - D;
+            const int slotO = fwd ? cA : cB, slotI = fwd ? cB : cA;             // towards the successor / from the predecessor
+            const int esO = (int)es[slotO], ebO = (int)eb[slotO], esI = (int)es[slotI], ebI = (int)eb[slotI];
+            const bool owner = tid < 360, head = tid < step, sink = tid + step >= 360;
+            uint32_t nI = 0, nO = 0, vI = 0, vO = 0, carry = 0;
+            post_ref rI = cn.post_ref_at(0), rO = rI;
+            if (owner) {
+              nI = cn.stored_neg_rt(slotI); nO = cn.stored_neg_rt(slotO);
+              rI = cn.post_ref_at(mod360(tid + esI) + ebI); rO = cn.post_ref_at(mod360(tid + esO) + ebO);
             }
-            for (int l = 1; l <= nl; ++l) {
-              if (mylev == l) {
-                const uint32_t vA = cn.shared_in(cA, aA, sA);
-                const uint32_t vB = cn.shared_in(cB, aB, sB);
-                uint32_t m0, m1, idn;
-                cn.minima(m0, m1, idn);
-                uint32_t r = cn.shared_out(cA, aA, vA, m0, m1, idn);
-                negA |= (r & 1u) << cA; negB |= (r >> 16) << cA;
-                r = cn.shared_out(cB, aB, vB, m0, m1, idn);
-                negA |= (r & 1u) << cB; negB |= (r >> 16) << cB;
+            if (head) {                                                          // run heads depend on nothing: whole check node now
+              vI = sat8_add(unpack_post(post_ld(rI)), nI);
+              vO = sat8_add(unpack_post(post_ld(rO)), nO);
+              cn.take(vI, slotI); cn.take(vO, slotO);
+              uint32_t m0, m1, idn, gI, gO;
+              cn.minima(m0, m1, idn);
+              const CnCore c = cn.core();
+              post_st(rI, pack_post(core_out(c, slotI, vI, m0, m1, idn, gI)));
+              carry = core_out(c, slotO, vO, m0, m1, idn, gO);
+              post_st(rO, pack_post(carry));
+              negA = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
+              negB = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
+            }
+            __syncthreads();
+            if (owner && !head) {                                                // what the walker needs from the others
+              vO = sat8_add(unpack_post(post_ld(rO)), nO);                       // (a run's last check node reads the bit a head just wrote)
+              uint32_t* st = walk + tid * kWalkWords;
+              const CnCore c = cn.core();
+              st[0] = (c.key0 >> 5) & 0x07ff07ffu; st[1] = c.sx; st[2] = vO; st[3] = nI;
+            }
+            __syncthreads();
+            if (head) {                                                          // the serial part: one posterior handed down the run
+              int j = tid + step;
+              uint4 w = *reinterpret_cast<const uint4*>(walk + (j < 360 ? j : tid) * kWalkWords);
+              while (j < 360) {                                                  // (the next check node's words are fetched a step ahead)
+                const int jn = j + step;
+                const uint4 wn = *reinterpret_cast<const uint4*>(walk + (jn < 360 ? jn : tid) * kWalkWords);
+                walk[j * kWalkWords] = carry;                                    // the posterior check node j starts from
+                carry = walk_carry(carry, w.x, w.y, w.z, w.w);
+                w = wn; j = jn;
               }
-              __syncthreads();
+            }
+            __syncthreads();
+            if (owner && !head) {                                                // ... and everybody finishes its own check node
+              vI = sat8_add(walk[tid * kWalkWords], nI);
+              cn.take(vI, slotI); cn.take(vO, slotO);
+              uint32_t m0, m1, idn, gI, gO;
+              cn.minima(m0, m1, idn);
+              const CnCore c = cn.core();
+              post_st(rI, pack_post(core_out(c, slotI, vI, m0, m1, idn, gI)));
+              const uint32_t pO = core_out(c, slotO, vO, m0, m1, idn, gO);
+              if (sink) post_st(rO, pack_post(pO));                              // elsewhere the successor writes this bit's final value
+              negA = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
+              negB = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
             }
           } else {
             for (int l = 1; l <= nl; ++l) {
@@ -492,9 +537,9 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
     const int slots = d->cnl + 2, nw = (slots + 7) / 8, tail = slots - 8 * (nw - 1);
     d->state_bytes = 2 * 4 * (size_t)(nw + (tail <= 5 ? 0 : 1));   // 2 codewords x CnLayout<CNL>::NS words per check node
   }
-  // shared memory: interleaved posteriors of the pair | two packed sign planes (+ padding words, rounded); check-node
-  // words are in global scratch
-  d->smem = (size_t)((2 * s.N + 15) & ~15) + 2 * (size_t)((((s.N + 31) >> 5) + 3) & ~1) * 4;
+  // shared memory: interleaved posteriors of the pair | two packed sign planes (+ padding words, rounded) | the parking
+  // area of the chain walk; check-node words are in global scratch
+  d->smem = (size_t)((2 * s.N + 15) & ~15) + 2 * (size_t)((((s.N + 31) >> 5) + 3) & ~1) * 4 + 360 * kWalkWords * 4;
   d->minb = (s.N > 16200 || d->cnl >= 17) ? 1 : 2;          // (the 17-slot check node of short r5/6 does not fit 80 registers)
   LdpcParams& p = d->proto;
   memset(&p, 0, sizeof(p));

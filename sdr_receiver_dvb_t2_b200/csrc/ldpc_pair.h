@@ -40,6 +40,7 @@ T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel)
 }
 T2_HD int mod360(int t) { return (int)__viaddmin_u32((unsigned)t, 0xfffffe98u, (unsigned)t); }    // t in [0, 720): t mod 360
 T2_HD uint32_t rotl(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+T2_HD uint32_t vneg2(uint32_t a) { return __vneg2(a); }                                               // per-half negation
 // the pair's posteriors by 32-bit shared-memory address (kept in a register from the load to the store of an edge)
 typedef uint32_t post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return (uint32_t)__cvta_generic_to_shared(post); }
@@ -78,6 +79,7 @@ template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b) { return prm
 T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel) { return prmt_any(a, b, sel); }
 T2_HD int mod360(int t) { return t >= 360 ? t - 360 : t; }
 T2_HD uint32_t rotl(uint32_t x, int r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
+T2_HD uint32_t vneg2(uint32_t a) { return pk16(-(int)lo16(a), -(int)hi16(a)); }
 typedef uint16_t* post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return post; }
 T2_HD post_ref post_at(post_ref base, int a) { return base + a; }
@@ -114,6 +116,54 @@ template <int CNL> struct CnLayout {
 };
 
 enum SlotMode { ALL_SLOTS, PREDICATED, BRANCHED };
+
+constexpr int kWalkWords = 4;         // words parked per check node by the chain walk (walk_carry's arguments; word 0 returns its carry-in)
+
+// The running state of one check node of the pair -- the two smallest keys and the xor of the inputs seen so far -- as a
+// value that can be handed from thread to thread (the chain walk of ldpc.cu parks it in shared memory).
+struct CnCore { uint32_t key0, key1, sx; };
+T2_HD void core_take(CnCore& c, uint32_t v, int slot)
+{
+  const uint32_t key = abs2(v) * 32u + (uint32_t)slot * kOne2;
+  c.key1 = vmin2(c.key1, vmax2(c.key0, key));
+  c.key0 = vmin2(c.key0, key);
+  c.sx ^= v;
+}
+T2_HD void core_minima(const CnCore& c, uint32_t& m0, uint32_t& m1, uint32_t& idn)
+{
+  const uint32_t c126 = 0x007e007eu, mone = 0xffffffffu;
+  m0 = vmin2(vaddmax((c.key0 >> 5) & 0x07ff07ffu, mone, 0u), c126);
+  m1 = vmin2(vaddmax((c.key1 >> 5) & 0x07ff07ffu, mone, 0u), c126);
+  idn = c.key0 & 0x001f001fu;
+}
+// new posterior pair of an edge whose input was v (vqadd of v and the check node's message); neg: bit 0 / 16 set when the
+// message is negative in codeword A / B
+T2_HD uint32_t core_out(const CnCore& c, int slot, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn, uint32_t& neg)
+{
+  const uint32_t t = c.sx ^ v;
+  const int negA = (t >> 15) & 1u, negB = t >> 31;
+  int ma = (int)((slot == (int)(idn & 0xffffu) ? m1 : m0) & 0xffffu);
+  int mb = (int)((slot == (int)(idn >> 16) ? m1 : m0) >> 16);
+  if (negA) ma = -ma;
+  if (negB) mb = -mb;
+  neg = (uint32_t)negA | ((uint32_t)negB << 16);
+  return sat8_add(v, ((uint32_t)ma & 0xffffu) | ((uint32_t)mb << 16));
+}
+
+// The serial core of the chain walk (ldpc.cu): a check node shares one bit with its predecessor in the layer's serial order
+// (slot I: its updated posterior pair arrives in `carry`) and one with its successor (slot O).  All the successor needs is
+// the new posterior of the O bit: vqadd(vO, message) with |message| = the smallest magnitude among the OTHER inputs (the
+// private edges, whose minimum a0mag = (key0 >> 5) is known beforehand, and the I input) after the offset, and sign = product
+// of the other inputs' signs (sxp: xor of the private inputs).  ~14 dependent instructions per check node; everything else
+// of the check node is done afterwards, in parallel, by its own thread.
+T2_HD uint32_t walk_carry(uint32_t carry, uint32_t a0mag, uint32_t sxp, uint32_t vO, uint32_t nI)
+{
+  const uint32_t vI = sat8_add(carry, nI);
+  const uint32_t mag = vmin2(a0mag, abs2(vI));
+  const uint32_t m = vmin2(vaddmax(mag, 0xffffffffu, 0u), 0x007e007eu);
+  const uint32_t smask = (((sxp ^ vI) >> 15) & kOne2) * 0xffffu;
+  return sat8_add(vO, (m & ~smask) | (vneg2(m) & smask));
+}
 
 // One check node of BOTH codewords of the pair, split so that the edges private to the check node and the edges it shares
 // with another check node of the same layer can be read / written at different times.
@@ -302,16 +352,15 @@ struct CheckNodePair {
   }
   T2_HD uint32_t shared_out_at(int slot, post_ref where, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn)
   {
-    const uint32_t t = sx ^ v;
-    const int negA = (t >> 15) & 1u, negB = t >> 31;
-    int ma = (int)((slot == (int)(idn & 0xffffu) ? m1 : m0) & 0xffffu);
-    int mb = (int)((slot == (int)(idn >> 16) ? m1 : m0) >> 16);
-    if (negA) ma = -ma;
-    if (negB) mb = -mb;
-    const uint32_t o = ((uint32_t)ma & 0xffffu) | ((uint32_t)mb << 16);
-    post_st(where, pack_post(sat8_add(v, o)));
-    return (uint32_t)negA | ((uint32_t)negB << 16);
+    uint32_t neg;
+    const CnCore c = {key0, key1, sx};
+    post_st(where, pack_post(core_out(c, slot, v, m0, m1, idn, neg)));
+    return neg;
   }
+  // the running state as a value / taken back (chain walk)
+  T2_HD CnCore core() const { return CnCore{key0, key1, sx}; }
+  T2_HD void set_core(const CnCore& c) { key0 = c.key0; key1 = c.key1; sx = c.sx; }
+  T2_HD post_ref post_ref_at(int a) const { return post_at(post, a); }
   template <int C> T2_HD void shared_load_generic(const uint16_t* eb, const uint16_t* es, uint32_t mask, int j)
   {
     if constexpr (C < CNL) {

@@ -103,30 +103,57 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
           cn[tid].template load<PREDICATED>(peb, pes, cnt, ~sh, i, tid, s.K, s.q);
         }
         if (__builtin_popcount(sh) == 2) {
+          // the chain walk of ldpc_decode_kernel, phase by phase (barriers between the loops)
           const int cA = __builtin_ffs(sh) - 1, cB = 31 - __builtin_clz(sh);
-          for (int l = 1; l <= nl; ++l) {
-            // threads of one level: all reads, then all writes (they do not share bits with each other)
-            struct Tmp { uint32_t vA, vB, m0, m1, idn; int aA, aB; };
-            std::vector<Tmp> tmp(360);
-            for (int tid = 0; tid < 360; ++tid)
-              if (level[tid] == l) {
-                int tA = tid + pes[cA], tB = tid + pes[cB];
-                if (tA >= 360) tA -= 360;
-                if (tB >= 360) tB -= 360;
-                Tmp& t = tmp[tid];
-                t.aA = tA + peb[cA]; t.aB = tB + peb[cB];
-                t.vA = cn[tid].shared_in(cA, t.aA, cn[tid].stored_neg_rt(cA));
-                t.vB = cn[tid].shared_in(cB, t.aB, cn[tid].stored_neg_rt(cB));
-                cn[tid].minima(t.m0, t.m1, t.idn);
-              }
-            for (int tid = 0; tid < 360; ++tid)
-              if (level[tid] == l) {
-                Tmp& t = tmp[tid];
-                uint32_t r = cn[tid].shared_out(cA, t.aA, t.vA, t.m0, t.m1, t.idn);
-                negA[tid] |= (r & 1u) << cA; negB[tid] |= (r >> 16) << cA;
-                r = cn[tid].shared_out(cB, t.aB, t.vB, t.m0, t.m1, t.idn);
-                negA[tid] |= (r & 1u) << cB; negB[tid] |= (r >> 16) << cB;
-              }
+          int D = (int)pes[cA] - (int)pes[cB];
+          D += D < 0 ? 360 : 0;
+          const bool fwd = D <= 180;
+          const int step = fwd ? D : 360 - D;
+          const int slotO = fwd ? cA : cB, slotI = fwd ? cB : cA;
+          const int esO = pes[slotO], ebO = peb[slotO], esI = pes[slotI], ebI = peb[slotI];
+          std::vector<uint32_t> walk(360 * kWalkWords, 0), nI(360), nO(360), vI(360), vO(360), carry(360, 0);
+          std::vector<post_ref> rI(360), rO(360);
+          for (int tid = 0; tid < 360; ++tid) {
+            nI[tid] = cn[tid].stored_neg_rt(slotI); nO[tid] = cn[tid].stored_neg_rt(slotO);
+            rI[tid] = cn[tid].post_ref_at(mod360(tid + esI) + ebI); rO[tid] = cn[tid].post_ref_at(mod360(tid + esO) + ebO);
+          }
+          for (int tid = 0; tid < step; ++tid) {                                 // heads
+            vI[tid] = sat8_add(unpack_post(post_ld(rI[tid])), nI[tid]);
+            vO[tid] = sat8_add(unpack_post(post_ld(rO[tid])), nO[tid]);
+            cn[tid].take(vI[tid], slotI); cn[tid].take(vO[tid], slotO);
+            uint32_t m0, m1, idn, gI, gO;
+            cn[tid].minima(m0, m1, idn);
+            const CnCore c = cn[tid].core();
+            post_st(rI[tid], pack_post(core_out(c, slotI, vI[tid], m0, m1, idn, gI)));
+            carry[tid] = core_out(c, slotO, vO[tid], m0, m1, idn, gO);
+            post_st(rO[tid], pack_post(carry[tid]));
+            negA[tid] = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
+            negB[tid] = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
+          }
+          for (int tid = step; tid < 360; ++tid) {                               // barrier; the others park what the walker needs
+            vO[tid] = sat8_add(unpack_post(post_ld(rO[tid])), nO[tid]);
+            uint32_t* st = walk.data() + tid * kWalkWords;
+            const CnCore c = cn[tid].core();
+            st[0] = (c.key0 >> 5) & 0x07ff07ffu; st[1] = c.sx; st[2] = vO[tid]; st[3] = nI[tid];
+          }
+          for (int tid = 0; tid < step; ++tid)                                   // barrier; the walk
+            for (int j = tid + step; j < 360; j += step) {
+              uint32_t* st = walk.data() + j * kWalkWords;
+              const uint32_t w0 = st[0], w1 = st[1], w2 = st[2], w3 = st[3];
+              st[0] = carry[tid];
+              carry[tid] = walk_carry(carry[tid], w0, w1, w2, w3);
+            }
+          for (int tid = step; tid < 360; ++tid) {                               // barrier; everybody finishes its own check node
+            vI[tid] = sat8_add(walk[tid * kWalkWords], nI[tid]);
+            cn[tid].take(vI[tid], slotI); cn[tid].take(vO[tid], slotO);
+            uint32_t m0, m1, idn, gI, gO;
+            cn[tid].minima(m0, m1, idn);
+            const CnCore c = cn[tid].core();
+            post_st(rI[tid], pack_post(core_out(c, slotI, vI[tid], m0, m1, idn, gI)));
+            const uint32_t pO = core_out(c, slotO, vO[tid], m0, m1, idn, gO);
+            if (tid + step >= 360) post_st(rO[tid], pack_post(pO));
+            negA[tid] = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
+            negB[tid] = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
           }
         } else {
           for (int l = 1; l <= nl; ++l) {
