@@ -16,19 +16,19 @@
 // B200 design (DESIGN.md "K5"):
 //   * two codewords per thread: one LDS.U16 / STS.U16, one address computation and one VIADDMNMX.S16x2 / VIMNMX.S16x2
 //     serve both -- about a third of the instructions per edge of a one-codeword-per-thread decoder.
-//   * posteriors 2 x int8[N] (<= 129.6 KB) stay in shared memory for the whole decode; the min-sum messages of a check
-//     node are fully determined by (two clamped minima, arg-min slot, output signs) and are kept as 8-16 bytes per check
-//     node and codeword in a global scratch that only the owning thread touches (L2-resident, prefetched a layer ahead)
-//     -> HBM traffic = the compulsory N bytes in, K out.
+//   * posteriors 2 x int8[N] (<= 129.6 KB) stay in shared memory for the whole decode; the stored messages (one byte per
+//     edge and codeword, already negated and clamped: ldpc_pair.h) live in a global scratch that only the owning thread
+//     touches (L2-resident, prefetched a layer ahead) -> HBM traffic = the compulsory N bytes in, K out.
 //   * one CTA of 384 threads per SM for 64 800-bit codes (<= 128 registers), two for 16 200-bit codes: a quarter of the
 //     register file, ~80 KB of shared memory and 1 280 threads of every SM stay free for the streaming kernels of
 //     another stream.
 //   * the quasi-cyclic structure makes every edge of a layer a contiguous (rotated) run of 360 posteriors: thread j of
 //     the CTA owns check node (i, j), so all shared-memory traffic is conflict-free and contiguous across a warp; no
 //     position table is read, addresses come from q * CNL (base, shift) pairs in the kernel-parameter constant bank.
-//   * the reference's serial j order matters only where two check nodes of one layer share a bit; the host precomputes
-//     the dependency depth of every check node in such layers and the CTA runs them level by level
-//     (ldpc_schedule.cpp), everything else is one parallel step per layer.
+//   * the reference's serial j order matters only where two check nodes of one layer share a bit; such edges are the
+//     first slots of their layer (ldpc_schedule.cpp).  A layer with one shared pair is resolved by walking its dependency
+//     runs in registers, the others level by level along the precomputed dependency depth; everything else is one
+//     parallel step per layer.
 //   * lock-step groups of 32 (reference batch semantics) are 16 co-resident CTAs that exchange their parity verdict
 //     through one global word per iteration; groups are claimed from an atomic queue.
 #include "stages.h"
@@ -53,16 +53,16 @@ struct LdpcParams {
   const int8_t* llr; uint8_t* bits; int32_t* trials_left; int32_t* iters; int8_t* post_out;
   const uint8_t* level; const uint8_t* prbs; unsigned* gsync;
   unsigned* gqueue;                   // [0] next unclaimed group; [1 + slot * (n_groups + 1) + round] group (+1) claimed by a slot's lane 0
-  uint32_t* cn_state;                 // [grid][2][NS][R] packed check-node words (L2-resident scratch, thread-private)
+  uint32_t* cn_state;                 // [grid][q][NSW][360] stored messages (L2-resident scratch, thread-private)
   unsigned* err_flag;                 // set when a lock-step wait timed out (the host turns it into T2B200_ERR_CUDA)
   int n_cw, group_lanes, max_trials; unsigned flags;
   int N, K, q, k_out;
   // CN (i,j) data edge c reads posterior eb + (j + es) mod 360
   uint16_t eb[kMaxEdgeWords];         // [q][CNL]: 360 * bit-group
   uint16_t es[kMaxEdgeWords];         // [q][CNL]: cyclic shift
-  uint32_t shared[kMaxLayers];        // per layer: data-edge slots whose bit another CN of the layer also uses
   int16_t cidx[kMaxLayers];           // row of level[] for layers with shared bits
   uint8_t cnt[kMaxLayers], nlev[kMaxLayers];
+  uint8_t ns[kMaxLayers];             // per layer: slots 0 .. ns-1 read a bit another check node of the layer also uses
 };
 static_assert(sizeof(LdpcParams) <= 4000, "kernel parameter block");
 
@@ -173,17 +173,16 @@ template <int CNL, int MINB>
 __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __grid_constant__ LdpcParams p)
 {
   using LY = CnLayout<CNL>;
-  constexpr int NS = LY::NS;
+  constexpr int NSW = LY::NSW;
   extern __shared__ __align__(16) unsigned char smem[];
   uint16_t* post = reinterpret_cast<uint16_t*>(smem);                       // [N]: low byte codeword A, high byte codeword B
   const int plane_words = (((p.N + 31) >> 5) + 3) & ~1;
   uint32_t* hbA = reinterpret_cast<uint32_t*>(smem + ((2 * p.N + 15) & ~15));
   uint32_t* hbB = hbA + plane_words;
   uint32_t* walk = hbB + plane_words;                                       // [360][kWalkWords]: parked check-node state of the chain walk
-  const int R = p.N - p.K;
-  // Check-node words are private to the thread that owns check node (i, tid): they live in an L2-resident global scratch
-  // (ld/st.cg, next layer's words prefetched a layer ahead).  2 x NS planes of R words per resident CTA.
-  uint32_t* state = p.cn_state + (size_t)blockIdx.x * 2 * NS * R;
+  // Stored messages are private to the thread that owns check node (i, tid): they live in an L2-resident global scratch
+  // (ld/st.cg, next layer's words prefetched a layer ahead), [layer][word][360] per resident CTA.
+  uint32_t* const state = p.cn_state + (size_t)blockIdx.x * (size_t)(p.q * NSW * 360) + threadIdx.x;
   __shared__ int s_flag, s_group;
 
   const int tid = threadIdx.x;
@@ -303,23 +302,19 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
       }
       if (!(go && --trials >= 0)) break;
       // ---- one update() ----
-      const bool stored = iters > 0 && tid < 360;                // first pass: all messages are zero, nothing to read
-      uint32_t nA[NS], nB[NS];
+      const bool owner = tid < 360;
+      const bool stored = iters > 0 && owner;                    // first pass: all messages are zero, nothing to read
+      uint32_t nw[NSW];
 #pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        nA[k] = stored ? __ldcg(state + k * R + tid) : 0u;
-        nB[k] = stored ? __ldcg(state + (NS + k) * R + tid) : 0u;
-      }
+      for (int k = 0; k < NSW; ++k) nw[k] = stored ? __ldcg(state + k * 360) : 0u;
       for (int i = 0; i < p.q; ++i) {
-        uint32_t wA[NS], wB[NS];
+        uint32_t* const sp = state + (size_t)i * (NSW * 360);
+        uint32_t w[NSW];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) { wA[k] = nA[k]; wB[k] = nB[k]; }
+        for (int k = 0; k < NSW; ++k) w[k] = nw[k];
         if (stored && i + 1 < p.q) {
 #pragma unroll
-          for (int k = 0; k < NS; ++k) {
-            nA[k] = __ldcg(state + k * R + (i + 1) * 360 + tid);
-            nB[k] = __ldcg(state + (NS + k) * R + (i + 1) * 360 + tid);
-          }
+          for (int k = 0; k < NSW; ++k) nw[k] = __ldcg(sp + (NSW + k) * 360);
         }
         const int cnt = p.cnt[i];
         const int nl = p.nlev[i];
@@ -327,119 +322,95 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
         const uint16_t* es = p.es + i * CNL;
         CheckNodePair<CNL> cn;
         if (nl == 1) {
-          if (tid < 360) {
-            cn.begin(post, wA, wB);
-            if (cnt == CNL) {
-              cn.template load<ALL_SLOTS>(eb, es, cnt, ~0u, i, tid, p.K, p.q);
-              cn.template store<ALL_SLOTS>(cnt, ~0u, i, tid, 0u, 0u, wA, wB);
-            } else {
-              cn.template load<PREDICATED>(eb, es, cnt, ~0u, i, tid, p.K, p.q);
-              cn.template store<PREDICATED>(cnt, ~0u, i, tid, 0u, 0u, wA, wB);
-            }
+          if (owner) {
+            cn.begin(post, w);
+            cn.load(eb, es, 0, cnt, i, tid, p.K, p.q, cnt == CNL);
+            cn.store(0, cnt, i, tid, cnt == CNL, w);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) {
-              __stcg(state + k * R + i * 360 + tid, wA[k]);
-              __stcg(state + (NS + k) * R + i * 360 + tid, wB[k]);
-            }
+            for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
           }
           __syncthreads();
         } else {
           // Two check nodes of this layer use the same bit: the reference runs j = 0..359 serially, so
           // the smaller j must finish that bit first.  Private edges go in parallel (before / after),
-          // shared edges are resolved level by level along the dependency chains.
-          const uint32_t sh = p.shared[i];
-          int mylev = 0;
-          uint32_t negA = 0, negB = 0;
-          if (tid < 360) {
-            mylev = __ldg(p.level + (int)p.cidx[i] * 360 + tid);
-            cn.begin(post, wA, wB);
-            cn.template load<PREDICATED>(eb, es, cnt, ~sh, i, tid, p.K, p.q);
+          // shared edges are resolved along the dependency chains.
+          const int ns = p.ns[i];
+          if (owner) {
+            cn.begin(post, w);
+            cn.load(eb, es, ns, cnt, i, tid, p.K, p.q, false);
           }
-          if (__popc(sh) == 2) {
-            // One pair of slots (cA, cB) reads the same bit-group (the common case).  Bit (j + es[cA]) mod 360 of check node j
-            // is bit (j' + es[cB]) mod 360 of check node j' = j + D, D = es[cA] - es[cB] (mod 360): the check nodes form runs
-            // j0, j0 + step, j0 + 2 step, ... (j0 < step = min(D, 360 - D)) in which each one hands ONE updated posterior
-            // to the next, and the last one of a run also shares a bit with the first one of another run.  Instead of one
-            // barrier per level of these dependency chains, the thread of a run's first check node WALKS its run: first
-            // every run head is done (they depend on nothing), then -- one barrier later -- each walker goes down its run with
-            // the handed-over posterior in a register; the other check nodes' private state is parked in shared memory.
-            const int cA = __ffs(sh) - 1, cB = 31 - __clz(sh);
-            int D = (int)es[cA] - (int)es[cB];
-            D += D < 0 ? 360 : 0;
-            const bool fwd = D <= 180;
-            const int step = fwd ? D : 360 - D;
-            const int slotO = fwd ? cA : cB, slotI = fwd ? cB : cA;             // towards the successor / from the predecessor
-            const int esO = (int)es[slotO], ebO = (int)eb[slotO], esI = (int)es[slotI], ebI = (int)eb[slotI];
-            const bool owner = tid < 360, head = tid < step, sink = tid + step >= 360;
-            uint32_t nI = 0, nO = 0, vI = 0, vO = 0, carry = 0;
-            post_ref rI = cn.post_ref_at(0), rO = rI;
+          if (ns == 2) {
+            // One pair of slots reads the same bit-group (the common case): slot 1 of check node j is slot 0 of check node
+            // j + step, so the check nodes form runs j0, j0 + step, j0 + 2 step, ... (j0 < step) in which each one hands ONE
+            // updated posterior to the next, and the last one of a run also shares a bit with the first one of another run.
+            // Instead of one barrier per level of these dependency chains, the thread of a run's first check node WALKS its
+            // run: first every run head is done (they depend on nothing), then -- one barrier later -- each walker goes down
+            // its run with the handed-over posterior in a register; what it needs from the other check nodes is parked in
+            // shared memory.
+            const int step = mod360((int)es[1] + 360 - (int)es[0]);
+            const bool head = tid < step, sink = tid + step >= 360;
+            uint32_t nI = 0, vO = 0, carry = 0;
+            post_ref rI = 0, rO = 0;
             if (owner) {
-              nI = cn.stored_neg_rt(slotI); nO = cn.stored_neg_rt(slotO);
-              rI = cn.post_ref_at(mod360(tid + esI) + ebI); rO = cn.post_ref_at(mod360(tid + esO) + ebO);
+              nI = cn.template stored_neg<0>();
+              rI = cn.template slot_ref<0>(eb, es, tid); rO = cn.template slot_ref<1>(eb, es, tid);
             }
-            if (head) {                                                          // run heads depend on nothing: whole check node now
-              vI = sat8_add(unpack_post(post_ld(rI)), nI);
-              vO = sat8_add(unpack_post(post_ld(rO)), nO);
-              cn.take(vI, slotI); cn.take(vO, slotO);
-              uint32_t m0, m1, idn, gI, gO;
-              cn.minima(m0, m1, idn);
-              const CnCore c = cn.core();
-              post_st(rI, pack_post(core_out(c, slotI, vI, m0, m1, idn, gI)));
-              carry = core_out(c, slotO, vO, m0, m1, idn, gO);
-              post_st(rO, pack_post(carry));
-              negA = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
-              negB = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
+            if (head) {                                                          // run heads depend on nothing: both shared edges now
+              cn.template edge_in_value<0>(sat8_add(unpack_post(post_ld(rI)), nI));
+              cn.template edge_in_value<1>(sat8_add(unpack_post(post_ld(rO)), cn.template stored_neg<1>()));
+              const CnOut o = cn.minima();
+              cn.template edge_out<0>(o, true, true);
+              carry = cn.template edge_out<1>(o, true, true);
             }
             __syncthreads();
             if (owner && !head) {                                                // what the walker needs from the others
-              vO = sat8_add(unpack_post(post_ld(rO)), nO);                       // (a run's last check node reads the bit a head just wrote)
-              uint32_t* st = walk + tid * kWalkWords;
-              const CnCore c = cn.core();
-              st[0] = (c.key0 >> 5) & 0x07ff07ffu; st[1] = c.sx; st[2] = vO; st[3] = nI;
+              vO = sat8_add(unpack_post(post_ld(rO)), cn.template stored_neg<1>());   // (a run's last check node reads the bit a head just wrote)
+              const CnOut o = cn.minima();                                       // of the private edges only: o.A1 ^ o.D = their candidate
+              uint4 a;
+              a.x = o.A1 ^ o.D; a.y = o.NA1 ^ o.ND; a.z = o.sx; a.w = vO;
+              *reinterpret_cast<uint4*>(walk + tid * kWalkWords) = a;
+              walk[tid * kWalkWords + 4] = nI;
             }
             __syncthreads();
             if (head) {                                                          // the serial part: one posterior handed down the run
               int j = tid + step;
-              uint4 w = *reinterpret_cast<const uint4*>(walk + (j < 360 ? j : tid) * kWalkWords);
+              const uint32_t* wj = walk + (j < 360 ? j : tid) * kWalkWords;
+              uint4 a = *reinterpret_cast<const uint4*>(wj);
+              uint32_t ni = wj[4];
               while (j < 360) {                                                  // (the next check node's words are fetched a step ahead)
                 const int jn = j + step;
-                const uint4 wn = *reinterpret_cast<const uint4*>(walk + (jn < 360 ? jn : tid) * kWalkWords);
-                walk[j * kWalkWords] = carry;                                    // the posterior check node j starts from
-                carry = walk_carry(carry, w.x, w.y, w.z, w.w);
-                w = wn; j = jn;
+                const uint32_t* wn = walk + (jn < 360 ? jn : tid) * kWalkWords;
+                const uint4 an = *reinterpret_cast<const uint4*>(wn);
+                const uint32_t nin = wn[4];
+                walk[j * kWalkWords + 5] = carry;                                // the posterior check node j starts from
+                carry = walk_carry(carry, a.x, a.y, a.z, a.w, ni);
+                a = an; ni = nin; j = jn;
               }
             }
             __syncthreads();
             if (owner && !head) {                                                // ... and everybody finishes its own check node
-              vI = sat8_add(walk[tid * kWalkWords], nI);
-              cn.take(vI, slotI); cn.take(vO, slotO);
-              uint32_t m0, m1, idn, gI, gO;
-              cn.minima(m0, m1, idn);
-              const CnCore c = cn.core();
-              post_st(rI, pack_post(core_out(c, slotI, vI, m0, m1, idn, gI)));
-              const uint32_t pO = core_out(c, slotO, vO, m0, m1, idn, gO);
-              if (sink) post_st(rO, pack_post(pO));                              // elsewhere the successor writes this bit's final value
-              negA = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
-              negB = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
+              cn.template edge_in_value<0>(sat8_add(walk[tid * kWalkWords + 5], nI));
+              cn.template edge_in_value<1>(vO);
+              const CnOut o = cn.minima();
+              cn.template edge_out<0>(o, true, true);
+              cn.template edge_out<1>(o, true, sink);                            // elsewhere the successor writes this bit's final value
             }
           } else {
+            int mylev = 0;
+            if (owner) mylev = __ldg(p.level + (int)p.cidx[i] * 360 + tid);
             for (int l = 1; l <= nl; ++l) {
               if (mylev == l) {
-                cn.template shared_load_generic<0>(eb, es, sh, tid);
-                uint32_t m0, m1, idn;
-                cn.minima(m0, m1, idn);
-                cn.template shared_store_generic<0>(sh, m0, m1, idn, negA, negB);
+                cn.template shared_load<0>(eb, es, ns, tid);
+                const CnOut o = cn.minima();
+                cn.template shared_store<0>(o, ns);
               }
               __syncthreads();
             }
           }
-          if (tid < 360) {
-            cn.template store<PREDICATED>(cnt, ~sh, i, tid, negA, negB, wA, wB);
+          if (owner) {
+            cn.store(ns, cnt, i, tid, false, w);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) {
-              __stcg(state + k * R + i * 360 + tid, wA[k]);
-              __stcg(state + (NS + k) * R + i * 360 + tid, wB[k]);
-            }
+            for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
           }
           __syncthreads();
         }
@@ -515,7 +486,7 @@ struct LdpcDeviceCode {
   LdpcSchedule s;
   int cnl = 0;              // instantiated bucket
   int minb = 1;             // co-resident CTAs per SM the kernel is built for (1: 64 800-bit codes, 2: 16 200-bit codes)
-  size_t state_bytes = 4, smem = 0;     // check-node words of one PAIR of codewords per check node; shared memory per CTA
+  size_t state_bytes = 4, smem = 0;     // stored messages of one PAIR of codewords per check node; shared memory per CTA
   int blocks_per_sm = 0;
   uint8_t* d_level = nullptr;
   LdpcParams proto;         // schedule part of the kernel parameters, filled once
@@ -533,10 +504,7 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
   if (!d->cnl || s.q > kMaxLayers || s.q * d->cnl > kMaxEdgeWords) {
     delete d; ctx->err = "LDPC code geometry not instantiated"; return T2B200_ERR_ARG;
   }
-  {
-    const int slots = d->cnl + 2, nw = (slots + 7) / 8, tail = slots - 8 * (nw - 1);
-    d->state_bytes = 2 * 4 * (size_t)(nw + (tail <= 5 ? 0 : 1));   // 2 codewords x CnLayout<CNL>::NS words per check node
-  }
+  d->state_bytes = 4 * (size_t)((d->cnl + 3) / 2);          // CnLayout<CNL>::NSW words per check node of the pair
   // shared memory: interleaved posteriors of the pair | two packed sign planes (+ padding words, rounded) | the parking
   // area of the chain walk; check-node words are in global scratch
   d->smem = (size_t)((2 * s.N + 15) & ~15) + 2 * (size_t)((((s.N + 31) >> 5) + 3) & ~1) * 4 + 360 * kWalkWords * 4;
@@ -551,7 +519,8 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
       p.es[i * d->cnl + c] = (uint16_t)shift;
       p.eb[i * d->cnl + c] = (uint16_t)((e & 0xffffu) - shift);
     }
-    p.shared[i] = s.shared[i]; p.cidx[i] = s.conflict_index[i]; p.cnt[i] = s.cnt[i]; p.nlev[i] = s.nlev[i];
+    p.ns[i] = s.ns[i]; p.cidx[i] = s.conflict_index[i]; p.cnt[i] = s.cnt[i]; p.nlev[i] = s.nlev[i];
+    if (s.ns[i] > 10) { delete d; ctx->err = "LDPC layer with more than 10 shared edges"; return T2B200_ERR_ARG; }
   }
   std::vector<uint8_t> level = s.level; if (level.empty()) level.resize(360, 1);
   cudaError_t ce = cudaMalloc(&d->d_level, level.size());

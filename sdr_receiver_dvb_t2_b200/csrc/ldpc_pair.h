@@ -1,12 +1,23 @@
 // Check-node arithmetic of the LDPC decoder for a PAIR of codewords: every 32-bit register holds the same quantity of
 // two codewords as s16x2 halves (low half: codeword A, high half: codeword B), so that one DPX instruction of sm_100
-// (VIADDMNMX.S16x2, VIMNMX.S16x2, VIADD.16x2) or one PRMT / LOP3 serves both.  The arithmetic is the reference's
+// (VIADDMNMX.S16x2, VIMNMX.S16x2) or one PRMT / LOP3 serves both.  The arithmetic is the reference's
 // (LDPC/layered_decoder.hh:87-107, LDPC/algorithms.hh:250-291: offset min-sum, beta = 1, int8 saturating, stored message
 // clamped to [-32, 31]); int8 values live sign-extended in their 16-bit half and are clamped back to [-128, 127] wherever
 // the reference saturates.
 //
-// The header compiles for the host too (T2_LDPC_HOST_EMULATION: the DPX / PRMT instructions are restated in plain C) so
-// that tests/cpp/ldpc_pair_emu.cpp can run exactly this code against the CPU oracle without a GPU.
+// Everything is kept in the form that costs the fewest ALU instructions per edge:
+//   * magnitudes are tracked NEGATED (n = -|v| = min(v, -v): one DPX instruction after the complement), the two largest n
+//     of a check node are its two smallest magnitudes;
+//   * "other(mag, min0, min1)" is the reference's own compare BY VALUE (algorithms.hh:266): max(n + a0, -1) is 0 for an
+//     input that attains the minimum and -1 (all ones) otherwise -- one DPX instruction gives the select mask of both
+//     codewords, one LOP3 picks between the two candidate magnitudes, no arg-min index is kept;
+//   * the sign of the outgoing message is the sign bit of (xor of all inputs) ^ input, turned into a half-wide mask by one
+//     sign-replicating PRMT; a LOP3 picks +mag or -mag;
+//   * the stored messages are kept as they are needed next time: negated and clamped, one byte per edge and codeword, two
+//     edges (x two codewords) per 32-bit word of an L2-resident scratch -- reading one back is a single PRMT.
+//
+// The header compiles for the host too (the DPX / PRMT instructions are restated in plain C) so that
+// tests/cpp/ldpc_pair_emu.cpp can run exactly this code, phase by phase, against the CPU oracle without a GPU.
 #pragma once
 #include <cstdint>
 
@@ -31,16 +42,14 @@ template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b)
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
   return r;
 }
-// run-time selector (low 16 bits); the callers' nibbles never have bit 3 set where the result is used
-T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel)
+// bitwise complement as a multiply-add (-x - 1): issues on the FMA pipe, the ALU pipe is the decoder's bottleneck
+T2_HD uint32_t not_fma(uint32_t x)
 {
   uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  asm("mad.lo.u32 %0, %1, 0xffffffff, 0xffffffff;" : "=r"(r) : "r"(x));
   return r;
 }
 T2_HD int mod360(int t) { return (int)__viaddmin_u32((unsigned)t, 0xfffffe98u, (unsigned)t); }    // t in [0, 720): t mod 360
-T2_HD uint32_t rotl(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
-T2_HD uint32_t vneg2(uint32_t a) { return __vneg2(a); }                                               // per-half negation
 // the pair's posteriors by 32-bit shared-memory address (kept in a register from the load to the store of an edge)
 typedef uint32_t post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return (uint32_t)__cvta_generic_to_shared(post); }
@@ -76,10 +85,8 @@ T2_HD uint32_t prmt_any(uint32_t a, uint32_t b, uint32_t sel)
   return r;
 }
 template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b) { return prmt_any(a, b, SEL); }
-T2_HD uint32_t prmt_rt(uint32_t a, uint32_t b, uint32_t sel) { return prmt_any(a, b, sel); }
+T2_HD uint32_t not_fma(uint32_t x) { return ~x; }
 T2_HD int mod360(int t) { return t >= 360 ? t - 360 : t; }
-T2_HD uint32_t rotl(uint32_t x, int r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
-T2_HD uint32_t vneg2(uint32_t a) { return pk16(-(int)lo16(a), -(int)hi16(a)); }
 typedef uint16_t* post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return post; }
 T2_HD post_ref post_at(post_ref base, int a) { return base + a; }
@@ -87,297 +94,191 @@ T2_HD uint32_t post_ld(post_ref r) { return *r; }
 T2_HD void post_st(post_ref r, uint32_t v) { *r = (uint16_t)v; }
 #endif
 
-constexpr uint32_t kP127 = 0x007f007fu, kM128 = 0xff80ff80u, kOne2 = 0x00010001u, kIdleKey = 0x7fff7fffu;
+constexpr uint32_t kP127 = 0x007f007fu, kM128 = 0xff80ff80u, kOne2 = 0x00010001u, kMinus1 = 0xffffffffu;
+constexpr uint32_t kIdleN = 0x80008000u;          // "no input": -32768 in the negated-magnitude domain
+constexpr uint32_t kC126 = 0x007e007eu, kM126 = 0xff82ff82u;
 
 // int8 saturating add of two sign-extended pairs (vqadd / vqsub with a negated operand)
 T2_HD uint32_t sat8_add(uint32_t a, uint32_t b) { return vmax2(vaddmin(a, b, kP127), kM128); }
-T2_HD uint32_t abs2(uint32_t v) { return vaddmax(~v, kOne2, v); }                                   // max(-v, v)
 // two posteriors (one per codeword) as they sit in shared memory (low byte A, high byte B) -> sign-extended s16x2
 T2_HD uint32_t unpack_post(uint32_t raw16) { return prmt<0x9180u>(raw16, 0u); }
 T2_HD uint32_t pack_post(uint32_t v) { return prmt<0x4420u>(v, 0u); }   // low bytes of the two halves, upper half zero
-T2_HD uint32_t pack4(int b0, int b1, int b2, int b3)
-{
-  return ((uint32_t)b0 & 0xffu) | (((uint32_t)b1 & 0xffu) << 8) | (((uint32_t)b2 & 0xffu) << 16) | ((uint32_t)b3 << 24);
-}
+// half-wide masks (0xffff / 0) from the sign bits of the two halves
+T2_HD uint32_t sign_mask2(uint32_t t) { return prmt<0xbb99u>(t, 0u); }
+T2_HD uint32_t pick(uint32_t a, uint32_t b, uint32_t m) { return (a & ~m) | (b & m); }              // one LOP3: m ? b : a
 
-// Check-node word layout (per codeword).  The min-sum messages of a check node are fully determined by (m0, m1, arg-min
-// slot, output signs): message of slot c = sign_c * (c == arg-min ? m1 : m0).  One 2-bit code per slot (bit 0: sign
-// negative, bit 1: slot is the arg-min), one code per NIBBLE, so that a single PRMT looks the messages of four slots up in
-// a 4-entry byte table {+m0, -m0, +m1, -m1}.  The words of codeword B are kept ROTATED by 16 bits (halves swapped): one
-// rotate of (sx ^ input) then drops the output-sign bits of both codewords (bits 15 and 31) onto their nibbles at once.
+// Stored messages of one check node of the pair: NSW words; word k holds slots 2k (bytes 0 / 1: codeword A / B) and
+// 2k + 1 (bytes 2 / 3), each byte = -clamp(message, -32, 31).
 template <int CNL> struct CnLayout {
-  static constexpr int SLOTS = CNL + 2;
-  static constexpr int NW = (SLOTS + 7) / 8;                 // code words, 8 nibbles each
-  static constexpr int TAIL = SLOTS - 8 * (NW - 1);          // nibbles in use in the last code word
-  static constexpr bool MPACK = TAIL <= 5;                   // m0 | m1 (6 + 6 bits) share the last code word
-  static constexpr int NS = NW + (MPACK ? 0 : 1);            // 32-bit words per check node and codeword
-  // bit position of slot's nibble in its code word; ROT = 0 for codeword A, 16 for codeword B
-  template <int ROT> static constexpr int nib(int slot) { return (4 * (slot & 7) + ROT) & 31; }
+  static constexpr int SLOTS = CNL + 2;                      // data edges + the two parity edges
+  static constexpr int NSW = (SLOTS + 1) / 2;
 };
 
-enum SlotMode { ALL_SLOTS, PREDICATED, BRANCHED };
+// what the outgoing messages of a check node are made from: the smallest magnitude a0 (for the compare by value), the
+// two candidate message magnitudes after the offset and the clamp (A1: for the input that attains the minimum, A0 = A1 ^ D
+// for the others) and their negatives
+struct CnOut { uint32_t a0, A1, D, NA1, ND, sx; };
 
-constexpr int kWalkWords = 4;         // words parked per check node by the chain walk (walk_carry's arguments; word 0 returns its carry-in)
-
-// The running state of one check node of the pair -- the two smallest keys and the xor of the inputs seen so far -- as a
-// value that can be handed from thread to thread (the chain walk of ldpc.cu parks it in shared memory).
-struct CnCore { uint32_t key0, key1, sx; };
-T2_HD void core_take(CnCore& c, uint32_t v, int slot)
+// the two candidates from the two largest negated magnitudes n0 >= n1 (<= 0; kIdleN when there is no second input)
+T2_HD CnOut cn_minima(uint32_t n0, uint32_t n1, uint32_t sx)
 {
-  const uint32_t key = abs2(v) * 32u + (uint32_t)slot * kOne2;
-  c.key1 = vmin2(c.key1, vmax2(c.key0, key));
-  c.key0 = vmin2(c.key0, key);
-  c.sx ^= v;
+  CnOut o;
+  const uint32_t c0 = not_fma(n0), c1 = not_fma(n1);                       // |v| - 1
+  const uint32_t A0 = vmin2(vmax2(c0, 0u), kC126);                          // vqsub(vqabs(v), 1), at most 126
+  o.A1 = vmin2(vmax2(c1, 0u), kC126);
+  o.a0 = vaddmax(c0, kOne2, kIdleN);                                        // -n0
+  const uint32_t NA0 = vmin2(vaddmax(n0, kOne2, kM126), 0u);                // -A0
+  o.NA1 = vmin2(vaddmax(n1, kOne2, kM126), 0u);
+  o.D = A0 ^ o.A1; o.ND = NA0 ^ o.NA1; o.sx = sx;
+  return o;
 }
-T2_HD void core_minima(const CnCore& c, uint32_t& m0, uint32_t& m1, uint32_t& idn)
+// One edge out: input v (n = -|v|) -> new posterior pair (vqadd of v and the check node's message) and `nm`, what is
+// stored for the next iteration: -clamp(message, -32, 31)
+T2_HD uint32_t cn_edge_out(const CnOut& o, uint32_t v, uint32_t n, uint32_t& nm)
 {
-  const uint32_t c126 = 0x007e007eu, mone = 0xffffffffu;
-  m0 = vmin2(vaddmax((c.key0 >> 5) & 0x07ff07ffu, mone, 0u), c126);
-  m1 = vmin2(vaddmax((c.key1 >> 5) & 0x07ff07ffu, mone, 0u), c126);
-  idn = c.key0 & 0x001f001fu;
+  const uint32_t mask = vaddmax(n, o.a0, kMinus1);           // 0: this input attains the minimum, -1: it does not
+  const uint32_t F = o.A1 ^ (o.D & mask), NF = o.NA1 ^ (o.ND & mask);
+  const uint32_t neg = sign_mask2(o.sx ^ v);                 // product of the OTHER inputs' signs is negative
+  const uint32_t msg = pick(F, NF, neg);
+  nm = vmax2(vmin2(F ^ NF ^ msg, 0x00200020u), 0xffe1ffe1u);
+  return sat8_add(v, msg);
 }
-// new posterior pair of an edge whose input was v (vqadd of v and the check node's message); neg: bit 0 / 16 set when the
-// message is negative in codeword A / B
-T2_HD uint32_t core_out(const CnCore& c, int slot, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn, uint32_t& neg)
-{
-  const uint32_t t = c.sx ^ v;
-  const int negA = (t >> 15) & 1u, negB = t >> 31;
-  int ma = (int)((slot == (int)(idn & 0xffffu) ? m1 : m0) & 0xffffu);
-  int mb = (int)((slot == (int)(idn >> 16) ? m1 : m0) >> 16);
-  if (negA) ma = -ma;
-  if (negB) mb = -mb;
-  neg = (uint32_t)negA | ((uint32_t)negB << 16);
-  return sat8_add(v, ((uint32_t)ma & 0xffffu) | ((uint32_t)mb << 16));
-}
+T2_HD uint32_t nabs2(uint32_t v) { return vaddmin(not_fma(v), kOne2, v); }                             // min(-v, v)
 
 // The serial core of the chain walk (ldpc.cu): a check node shares one bit with its predecessor in the layer's serial order
-// (slot I: its updated posterior pair arrives in `carry`) and one with its successor (slot O).  All the successor needs is
-// the new posterior of the O bit: vqadd(vO, message) with |message| = the smallest magnitude among the OTHER inputs (the
-// private edges, whose minimum a0mag = (key0 >> 5) is known beforehand, and the I input) after the offset, and sign = product
-// of the other inputs' signs (sxp: xor of the private inputs).  ~14 dependent instructions per check node; everything else
-// of the check node is done afterwards, in parallel, by its own thread.
-T2_HD uint32_t walk_carry(uint32_t carry, uint32_t a0mag, uint32_t sxp, uint32_t vO, uint32_t nI)
+// (slot 0: its updated posterior pair arrives in `carry`) and one with its successor (slot 1).  All the successor needs is
+// the new posterior of the slot-1 bit: vqadd(vO, message) with |message| = the smallest magnitude among the OTHER inputs
+// (the private edges, whose candidate A0p / -A0p is known beforehand, and the slot-0 input) and sign = product of the
+// other inputs' signs (sxp: xor of the private inputs).  Nine dependent instructions per check node; everything else of
+// the check node is done afterwards, in parallel, by its own thread.
+T2_HD uint32_t walk_carry(uint32_t carry, uint32_t A0p, uint32_t NA0p, uint32_t sxp, uint32_t vO, uint32_t nI)
 {
   const uint32_t vI = sat8_add(carry, nI);
-  const uint32_t mag = vmin2(a0mag, abs2(vI));
-  const uint32_t m = vmin2(vaddmax(mag, 0xffffffffu, 0u), 0x007e007eu);
-  const uint32_t smask = (((sxp ^ vI) >> 15) & kOne2) * 0xffffu;
-  return sat8_add(vO, (m & ~smask) | (vneg2(m) & smask));
+  const uint32_t c = not_fma(vI);
+  const uint32_t F = vmin2(A0p, vaddmax(vaddmax(c, kOne2, vI), kMinus1, 0u));        // min(A0p, max(|vI| - 1, 0))
+  const uint32_t NF = vmax2(NA0p, vaddmin(vaddmin(c, kOne2, vI), kOne2, 0u));        // its negative
+  return sat8_add(vO, pick(F, NF, sign_mask2(sxp ^ vI)));
 }
+constexpr int kWalkWords = 8;         // words parked per check node by the chain walk: A0p, -A0p, sxp, vO, nI, carry-in
 
-// One check node of BOTH codewords of the pair, split so that the edges private to the check node and the edges it shares
-// with another check node of the same layer can be read / written at different times.
+// One check node of BOTH codewords of the pair.  Slots 0 .. CNL-1 are the data edges (those shared with another check node
+// of the layer come first, ldpc_schedule.cpp), slot CNL the parity bit of the check node, slot CNL+1 the previous one.
 template <int CNL>
 struct CheckNodePair {
   using LY = CnLayout<CNL>;
-  static constexpr int SLOTS = LY::SLOTS, NW = LY::NW, NG = (SLOTS + 3) / 4;
-  uint32_t inp[SLOTS];      // vqsub(posterior, stored message), s16x2
+  static constexpr int SLOTS = LY::SLOTS, NSW = LY::NSW;
+  uint32_t v[SLOTS];        // input vqsub(posterior, stored message), s16x2; after the edge has been written: what is stored
+  uint32_t n[SLOTS];        // -|v|
   post_ref adr[SLOTS];      // where the edge's pair of posteriors lives
-  uint32_t key0, key1;      // two smallest keys |v| * 32 + slot per half
-  uint32_t sx;              // xor of the inputs: sign bits at 15 / 31
-  uint32_t tinA, tinB;      // bytes {-clamp(+m0), -clamp(-m0), -clamp(+m1), -clamp(-m1)} of the PREVIOUS iteration
-  uint32_t cwA[NW], cwB[NW];        // previous iteration's codes
-  uint32_t ninA[NG], ninB[NG];      // minus stored message of slots 4g .. 4g+3, one byte each
-  uint32_t ncwA[NW], ncwB[NW];      // codes being built
+  uint32_t w[NSW];          // stored messages of the previous iteration
+  uint32_t n0, n1, sx;      // two largest n, xor of the inputs (sign bits at 15 / 31)
   post_ref post;
 
-  template <int ROT> static T2_HD uint32_t table_in(uint32_t mw)
-  {
-    constexpr int P = (20 + ROT) & 31;                          // the minima sit behind the nibbles of the last code word
-    const int m0c = LY::MPACK ? (int)((mw >> P) & 63u) : (int)(mw & 63u);
-    const int m1c = LY::MPACK ? (int)((mw >> (P + 6)) & 63u) : (int)((mw >> 6) & 63u);
-    return pack4(-(m0c < 31 ? m0c : 31), m0c, -(m1c < 31 ? m1c : 31), m1c);
-  }
-  T2_HD void begin(uint16_t* post_, const uint32_t (&wA)[LY::NS], const uint32_t (&wB)[LY::NS])
+  T2_HD void begin(uint16_t* post_, const uint32_t (&w_)[NSW])
   {
     post = post_base(post_);
-    tinA = table_in<0>(wA[LY::NS - 1]);
-    tinB = table_in<16>(wB[LY::NS - 1]);
 #pragma unroll
-    for (int k = 0; k < NW; ++k) { cwA[k] = wA[k]; cwB[k] = wB[k]; ncwA[k] = 0; ncwB[k] = 0; }
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      ninA[g] = prmt_rt(tinA, 0u, (g & 1) ? (cwA[g >> 1] >> 16) : cwA[g >> 1]);
-      ninB[g] = prmt_rt(tinB, 0u, (g & 1) ? cwB[g >> 1] : (cwB[g >> 1] >> 16));
-    }
-    key0 = kIdleKey; key1 = kIdleKey; sx = 0;
+    for (int k = 0; k < NSW; ++k) w[k] = w_[k];
+    n0 = kIdleN; n1 = kIdleN; sx = 0;
   }
-  // byte c of a (codeword A) and byte c of b (codeword B), each sign-extended into its half
-  template <int C> static T2_HD uint32_t pick(uint32_t a, uint32_t b)
+  template <int SLOT> T2_HD uint32_t stored_neg() const
   {
-    return prmt<(uint32_t)(C | ((8 | C) << 4) | ((4 + C) << 8) | ((12 + C) << 12))>(a, b);
+    return (SLOT & 1) ? prmt<0xb3a2u>(w[SLOT >> 1], 0u) : prmt<0x9180u>(w[SLOT >> 1], 0u);
   }
-  template <int SLOT> T2_HD uint32_t stored_neg() const { return pick<SLOT & 3>(ninA[SLOT >> 2], ninB[SLOT >> 2]); }
-  T2_HD uint32_t stored_neg_rt(int slot) const
+  T2_HD void take(uint32_t vv, uint32_t nn, bool active = true)
   {
-    const int sh4 = 4 * (slot & 7), sh4b = (sh4 + 16) & 31;
-    uint32_t ca = (cwA[0] >> sh4) & 3u, cb = (cwB[0] >> sh4b) & 3u;
-#pragma unroll
-    for (int k = 1; k < NW; ++k) {
-      const uint32_t xa = (cwA[k] >> sh4) & 3u, xb = (cwB[k] >> sh4b) & 3u;
-      ca = (slot >> 3) == k ? xa : ca;
-      cb = (slot >> 3) == k ? xb : cb;
-    }
-    const int a = (int)(int8_t)(tinA >> (8 * ca)), b = (int)(int8_t)(tinB >> (8 * cb));
-    return ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+    nn = active ? nn : kIdleN;
+    n1 = vmax2(n1, vmin2(n0, nn));
+    n0 = vmax2(n0, nn);
+    sx ^= active ? vv : 0u;
   }
   // `active` false: the slot does not take part (it is computed and discarded, branch-free, so that the loads of a layer
   // still issue back to back)
-  T2_HD void take(uint32_t v, int slot_const, bool active = true)
-  {
-    uint32_t key = abs2(v) * 32u + (uint32_t)slot_const * kOne2;             // |v| <= 128: no carry between the halves
-    key = active ? key : kIdleKey;
-    key1 = vmin2(key1, vmax2(key0, key));
-    key0 = vmin2(key0, key);
-    sx ^= active ? v : 0u;
-  }
   template <int SLOT> T2_HD void edge_in(int a, bool active)
   {
     const post_ref r = post_at(post, a);
-    const uint32_t pv = unpack_post(post_ld(r));
-    const uint32_t v = sat8_add(pv, stored_neg<SLOT>());                      // vqsub(posterior, stored message)
-    inp[SLOT] = v; adr[SLOT] = r;
-    take(v, SLOT, active);
+    const uint32_t vv = sat8_add(unpack_post(post_ld(r)), stored_neg<SLOT>());         // vqsub(posterior, stored message)
+    const uint32_t nn = nabs2(vv);
+    v[SLOT] = vv; n[SLOT] = nn; adr[SLOT] = r;
+    take(vv, nn, active);
   }
-  // m0 / m1 (after vqabs and the unsigned vqsub of beta = 1: both monotone, so applied to the two minima only) and the
-  // arg-min slot of everything seen so far, per half
-  T2_HD void minima(uint32_t& m0, uint32_t& m1, uint32_t& idn) const
+  // input of a slot that arrives in a register (chain walk)
+  template <int SLOT> T2_HD void edge_in_value(uint32_t vv)
   {
-    const uint32_t c126 = 0x007e007eu, mone = 0xffffffffu;
-    m0 = vmin2(vaddmax((key0 >> 5) & 0x07ff07ffu, mone, 0u), c126);
-    m1 = vmin2(vaddmax((key1 >> 5) & 0x07ff07ffu, mone, 0u), c126);
-    idn = key0 & 0x001f001fu;
+    const uint32_t nn = nabs2(vv);
+    v[SLOT] = vv; n[SLOT] = nn;
+    take(vv, nn);
   }
-  template <int SLOT> T2_HD void mark_sign(bool active)
+  template <int SLOT> T2_HD post_ref slot_ref(const uint16_t* eb, const uint16_t* es, int j)
   {
-    // sign of the product of the OTHER links: bit 15 (A) lands on its nibble, bit 31 (B) on the rotated one
-    constexpr int pos = LY::template nib<0>(SLOT), posb = LY::template nib<16>(SLOT);
-    const uint32_t u = active ? rotl(sx ^ inp[SLOT], (pos + 17) & 31) : 0u;
-    ncwA[SLOT >> 3] |= u & (1u << pos);
-    ncwB[SLOT >> 3] |= u & (1u << posb);
+    adr[SLOT] = post_at(post, mod360(j + (int)es[SLOT]) + (int)eb[SLOT]);
+    return adr[SLOT];
   }
-  template <SlotMode MODE, int C>
-  T2_HD void load_from(const uint16_t* eb, const uint16_t* es, int cnt, uint32_t mask, int j)
+  T2_HD CnOut minima() const { return cn_minima(n0, n1, sx); }
+  // write the edge back (when `store`) and leave what is stored for the next iteration in v[SLOT]
+  template <int SLOT> T2_HD uint32_t edge_out(const CnOut& o, bool active, bool store)
+  {
+    uint32_t nm;
+    const uint32_t np = cn_edge_out(o, v[SLOT], n[SLOT], nm);
+    if (active && store) post_st(adr[SLOT], pack_post(np));
+    v[SLOT] = active ? nm : 0u;
+    return np;
+  }
+  // data slots lo <= C < hi, in order
+  template <int C> T2_HD void load_from(const uint16_t* eb, const uint16_t* es, int lo, int hi, int j, bool all)
   {
     if constexpr (C < CNL) {
-      const bool on = MODE == ALL_SLOTS ? true : (C < cnt && ((mask >> C) & 1u));
-      if (!(MODE == BRANCHED && !on)) {
-        edge_in<C>(mod360(j + (int)es[C]) + (int)eb[C], on);                   // eb + (j + es) mod 360
-      }
-      load_from<MODE, C + 1>(eb, es, cnt, mask, j);
+      edge_in<C>(mod360(j + (int)es[C]) + (int)eb[C], all || (C >= lo && C < hi));      // eb + (j + es) mod 360
+      load_from<C + 1>(eb, es, lo, hi, j, all);
     }
   }
-  template <SlotMode MODE>
-  T2_HD void load(const uint16_t* eb, const uint16_t* es, int cnt, uint32_t mask, int i, int j, int K, int q)
+  // the private edges: data slots lo .. cnt-1 and the two parity slots (`all`: lo = 0 and cnt = CNL, known to the caller)
+  T2_HD void load(const uint16_t* eb, const uint16_t* es, int lo, int cnt, int i, int j, int K, int q, bool all)
   {
-    load_from<MODE, 0>(eb, es, cnt, mask, j);
+    load_from<0>(eb, es, lo, cnt, j, all);
     edge_in<CNL>(K + 360 * i + j, true);
     const bool hasB = (i | j) != 0;
     edge_in<CNL + 1>(i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + (hasB ? j - 1 : 0), hasB);
   }
-  template <SlotMode MODE, int C> T2_HD void sign_from(int cnt, uint32_t mask)
+  template <int C> T2_HD void out_from(const CnOut& o, int lo, int hi, bool all)
   {
     if constexpr (C < CNL) {
-      const bool on = MODE == ALL_SLOTS ? true : (C < cnt && ((mask >> C) & 1u));
-      if (!(MODE == BRANCHED && !on)) mark_sign<C>(on);
-      sign_from<MODE, C + 1>(cnt, mask);
+      const bool on = all || (C >= lo && C < hi);
+      if (all || C >= lo) edge_out<C>(o, on, true);                    // (slots below lo were written earlier: v[C] holds their stored value)
+      out_from<C + 1>(o, lo, hi, all);
     }
   }
-  template <int SLOT> T2_HD void edge_out(const uint32_t (&noutA)[NG], const uint32_t (&noutB)[NG], bool active)
+  // Write the private edges back and pack what is stored.
+  T2_HD void store(int lo, int cnt, int i, int j, bool all, uint32_t (&w_)[NSW])
   {
-    const uint32_t o = pick<SLOT & 3>(noutA[SLOT >> 2], noutB[SLOT >> 2]);     // other(mags[i], mins[0], mins[1]) with the sign
-    if (active) post_st(adr[SLOT], pack_post(sat8_add(inp[SLOT], o)));          // vqadd
+    const CnOut o = minima();
+    out_from<0>(o, lo, cnt, all);
+    edge_out<CNL>(o, true, true);
+    edge_out<CNL + 1>(o, (i | j) != 0, true);
+    pack(w_);
   }
-  template <SlotMode MODE, int C>
-  T2_HD void out_from(const uint32_t (&noutA)[NG], const uint32_t (&noutB)[NG], int cnt, uint32_t mask)
+  T2_HD void pack(uint32_t (&w_)[NSW]) const
   {
-    if constexpr (C < CNL) {
-      const bool on = MODE == ALL_SLOTS ? true : (C < cnt && ((mask >> C) & 1u));
-      if (!(MODE == BRANCHED && !on)) edge_out<C>(noutA, noutB, on);
-      out_from<MODE, C + 1>(noutA, noutB, cnt, mask);
-    }
-  }
-  // sign codes of the shared slots resolved earlier: bit c of negA / negB
-  template <int C> T2_HD void merge_shared(uint32_t negA, uint32_t negB)
-  {
-    if constexpr (C < CNL) {
-      if ((negA >> C) & 1u) ncwA[C >> 3] |= 1u << (4 * (C & 7));
-      if ((negB >> C) & 1u) ncwB[C >> 3] |= 1u << LY::template nib<16>(C);
-      merge_shared<C + 1>(negA, negB);
-    }
-  }
-  template <int ROT>
-  static T2_HD void finish_codes(uint32_t (&ncw)[NW], int idn, int m0, int m1, uint32_t (&nout)[NG], uint32_t (&w)[LY::NS])
-  {
-    const uint32_t bit = 2u << ((4 * (idn & 7) + ROT) & 31);
 #pragma unroll
-    for (int k = 0; k < NW; ++k) ncw[k] |= (idn >> 3) == k ? bit : 0u;
-    const uint32_t tout = pack4(m0, -m0, m1, -m1);
-#pragma unroll
-    for (int g = 0; g < NG; ++g) nout[g] = prmt_rt(tout, 0u, ((g & 1) != (ROT != 0)) ? (ncw[g >> 1] >> 16) : ncw[g >> 1]);
-    const uint32_t mm = (uint32_t)(m0 < 32 ? m0 : 32) | ((uint32_t)(m1 < 32 ? m1 : 32) << 6);
-#pragma unroll
-    for (int k = 0; k < NW; ++k) w[k] = ncw[k];
-    if (LY::MPACK) w[NW - 1] |= mm << ((20 + ROT) & 31); else w[LY::NS - 1] = mm;
+    for (int k = 0; k < NSW; ++k) w_[k] = prmt<0x6420u>(v[2 * k], 2 * k + 1 < SLOTS ? v[2 * k + 1] : 0u);
   }
-  // Write the private edges back and finish the check-node words.  negA / negB: bit c set when shared slot c (already
-  // written by shared_out) carried a negative output sign in codeword A / B.
-  template <SlotMode MODE>
-  T2_HD void store(int cnt, uint32_t mask, int i, int j, uint32_t negA, uint32_t negB, uint32_t (&wA)[LY::NS], uint32_t (&wB)[LY::NS])
+  // ---- shared slots 0 .. ns-1 of a layer resolved level by level ----
+  template <int C> T2_HD void shared_load(const uint16_t* eb, const uint16_t* es, int ns, int j)
   {
-    uint32_t m0, m1, idn;
-    minima(m0, m1, idn);
-    sign_from<MODE, 0>(cnt, mask);
-    mark_sign<CNL>(true);
-    mark_sign<CNL + 1>((i | j) != 0);
-    if (MODE != ALL_SLOTS) merge_shared<0>(negA, negB);
-    uint32_t noutA[NG], noutB[NG];
-    finish_codes<0>(ncwA, (int)(idn & 0xffffu), (int)(m0 & 0xffffu), (int)(m1 & 0xffffu), noutA, wA);
-    finish_codes<16>(ncwB, (int)(idn >> 16), (int)(m0 >> 16), (int)(m1 >> 16), noutB, wB);
-    out_from<MODE, 0>(noutA, noutB, cnt, mask);
-    edge_out<CNL>(noutA, noutB, true);
-    edge_out<CNL + 1>(noutA, noutB, (i | j) != 0);
-  }
-  // ---- shared-edge path: the slot number is a run-time (warp-uniform) value ----
-  T2_HD uint32_t shared_in(int slot, int a, uint32_t nbl)
-  {
-    const uint32_t v = sat8_add(unpack_post(post_ld(post_at(post, a))), nbl);
-    take(v, slot);
-    return v;
-  }
-  // returns bit 0 (A) / bit 16 (B) set when the output sign is negative
-  T2_HD uint32_t shared_out(int slot, int a, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn)
-  {
-    return shared_out_at(slot, post_at(post, a), v, m0, m1, idn);
-  }
-  T2_HD uint32_t shared_out_at(int slot, post_ref where, uint32_t v, uint32_t m0, uint32_t m1, uint32_t idn)
-  {
-    uint32_t neg;
-    const CnCore c = {key0, key1, sx};
-    post_st(where, pack_post(core_out(c, slot, v, m0, m1, idn, neg)));
-    return neg;
-  }
-  // the running state as a value / taken back (chain walk)
-  T2_HD CnCore core() const { return CnCore{key0, key1, sx}; }
-  T2_HD void set_core(const CnCore& c) { key0 = c.key0; key1 = c.key1; sx = c.sx; }
-  T2_HD post_ref post_ref_at(int a) const { return post_at(post, a); }
-  template <int C> T2_HD void shared_load_generic(const uint16_t* eb, const uint16_t* es, uint32_t mask, int j)
-  {
-    if constexpr (C < CNL) {
-      if ((mask >> C) & 1u) {
+    if constexpr (C < CNL && C < 10) {
+      if (C < ns) {
         edge_in<C>(mod360(j + (int)es[C]) + (int)eb[C], true);
+        shared_load<C + 1>(eb, es, ns, j);
       }
-      shared_load_generic<C + 1>(eb, es, mask, j);
     }
   }
-  template <int C> T2_HD void shared_store_generic(uint32_t mask, uint32_t m0, uint32_t m1, uint32_t idn, uint32_t& negA, uint32_t& negB)
+  template <int C> T2_HD void shared_store(const CnOut& o, int ns)
   {
-    if constexpr (C < CNL) {
-      if ((mask >> C) & 1u) {
-        const uint32_t r = shared_out_at(C, adr[C], inp[C], m0, m1, idn);
-        negA |= (r & 1u) << C; negB |= (r >> 16) << C;
+    if constexpr (C < CNL && C < 10) {
+      if (C < ns) {
+        edge_out<C>(o, true, true);
+        shared_store<C + 1>(o, ns);
       }
-      shared_store_generic<C + 1>(mask, m0, m1, idn, negA, negB);
     }
   }
 };

@@ -36,9 +36,29 @@ bool t2_build_ldpc_schedule(int code, LdpcSchedule& s)
     s.links_total += 360 * (int)layer[i].size();
   }
   s.edge.assign((size_t)q * s.cnl_max, 0);
-  s.shared.assign(q, 0); s.conflict_index.assign(q, -1); s.nlev.assign(q, 1); s.level.clear(); s.total_substeps = 0;
+  s.shared.assign(q, 0); s.ns.assign(q, 0); s.conflict_index.assign(q, -1); s.nlev.assign(q, 1); s.level.clear(); s.total_substeps = 0;
   for (int i = 0; i < q; ++i) {
     auto& L = layer[i];
+    // Data edges that read a bit-group another edge of the layer reads too go FIRST (their slot numbers are then known
+    // at compile time in the kernel).  With a single such pair the slots are ordered (I, O): bit (j + shift_O) of check node
+    // j is bit (j' + shift_I) of check node j' = j + step, step = (shift_O - shift_I) mod 360 <= 180 -- the O bit is
+    // handed to a LATER check node of the serial order (except at the wrap), the I bit comes from an earlier one.
+    {
+      std::vector<int> is_shared(L.size(), 0);
+      for (size_t x = 0; x < L.size(); ++x)
+        for (size_t y = x + 1; y < L.size(); ++y)
+          if (L[x].g == L[y].g) { is_shared[x] = 1; is_shared[y] = 1; }
+      std::vector<E> front, back;
+      for (size_t x = 0; x < L.size(); ++x) (is_shared[x] ? front : back).push_back(L[x]);
+      s.ns[i] = (uint8_t)front.size();
+      if (front.size() == 2) {
+        auto shift = [](const E& e) { return (360 - e.jx) % 360; };
+        const int D = ((shift(front[0]) - shift(front[1])) % 360 + 360) % 360;      // front[0] as O, front[1] as I
+        if (D <= 180) std::swap(front[0], front[1]);                                 // -> (I, O)
+      }
+      L = front;
+      L.insert(L.end(), back.begin(), back.end());
+    }
     for (size_t c = 0; c < L.size(); ++c)
     {
       const int sh = (360 - L[c].jx) % 360;

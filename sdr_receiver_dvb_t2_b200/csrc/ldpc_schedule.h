@@ -22,6 +22,8 @@ struct LdpcSchedule {
                                    //   = j + low16 - (j >= high16 ? 360 : 0)
   std::vector<uint32_t> shared;    // [q] bit c set: data edge c of this layer reads a bit-group that another
                                    //   edge of the same layer reads too (two check nodes share each such bit)
+  std::vector<uint8_t> ns;         // [q] number of such edges; they are slots 0 .. ns-1 (with ns == 2: slot 0 takes the
+                                   //   bit from an earlier check node of the serial order, slot 1 hands it to a later one)
   // Exact emulation of the reference's serial j = 0..359 order inside a layer: two check nodes of
   // one layer that share a bit must run smaller-j first.  level[][] is the longest-chain depth.
   std::vector<int16_t> conflict_index;  // [q] row into level[], or -1 when the layer has no shared bit

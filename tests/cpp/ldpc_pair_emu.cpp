@@ -43,7 +43,7 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
                 int* iters_out)
 {
   using LY = CnLayout<CNL>;
-  constexpr int NS = LY::NS;
+  constexpr int NSW = LY::NSW;
   std::vector<uint16_t> eb((size_t)s.q * CNL, 0), es((size_t)s.q * CNL, 0);
   for (int i = 0; i < s.q; ++i)
     for (int c = 0; c < s.cnl_max; ++c) {
@@ -54,7 +54,7 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
     }
   std::vector<uint16_t> post(s.N);
   for (int n = 0; n < s.N; ++n) post[n] = (uint16_t)((uint8_t)llrA[n] | ((uint16_t)(uint8_t)llrB[n] << 8));
-  std::vector<uint32_t> state((size_t)2 * NS * s.R, 0);
+  std::vector<uint32_t> state((size_t)s.q * NSW * 360, 0);
   int trials = max_trials, iters = 0;
   for (;;) {
     const bool bad = lane_bad(s, post, 0, eb, es, CNL) || lane_bad(s, post, 1, eb, es, CNL);
@@ -63,114 +63,81 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
       const int cnt = s.cnt[i], nl = s.nlev[i];
       const uint16_t* peb = eb.data() + i * CNL;
       const uint16_t* pes = es.data() + i * CNL;
-      auto ld = [&](int tid, uint32_t (&wA)[NS], uint32_t (&wB)[NS]) {
-        for (int k = 0; k < NS; ++k) {
-          wA[k] = iters ? state[(size_t)k * s.R + i * 360 + tid] : 0u;
-          wB[k] = iters ? state[(size_t)(NS + k) * s.R + i * 360 + tid] : 0u;
-        }
-      };
-      auto st = [&](int tid, const uint32_t (&wA)[NS], const uint32_t (&wB)[NS]) {
-        for (int k = 0; k < NS; ++k) {
-          state[(size_t)k * s.R + i * 360 + tid] = wA[k];
-          state[(size_t)(NS + k) * s.R + i * 360 + tid] = wB[k];
-        }
-      };
+      uint32_t* sp = state.data() + (size_t)i * NSW * 360;
+      auto ld = [&](int tid, uint32_t (&w)[NSW]) { for (int k = 0; k < NSW; ++k) w[k] = iters ? sp[k * 360 + tid] : 0u; };
+      auto st = [&](int tid, const uint32_t (&w)[NSW]) { for (int k = 0; k < NSW; ++k) sp[k * 360 + tid] = w[k]; };
+      std::vector<CheckNodePair<CNL>> cn(360);
       if (nl == 1) {
-        // one barrier phase: every thread reads all its inputs before any thread writes (emulated: two passes)
-        std::vector<CheckNodePair<CNL>> cn(360);
+        // one barrier phase: a thread's bits are touched by no other thread of the layer
         for (int tid = 0; tid < 360; ++tid) {
-          uint32_t wA[NS], wB[NS];
-          ld(tid, wA, wB);
-          cn[tid].begin(post.data(), wA, wB);
-          if (cnt == CNL) cn[tid].template load<ALL_SLOTS>(peb, pes, cnt, ~0u, i, tid, s.K, s.q);
-          else cn[tid].template load<PREDICATED>(peb, pes, cnt, ~0u, i, tid, s.K, s.q);
-        }
-        for (int tid = 0; tid < 360; ++tid) {
-          uint32_t wA[NS], wB[NS];
-          if (cnt == CNL) cn[tid].template store<ALL_SLOTS>(cnt, ~0u, i, tid, 0u, 0u, wA, wB);
-          else cn[tid].template store<PREDICATED>(cnt, ~0u, i, tid, 0u, 0u, wA, wB);
-          st(tid, wA, wB);
+          uint32_t w[NSW];
+          ld(tid, w);
+          cn[tid].begin(post.data(), w);
+          cn[tid].load(peb, pes, 0, cnt, i, tid, s.K, s.q, cnt == CNL);
+          cn[tid].store(0, cnt, i, tid, cnt == CNL, w);
+          st(tid, w);
         }
       } else {
-        const uint32_t sh = s.shared[i];
+        const int ns = s.ns[i];
         const uint8_t* level = s.level.data() + (size_t)s.conflict_index[i] * 360;
-        std::vector<CheckNodePair<CNL>> cn(360);
-        std::vector<uint32_t> negA(360, 0), negB(360, 0);
         for (int tid = 0; tid < 360; ++tid) {
-          uint32_t wA[NS], wB[NS];
-          ld(tid, wA, wB);
-          cn[tid].begin(post.data(), wA, wB);
-          cn[tid].template load<PREDICATED>(peb, pes, cnt, ~sh, i, tid, s.K, s.q);
+          uint32_t w[NSW];
+          ld(tid, w);
+          cn[tid].begin(post.data(), w);
+          cn[tid].load(peb, pes, ns, cnt, i, tid, s.K, s.q, false);
         }
-        if (__builtin_popcount(sh) == 2) {
+        if (ns == 2) {
           // the chain walk of ldpc_decode_kernel, phase by phase (barriers between the loops)
-          const int cA = __builtin_ffs(sh) - 1, cB = 31 - __builtin_clz(sh);
-          int D = (int)pes[cA] - (int)pes[cB];
-          D += D < 0 ? 360 : 0;
-          const bool fwd = D <= 180;
-          const int step = fwd ? D : 360 - D;
-          const int slotO = fwd ? cA : cB, slotI = fwd ? cB : cA;
-          const int esO = pes[slotO], ebO = peb[slotO], esI = pes[slotI], ebI = peb[slotI];
-          std::vector<uint32_t> walk(360 * kWalkWords, 0), nI(360), nO(360), vI(360), vO(360), carry(360, 0);
+          const int step = mod360((int)pes[1] + 360 - (int)pes[0]);
+          std::vector<uint32_t> walk(360 * kWalkWords, 0), nI(360), vO(360), carry(360, 0);
           std::vector<post_ref> rI(360), rO(360);
           for (int tid = 0; tid < 360; ++tid) {
-            nI[tid] = cn[tid].stored_neg_rt(slotI); nO[tid] = cn[tid].stored_neg_rt(slotO);
-            rI[tid] = cn[tid].post_ref_at(mod360(tid + esI) + ebI); rO[tid] = cn[tid].post_ref_at(mod360(tid + esO) + ebO);
+            nI[tid] = cn[tid].template stored_neg<0>();
+            rI[tid] = cn[tid].template slot_ref<0>(peb, pes, tid); rO[tid] = cn[tid].template slot_ref<1>(peb, pes, tid);
           }
           for (int tid = 0; tid < step; ++tid) {                                 // heads
-            vI[tid] = sat8_add(unpack_post(post_ld(rI[tid])), nI[tid]);
-            vO[tid] = sat8_add(unpack_post(post_ld(rO[tid])), nO[tid]);
-            cn[tid].take(vI[tid], slotI); cn[tid].take(vO[tid], slotO);
-            uint32_t m0, m1, idn, gI, gO;
-            cn[tid].minima(m0, m1, idn);
-            const CnCore c = cn[tid].core();
-            post_st(rI[tid], pack_post(core_out(c, slotI, vI[tid], m0, m1, idn, gI)));
-            carry[tid] = core_out(c, slotO, vO[tid], m0, m1, idn, gO);
-            post_st(rO[tid], pack_post(carry[tid]));
-            negA[tid] = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
-            negB[tid] = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
+            cn[tid].template edge_in_value<0>(sat8_add(unpack_post(post_ld(rI[tid])), nI[tid]));
+            cn[tid].template edge_in_value<1>(sat8_add(unpack_post(post_ld(rO[tid])), cn[tid].template stored_neg<1>()));
+            const CnOut o = cn[tid].minima();
+            cn[tid].template edge_out<0>(o, true, true);
+            carry[tid] = cn[tid].template edge_out<1>(o, true, true);
           }
           for (int tid = step; tid < 360; ++tid) {                               // barrier; the others park what the walker needs
-            vO[tid] = sat8_add(unpack_post(post_ld(rO[tid])), nO[tid]);
-            uint32_t* st = walk.data() + tid * kWalkWords;
-            const CnCore c = cn[tid].core();
-            st[0] = (c.key0 >> 5) & 0x07ff07ffu; st[1] = c.sx; st[2] = vO[tid]; st[3] = nI[tid];
+            vO[tid] = sat8_add(unpack_post(post_ld(rO[tid])), cn[tid].template stored_neg<1>());
+            const CnOut o = cn[tid].minima();
+            uint32_t* w = walk.data() + tid * kWalkWords;
+            w[0] = o.A1 ^ o.D; w[1] = o.NA1 ^ o.ND; w[2] = o.sx; w[3] = vO[tid]; w[4] = nI[tid];
           }
           for (int tid = 0; tid < step; ++tid)                                   // barrier; the walk
             for (int j = tid + step; j < 360; j += step) {
-              uint32_t* st = walk.data() + j * kWalkWords;
-              const uint32_t w0 = st[0], w1 = st[1], w2 = st[2], w3 = st[3];
-              st[0] = carry[tid];
-              carry[tid] = walk_carry(carry[tid], w0, w1, w2, w3);
+              uint32_t* w = walk.data() + j * kWalkWords;
+              w[5] = carry[tid];
+              carry[tid] = walk_carry(carry[tid], w[0], w[1], w[2], w[3], w[4]);
             }
           for (int tid = step; tid < 360; ++tid) {                               // barrier; everybody finishes its own check node
-            vI[tid] = sat8_add(walk[tid * kWalkWords], nI[tid]);
-            cn[tid].take(vI[tid], slotI); cn[tid].take(vO[tid], slotO);
-            uint32_t m0, m1, idn, gI, gO;
-            cn[tid].minima(m0, m1, idn);
-            const CnCore c = cn[tid].core();
-            post_st(rI[tid], pack_post(core_out(c, slotI, vI[tid], m0, m1, idn, gI)));
-            const uint32_t pO = core_out(c, slotO, vO[tid], m0, m1, idn, gO);
-            if (tid + step >= 360) post_st(rO[tid], pack_post(pO));
-            negA[tid] = ((gI & 1u) << slotI) | ((gO & 1u) << slotO);
-            negB[tid] = ((gI >> 16) << slotI) | ((gO >> 16) << slotO);
+            cn[tid].template edge_in_value<0>(sat8_add(walk[tid * kWalkWords + 5], nI[tid]));
+            cn[tid].template edge_in_value<1>(vO[tid]);
+            const CnOut o = cn[tid].minima();
+            cn[tid].template edge_out<0>(o, true, true);
+            cn[tid].template edge_out<1>(o, true, tid + step >= 360);
           }
         } else {
           for (int l = 1; l <= nl; ++l) {
-            std::vector<uint32_t> m0(360), m1(360), idn(360);
+            // threads of one level: all reads, then all writes (they do not share bits with each other)
+            std::vector<CnOut> o(360);
             for (int tid = 0; tid < 360; ++tid)
               if (level[tid] == l) {
-                cn[tid].template shared_load_generic<0>(peb, pes, sh, tid);
-                cn[tid].minima(m0[tid], m1[tid], idn[tid]);
+                cn[tid].template shared_load<0>(peb, pes, ns, tid);
+                o[tid] = cn[tid].minima();
               }
             for (int tid = 0; tid < 360; ++tid)
-              if (level[tid] == l) cn[tid].template shared_store_generic<0>(sh, m0[tid], m1[tid], idn[tid], negA[tid], negB[tid]);
+              if (level[tid] == l) cn[tid].template shared_store<0>(o[tid], ns);
           }
         }
         for (int tid = 0; tid < 360; ++tid) {
-          uint32_t wA[NS], wB[NS];
-          cn[tid].template store<PREDICATED>(cnt, ~sh, i, tid, negA[tid], negB[tid], wA, wB);
-          st(tid, wA, wB);
+          uint32_t w[NSW];
+          cn[tid].store(ns, cnt, i, tid, false, w);
+          st(tid, w);
         }
       }
     }
