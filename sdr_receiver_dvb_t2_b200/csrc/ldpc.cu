@@ -57,12 +57,13 @@ struct LdpcParams {
   unsigned* err_flag;                 // set when a lock-step wait timed out (the host turns it into T2B200_ERR_CUDA)
   int n_cw, group_lanes, max_trials; unsigned flags;
   int N, K, q, k_out;
-  // CN (i,j) data edge c reads posterior eb + (j + es) mod 360
-  uint16_t eb[kMaxEdgeWords];         // [q][CNL]: 360 * bit-group
-  uint16_t es[kMaxEdgeWords];         // [q][CNL]: cyclic shift
+  // CN (i,j) data edge c reads posterior 360 eg + (j + es2 / 2) mod 360
+  uint16_t eg[kMaxEdgeWords];         // [q][CNL]: bit-group
+  uint16_t es2[kMaxEdgeWords];        // [q][CNL]: 2 x cyclic shift (byte offset in the interleaved posteriors)
   int16_t cidx[kMaxLayers];           // row of level[] for layers with shared bits
   uint8_t cnt[kMaxLayers], nlev[kMaxLayers];
   uint8_t ns[kMaxLayers];             // per layer: slots 0 .. ns-1 read a bit another check node of the layer also uses
+  uint8_t sync_after[kMaxLayers];     // per layer: the next layer touches a bit-group written since the last barrier
 };
 static_assert(sizeof(LdpcParams) <= 4000, "kernel parameter block");
 
@@ -140,7 +141,7 @@ __device__ __forceinline__ int syndrome_bad(const uint16_t* __restrict__ post, u
 #pragma unroll
     for (int c = 0; c < CNL; ++c)
       if (c < cnt) {
-        const int sh = (int)p.es[i * CNL + c], base = (int)p.eb[i * CNL + c];
+        const int sh = (int)p.es2[i * CNL + c] >> 1, base = 360 * (int)p.eg[i * CNL + c];
         int o = 32 * w + sh;
         if (o >= 360) o -= 360;
         uint32_t r = bits32(hb, base + o);
@@ -318,18 +319,25 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
         }
         const int cnt = p.cnt[i];
         const int nl = p.nlev[i];
-        const uint16_t* eb = p.eb + i * CNL;
-        const uint16_t* es = p.es + i * CNL;
+        const uint16_t* eb = p.eg + i * CNL;
+        const uint16_t* es = p.es2 + i * CNL;
         CheckNodePair<CNL> cn;
         if (nl == 1) {
           if (owner) {
             cn.begin(post, w);
-            cn.load(eb, es, 0, cnt, i, tid, p.K, p.q, cnt == CNL);
-            cn.store(0, cnt, i, tid, cnt == CNL, w);
+            if (cnt == CNL) {
+              cn.template load<true>(eb, es, 0, cnt, i, tid, p.K, p.q);
+              cn.template store<true>(0, cnt, i, tid, w);
+            } else {
+              cn.template load<false>(eb, es, 0, cnt, i, tid, p.K, p.q);
+              cn.template store<false>(0, cnt, i, tid, w);
+            }
 #pragma unroll
             for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
           }
-          __syncthreads();
+          // Layers whose data bit-groups are disjoint need no barrier between them (the parity bit a check node shares
+          // with the next layer is read by the thread that wrote it).
+          if (p.sync_after[i]) __syncthreads();
         } else {
           // Two check nodes of this layer use the same bit: the reference runs j = 0..359 serially, so
           // the smaller j must finish that bit first.  Private edges go in parallel (before / after),
@@ -337,7 +345,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
           const int ns = p.ns[i];
           if (owner) {
             cn.begin(post, w);
-            cn.load(eb, es, ns, cnt, i, tid, p.K, p.q, false);
+            cn.template load<false>(eb, es, ns, cnt, i, tid, p.K, p.q);
           }
           if (ns == 2) {
             // One pair of slots reads the same bit-group (the common case): slot 1 of check node j is slot 0 of check node
@@ -347,7 +355,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
             // run: first every run head is done (they depend on nothing), then -- one barrier later -- each walker goes down
             // its run with the handed-over posterior in a register; what it needs from the other check nodes is parked in
             // shared memory.
-            const int step = mod360((int)es[1] + 360 - (int)es[0]);
+            const int step = mod360(((int)es[1] >> 1) + 360 - ((int)es[0] >> 1));
             const bool head = tid < step, sink = tid + step >= 360;
             uint32_t nI = 0, vO = 0, carry = 0;
             post_ref rI = 0, rO = 0;
@@ -365,9 +373,9 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
             __syncthreads();
             if (owner && !head) {                                                // what the walker needs from the others
               vO = sat8_add(unpack_post(post_ld(rO)), cn.template stored_neg<1>());   // (a run's last check node reads the bit a head just wrote)
-              const CnOut o = cn.minima();                                       // of the private edges only: o.A1 ^ o.D = their candidate
+              const CnMags m = cn.mags();                                        // of the private edges only
               uint4 a;
-              a.x = o.A1 ^ o.D; a.y = o.NA1 ^ o.ND; a.z = o.sx; a.w = vO;
+              a.x = m.A0; a.y = m.NA0; a.z = cn.sx; a.w = vO;
               *reinterpret_cast<uint4*>(walk + tid * kWalkWords) = a;
               walk[tid * kWalkWords + 4] = nI;
             }
@@ -408,11 +416,11 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
             }
           }
           if (owner) {
-            cn.store(ns, cnt, i, tid, false, w);
+            cn.template store<false>(ns, cnt, i, tid, w);
 #pragma unroll
             for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
           }
-          __syncthreads();
+          if (p.sync_after[i]) __syncthreads();
         }
       }
       ++iters;
@@ -516,11 +524,23 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
     for (int c = 0; c < s.cnl_max; ++c) {
       const uint32_t e = s.edge[(size_t)i * s.cnl_max + c];
       const int shift = e ? 360 - (int)(e >> 16) : 0;              // edge word: 360*g + shift | (360 - shift) << 16
-      p.es[i * d->cnl + c] = (uint16_t)shift;
-      p.eb[i * d->cnl + c] = (uint16_t)((e & 0xffffu) - shift);
+      p.es2[i * d->cnl + c] = (uint16_t)(2 * shift);
+      p.eg[i * d->cnl + c] = (uint16_t)(((e & 0xffffu) - shift) / 360);
     }
     p.ns[i] = s.ns[i]; p.cidx[i] = s.conflict_index[i]; p.cnt[i] = s.cnt[i]; p.nlev[i] = s.nlev[i];
     if (s.ns[i] > 10) { delete d; ctx->err = "LDPC layer with more than 10 shared edges"; return T2B200_ERR_ARG; }
+  }
+  {
+    // a barrier is needed before a layer that touches a bit-group some layer has touched since the last barrier
+    std::vector<char> dirty(s.K / 360 + 1, 0);
+    for (int i = 0; i < s.q; ++i) {
+      bool need = false;
+      for (int c = 0; c < s.cnt[i]; ++c) need = need || dirty[p.eg[i * d->cnl + c]];
+      if (i) p.sync_after[i - 1] = need;
+      if (need) std::fill(dirty.begin(), dirty.end(), 0);
+      for (int c = 0; c < s.cnt[i]; ++c) dirty[p.eg[i * d->cnl + c]] = 1;
+    }
+    p.sync_after[s.q - 1] = 1;                                  // the parity test reads everything
   }
   std::vector<uint8_t> level = s.level; if (level.empty()) level.resize(360, 1);
   cudaError_t ce = cudaMalloc(&d->d_level, level.size());

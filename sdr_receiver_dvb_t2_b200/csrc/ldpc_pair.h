@@ -29,12 +29,17 @@
 
 namespace t2pair {
 
+#if defined(__CUDACC__)
+__constant__ uint32_t kFmaMinus1 = 0xffffffffu;          // see not_fma()
+#endif
+
 // ---- the handful of machine operations everything below is written in -------------------------------------------------
 #if defined(__CUDA_ARCH__)
 T2_HD uint32_t vaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }   // min(a + b, c) per half
 T2_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }   // max(a + b, c) per half
 T2_HD uint32_t vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 T2_HD uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+T2_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 // prmt.b32 with a selector known at compile time; selector nibbles with bit 3 set replicate the sign of the selected byte
 template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b)
 {
@@ -42,18 +47,16 @@ template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b)
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
   return r;
 }
-// bitwise complement as a multiply-add (-x - 1): issues on the FMA pipe, the ALU pipe is the decoder's bottleneck
-T2_HD uint32_t not_fma(uint32_t x)
-{
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, 0xffffffff, 0xffffffff;" : "=r"(r) : "r"(x));
-  return r;
-}
+// Bitwise complement as a multiply-add, x * (-1) + (-1): issues on the FMA pipe -- the ALU pipe is the decoder's
+// bottleneck.  The -1 comes from constant memory so that ptxas cannot turn the IMAD back into an ALU instruction.
+__device__ __forceinline__ uint32_t not_fma(uint32_t x) { return x * kFmaMinus1 + kFmaMinus1; }
 T2_HD int mod360(int t) { return (int)__viaddmin_u32((unsigned)t, 0xfffffe98u, (unsigned)t); }    // t in [0, 720): t mod 360
+T2_HD uint32_t mod720(uint32_t t) { return __viaddmin_u32(t, 0xfffffd30u, t); }                       // t in [0, 1440): t mod 720
 // the pair's posteriors by 32-bit shared-memory address (kept in a register from the load to the store of an edge)
 typedef uint32_t post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return (uint32_t)__cvta_generic_to_shared(post); }
 T2_HD post_ref post_at(post_ref base, int a) { return base + 2u * (uint32_t)a; }
+T2_HD post_ref post_at_bytes(post_ref base, uint32_t b) { return base + b; }
 T2_HD uint32_t post_ld(post_ref r) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(r) : "memory"); return v; }
 T2_HD void post_st(post_ref r, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r), "r"(v) : "memory"); }
 #else
@@ -72,6 +75,7 @@ T2_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c)
 }
 T2_HD uint32_t vmin2(uint32_t a, uint32_t b) { return pk16(imin(lo16(a), lo16(b)), imin(hi16(a), hi16(b))); }
 T2_HD uint32_t vmax2(uint32_t a, uint32_t b) { return pk16(imax(lo16(a), lo16(b)), imax(hi16(a), hi16(b))); }
+T2_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vmax2(a, b), c); }
 T2_HD uint32_t prmt_any(uint32_t a, uint32_t b, uint32_t sel)
 {
   const uint64_t src = ((uint64_t)b << 32) | a;
@@ -87,9 +91,11 @@ T2_HD uint32_t prmt_any(uint32_t a, uint32_t b, uint32_t sel)
 template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b) { return prmt_any(a, b, SEL); }
 T2_HD uint32_t not_fma(uint32_t x) { return ~x; }
 T2_HD int mod360(int t) { return t >= 360 ? t - 360 : t; }
+T2_HD uint32_t mod720(uint32_t t) { return t >= 720 ? t - 720 : t; }
 typedef uint16_t* post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return post; }
 T2_HD post_ref post_at(post_ref base, int a) { return base + a; }
+T2_HD post_ref post_at_bytes(post_ref base, uint32_t b) { return base + b / 2; }
 T2_HD uint32_t post_ld(post_ref r) { return *r; }
 T2_HD void post_st(post_ref r, uint32_t v) { *r = (uint16_t)v; }
 #endif
@@ -114,22 +120,32 @@ template <int CNL> struct CnLayout {
   static constexpr int NSW = (SLOTS + 1) / 2;
 };
 
-// what the outgoing messages of a check node are made from: the smallest magnitude a0 (for the compare by value), the
-// two candidate message magnitudes after the offset and the clamp (A1: for the input that attains the minimum, A0 = A1 ^ D
-// for the others) and their negatives
-struct CnOut { uint32_t a0, A1, D, NA1, ND, sx; };
+// what the outgoing messages of a check node are made from: the smallest magnitude a0 (for the compare by value) and the
+// two candidate messages after the offset and the clamp -- P1 for an input that attains the minimum, P0 = P1 ^ D for the
+// others -- with the sign the message has when the input itself is positive (the product of ALL input signs), and their
+// negatives N1 / N0 = N1 ^ ND for a negative input
+struct CnOut { uint32_t a0, P1, D, N1, ND; };
 
-// the two candidates from the two largest negated magnitudes n0 >= n1 (<= 0; kIdleN when there is no second input)
+// the raw candidates from the two largest negated magnitudes n0 >= n1 (<= 0; kIdleN when there is no second input)
+struct CnMags { uint32_t A0, A1, NA0, NA1; };
+T2_HD CnMags cn_mags(uint32_t n0, uint32_t n1)
+{
+  CnMags m;
+  m.A0 = vmin2(vmax2(not_fma(n0), 0u), kC126);                              // vqsub(vqabs(v), 1), at most 126
+  m.A1 = vmin2(vmax2(not_fma(n1), 0u), kC126);
+  m.NA0 = vmin2(vaddmax(n0, kOne2, kM126), 0u);                             // -A0
+  m.NA1 = vmin2(vaddmax(n1, kOne2, kM126), 0u);
+  return m;
+}
 T2_HD CnOut cn_minima(uint32_t n0, uint32_t n1, uint32_t sx)
 {
+  const CnMags m = cn_mags(n0, n1);
+  const uint32_t sg = sign_mask2(sx);
   CnOut o;
-  const uint32_t c0 = not_fma(n0), c1 = not_fma(n1);                       // |v| - 1
-  const uint32_t A0 = vmin2(vmax2(c0, 0u), kC126);                          // vqsub(vqabs(v), 1), at most 126
-  o.A1 = vmin2(vmax2(c1, 0u), kC126);
-  o.a0 = vaddmax(c0, kOne2, kIdleN);                                        // -n0
-  const uint32_t NA0 = vmin2(vaddmax(n0, kOne2, kM126), 0u);                // -A0
-  o.NA1 = vmin2(vaddmax(n1, kOne2, kM126), 0u);
-  o.D = A0 ^ o.A1; o.ND = NA0 ^ o.NA1; o.sx = sx;
+  o.a0 = vaddmax(not_fma(n0), kOne2, kIdleN);                               // -n0
+  const uint32_t P0 = pick(m.A0, m.NA0, sg), N0 = pick(m.NA0, m.A0, sg);
+  o.P1 = pick(m.A1, m.NA1, sg); o.N1 = pick(m.NA1, m.A1, sg);
+  o.D = P0 ^ o.P1; o.ND = N0 ^ o.N1;
   return o;
 }
 // One edge out: input v (n = -|v|) -> new posterior pair (vqadd of v and the check node's message) and `nm`, what is
@@ -137,10 +153,9 @@ T2_HD CnOut cn_minima(uint32_t n0, uint32_t n1, uint32_t sx)
 T2_HD uint32_t cn_edge_out(const CnOut& o, uint32_t v, uint32_t n, uint32_t& nm)
 {
   const uint32_t mask = vaddmax(n, o.a0, kMinus1);           // 0: this input attains the minimum, -1: it does not
-  const uint32_t F = o.A1 ^ (o.D & mask), NF = o.NA1 ^ (o.ND & mask);
-  const uint32_t neg = sign_mask2(o.sx ^ v);                 // product of the OTHER inputs' signs is negative
-  const uint32_t msg = pick(F, NF, neg);
-  nm = vmax2(vmin2(F ^ NF ^ msg, 0x00200020u), 0xffe1ffe1u);
+  const uint32_t P = o.P1 ^ (o.D & mask), N = o.N1 ^ (o.ND & mask);
+  const uint32_t msg = pick(P, N, sign_mask2(v));            // sign = product of the OTHER inputs' signs
+  nm = vmax2(vmin2(P ^ N ^ msg, 0x00200020u), 0xffe1ffe1u);
   return sat8_add(v, msg);
 }
 T2_HD uint32_t nabs2(uint32_t v) { return vaddmin(not_fma(v), kOne2, v); }                             // min(-v, v)
@@ -192,15 +207,30 @@ struct CheckNodePair {
     n0 = vmax2(n0, nn);
     sx ^= active ? vv : 0u;
   }
+  // two inputs at once: five min / max instructions instead of six
+  T2_HD void take2(uint32_t va, uint32_t na, uint32_t vb, uint32_t nb)
+  {
+    const uint32_t hi = vmax2(na, nb), lo = vmin2(na, nb);
+    n1 = vmax3(n1, vmin2(n0, hi), lo);
+    n0 = vmax2(n0, hi);
+    sx ^= va ^ vb;
+  }
   // `active` false: the slot does not take part (it is computed and discarded, branch-free, so that the loads of a layer
   // still issue back to back)
-  template <int SLOT> T2_HD void edge_in(int a, bool active)
+  template <int SLOT> T2_HD void edge_read(post_ref r)
   {
-    const post_ref r = post_at(post, a);
     const uint32_t vv = sat8_add(unpack_post(post_ld(r)), stored_neg<SLOT>());         // vqsub(posterior, stored message)
-    const uint32_t nn = nabs2(vv);
-    v[SLOT] = vv; n[SLOT] = nn; adr[SLOT] = r;
-    take(vv, nn, active);
+    v[SLOT] = vv; n[SLOT] = nabs2(vv); adr[SLOT] = r;
+  }
+  template <int SLOT> T2_HD void edge_in(post_ref r, bool active)
+  {
+    edge_read<SLOT>(r);
+    take(v[SLOT], n[SLOT], active);
+  }
+  // data slot C of check node j (j2 = 2 j): bit-group eg, cyclic shift es2 / 2 -> byte offset 720 eg + (2 j + es2) mod 720
+  template <int C> T2_HD post_ref data_ref(const uint16_t* eg, const uint16_t* es2, uint32_t j2) const
+  {
+    return post_at_bytes(post, (uint32_t)eg[C] * 720u + mod720(j2 + (uint32_t)es2[C]));
   }
   // input of a slot that arrives in a register (chain walk)
   template <int SLOT> T2_HD void edge_in_value(uint32_t vv)
@@ -209,12 +239,13 @@ struct CheckNodePair {
     v[SLOT] = vv; n[SLOT] = nn;
     take(vv, nn);
   }
-  template <int SLOT> T2_HD post_ref slot_ref(const uint16_t* eb, const uint16_t* es, int j)
+  template <int SLOT> T2_HD post_ref slot_ref(const uint16_t* eg, const uint16_t* es2, int j)
   {
-    adr[SLOT] = post_at(post, mod360(j + (int)es[SLOT]) + (int)eb[SLOT]);
+    adr[SLOT] = data_ref<SLOT>(eg, es2, 2u * (uint32_t)j);
     return adr[SLOT];
   }
   T2_HD CnOut minima() const { return cn_minima(n0, n1, sx); }
+  T2_HD CnMags mags() const { return cn_mags(n0, n1); }
   // write the edge back (when `store`) and leave what is stored for the next iteration in v[SLOT]
   template <int SLOT> T2_HD uint32_t edge_out(const CnOut& o, bool active, bool store)
   {
@@ -224,35 +255,52 @@ struct CheckNodePair {
     v[SLOT] = active ? nm : 0u;
     return np;
   }
-  // data slots lo <= C < hi, in order
-  template <int C> T2_HD void load_from(const uint16_t* eb, const uint16_t* es, int lo, int hi, int j, bool all)
+  // data slots lo <= C < hi (ALL: every slot, known at compile time): all the reads first, then the running minima two
+  // inputs at a time
+  template <bool ALL, int C> T2_HD void read_from(const uint16_t* eg, const uint16_t* es2, uint32_t j2)
   {
     if constexpr (C < CNL) {
-      edge_in<C>(mod360(j + (int)es[C]) + (int)eb[C], all || (C >= lo && C < hi));      // eb + (j + es) mod 360
-      load_from<C + 1>(eb, es, lo, hi, j, all);
+      edge_read<C>(data_ref<C>(eg, es2, j2));
+      read_from<ALL, C + 1>(eg, es2, j2);
     }
   }
-  // the private edges: data slots lo .. cnt-1 and the two parity slots (`all`: lo = 0 and cnt = CNL, known to the caller)
-  T2_HD void load(const uint16_t* eb, const uint16_t* es, int lo, int cnt, int i, int j, int K, int q, bool all)
+  template <bool ALL, int C> T2_HD void reduce_from(int lo, int hi, bool lastB)
   {
-    load_from<0>(eb, es, lo, cnt, j, all);
-    edge_in<CNL>(K + 360 * i + j, true);
-    const bool hasB = (i | j) != 0;
-    edge_in<CNL + 1>(i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + (hasB ? j - 1 : 0), hasB);
+    if constexpr (C + 1 < SLOTS) {
+      if (ALL && C + 1 < CNL) take2(v[C], n[C], v[C + 1], n[C + 1]);
+      else {
+        take(v[C], n[C], C >= CNL ? true : (ALL || (C >= lo && C < hi)));
+        take(v[C + 1], n[C + 1], C + 1 == CNL + 1 ? lastB : C + 1 == CNL ? true : (ALL || (C + 1 >= lo && C + 1 < hi)));
+      }
+      reduce_from<ALL, C + 2>(lo, hi, lastB);
+    } else if constexpr (C < SLOTS) {
+      take(v[C], n[C], C == CNL + 1 ? lastB : C == CNL ? true : (ALL || (C >= lo && C < hi)));
+    }
   }
-  template <int C> T2_HD void out_from(const CnOut& o, int lo, int hi, bool all)
+  // the private edges: data slots lo .. cnt-1 and the two parity slots (ALL: lo = 0 and cnt = CNL)
+  template <bool ALL>
+  T2_HD void load(const uint16_t* eg, const uint16_t* es2, int lo, int cnt, int i, int j, int K, int q)
+  {
+    read_from<ALL, 0>(eg, es2, 2u * (uint32_t)j);
+    edge_read<CNL>(post_at(post, K + 360 * i + j));
+    const bool hasB = (i | j) != 0;
+    edge_read<CNL + 1>(post_at(post, i ? K + 360 * (i - 1) + j : K + 360 * (q - 1) + (hasB ? j - 1 : 0)));
+    reduce_from<ALL, 0>(lo, cnt, hasB);
+  }
+  template <bool ALL, int C> T2_HD void out_from(const CnOut& o, int lo, int hi)
   {
     if constexpr (C < CNL) {
-      const bool on = all || (C >= lo && C < hi);
-      if (all || C >= lo) edge_out<C>(o, on, true);                    // (slots below lo were written earlier: v[C] holds their stored value)
-      out_from<C + 1>(o, lo, hi, all);
+      const bool on = ALL || (C >= lo && C < hi);
+      if (ALL || C >= lo) edge_out<C>(o, on, true);                    // (slots below lo were written earlier: v[C] holds their stored value)
+      out_from<ALL, C + 1>(o, lo, hi);
     }
   }
   // Write the private edges back and pack what is stored.
-  T2_HD void store(int lo, int cnt, int i, int j, bool all, uint32_t (&w_)[NSW])
+  template <bool ALL>
+  T2_HD void store(int lo, int cnt, int i, int j, uint32_t (&w_)[NSW])
   {
     const CnOut o = minima();
-    out_from<0>(o, lo, cnt, all);
+    out_from<ALL, 0>(o, lo, cnt);
     edge_out<CNL>(o, true, true);
     edge_out<CNL + 1>(o, (i | j) != 0, true);
     pack(w_);
@@ -263,12 +311,12 @@ struct CheckNodePair {
     for (int k = 0; k < NSW; ++k) w_[k] = prmt<0x6420u>(v[2 * k], 2 * k + 1 < SLOTS ? v[2 * k + 1] : 0u);
   }
   // ---- shared slots 0 .. ns-1 of a layer resolved level by level ----
-  template <int C> T2_HD void shared_load(const uint16_t* eb, const uint16_t* es, int ns, int j)
+  template <int C> T2_HD void shared_load(const uint16_t* eg, const uint16_t* es2, int ns, int j)
   {
     if constexpr (C < CNL && C < 10) {
       if (C < ns) {
-        edge_in<C>(mod360(j + (int)es[C]) + (int)eb[C], true);
-        shared_load<C + 1>(eb, es, ns, j);
+        edge_in<C>(data_ref<C>(eg, es2, 2u * (uint32_t)j), true);
+        shared_load<C + 1>(eg, es2, ns, j);
       }
     }
   }

@@ -29,9 +29,9 @@ bool lane_bad(const LdpcSchedule& s, const std::vector<uint16_t>& post, int lane
       if (i) use(s.K + 360 * (i - 1) + j);
       else if (j) use(s.K + 360 * (s.q - 1) + j - 1);
       for (int c = 0; c < s.cnt[i]; ++c) {
-        int t = j + es[i * cnl + c];
+        int t = j + es[i * cnl + c] / 2;
         if (t >= 360) t -= 360;
-        use(t + eb[i * cnl + c]);
+        use(t + 360 * eb[i * cnl + c]);
       }
       if (zero || neg) return true;
     }
@@ -49,8 +49,8 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
     for (int c = 0; c < s.cnl_max; ++c) {
       const uint32_t e = s.edge[(size_t)i * s.cnl_max + c];
       const int shift = e ? 360 - (int)(e >> 16) : 0;
-      es[i * CNL + c] = (uint16_t)shift;
-      eb[i * CNL + c] = (uint16_t)((e & 0xffffu) - shift);
+      es[i * CNL + c] = (uint16_t)(2 * shift);                                  // the kernel's tables: 2 x shift, bit-group
+      eb[i * CNL + c] = (uint16_t)(((e & 0xffffu) - shift) / 360);
     }
   std::vector<uint16_t> post(s.N);
   for (int n = 0; n < s.N; ++n) post[n] = (uint16_t)((uint8_t)llrA[n] | ((uint16_t)(uint8_t)llrB[n] << 8));
@@ -73,8 +73,13 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
           uint32_t w[NSW];
           ld(tid, w);
           cn[tid].begin(post.data(), w);
-          cn[tid].load(peb, pes, 0, cnt, i, tid, s.K, s.q, cnt == CNL);
-          cn[tid].store(0, cnt, i, tid, cnt == CNL, w);
+          if (cnt == CNL) {
+            cn[tid].template load<true>(peb, pes, 0, cnt, i, tid, s.K, s.q);
+            cn[tid].template store<true>(0, cnt, i, tid, w);
+          } else {
+            cn[tid].template load<false>(peb, pes, 0, cnt, i, tid, s.K, s.q);
+            cn[tid].template store<false>(0, cnt, i, tid, w);
+          }
           st(tid, w);
         }
       } else {
@@ -84,11 +89,11 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
           uint32_t w[NSW];
           ld(tid, w);
           cn[tid].begin(post.data(), w);
-          cn[tid].load(peb, pes, ns, cnt, i, tid, s.K, s.q, false);
+          cn[tid].template load<false>(peb, pes, ns, cnt, i, tid, s.K, s.q);
         }
         if (ns == 2) {
           // the chain walk of ldpc_decode_kernel, phase by phase (barriers between the loops)
-          const int step = mod360((int)pes[1] + 360 - (int)pes[0]);
+          const int step = mod360(((int)pes[1] >> 1) + 360 - ((int)pes[0] >> 1));
           std::vector<uint32_t> walk(360 * kWalkWords, 0), nI(360), vO(360), carry(360, 0);
           std::vector<post_ref> rI(360), rO(360);
           for (int tid = 0; tid < 360; ++tid) {
@@ -104,9 +109,9 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
           }
           for (int tid = step; tid < 360; ++tid) {                               // barrier; the others park what the walker needs
             vO[tid] = sat8_add(unpack_post(post_ld(rO[tid])), cn[tid].template stored_neg<1>());
-            const CnOut o = cn[tid].minima();
+            const CnMags m = cn[tid].mags();
             uint32_t* w = walk.data() + tid * kWalkWords;
-            w[0] = o.A1 ^ o.D; w[1] = o.NA1 ^ o.ND; w[2] = o.sx; w[3] = vO[tid]; w[4] = nI[tid];
+            w[0] = m.A0; w[1] = m.NA0; w[2] = cn[tid].sx; w[3] = vO[tid]; w[4] = nI[tid];
           }
           for (int tid = 0; tid < step; ++tid)                                   // barrier; the walk
             for (int j = tid + step; j < 360; j += step) {
@@ -136,7 +141,7 @@ int decode_pair(const LdpcSchedule& s, const int8_t* llrA, const int8_t* llrB, i
         }
         for (int tid = 0; tid < 360; ++tid) {
           uint32_t w[NSW];
-          cn[tid].store(ns, cnt, i, tid, false, w);
+          cn[tid].template store<false>(ns, cnt, i, tid, w);
           st(tid, w);
         }
       }
