@@ -63,7 +63,7 @@ struct LdpcParams {
   int16_t cidx[kMaxLayers];           // row of level[] for layers with shared bits
   uint8_t cnt[kMaxLayers], nlev[kMaxLayers];
   uint8_t ns[kMaxLayers];             // per layer: slots 0 .. ns-1 read a bit another check node of the layer also uses
-  uint8_t sync_after[kMaxLayers];     // per layer: the next layer touches a bit-group written since the last barrier
+  uint8_t walked[kMaxLayers];         // per layer: one shared pair whose dependency runs are long enough to be walked
 };
 static_assert(sizeof(LdpcParams) <= 4000, "kernel parameter block");
 
@@ -164,6 +164,28 @@ __device__ __forceinline__ int syndrome_bad(const uint16_t* __restrict__ post, u
   const int n_tasks = p.q * 12;
   for (int t = tid; t < n_tasks; t += kThreads) bad |= word_check(hbA, t) | (word_check(hbB, t) << 1);
   return bad;
+}
+
+// A cheap sufficient test for "bad": the posteriors the LAST layer touched are final for the iteration, so the sign parity
+// of a check node of that layer is its parity check.  Thread j tests check node (q-1, j); bit 0 / 1: the check of codeword
+// A / B fails.  (A zero posterior also fails a check: that, and every other layer, is left to syndrome_bad when this test
+// finds nothing.)
+template <int CNL>
+__device__ __forceinline__ int last_layer_bad(const uint16_t* __restrict__ post, const LdpcParams& p)
+{
+  const int tid = threadIdx.x;
+  if (tid >= 360) return 0;
+  const int i = p.q - 1, cnt = p.cnt[i];
+  uint32_t x = post[p.K + 360 * i + tid];
+  x ^= i ? post[p.K + 360 * (i - 1) + tid] : (tid ? post[p.K + 360 * (p.q - 1) + tid - 1] : 0u);
+#pragma unroll
+  for (int c = 0; c < CNL; ++c)
+    if (c < cnt) {
+      int o = tid + ((int)p.es2[i * CNL + c] >> 1);
+      if (o >= 360) o -= 360;
+      x ^= post[360 * (int)p.eg[i * CNL + c] + o];
+    }
+  return (int)((x >> 7) & 1u) | (int)((x >> 14) & 2u);
 }
 
 // Register budget: one CTA per SM for the 64 800-bit codes (MINB = 1: 128 registers, so that a quarter of the register file
@@ -280,8 +302,15 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
     int trials = p.max_trials, iters = 0;
     int done = haveB ? 0 : 2;            // per-codeword mode: bit 0 / 1 set once codeword A / B has stopped and been written
     for (;;) {
-      const int mine = syndrome_bad<CNL>(post, hbA, hbB, p);
-      const int badA = __syncthreads_or(mine & 1), badB = __syncthreads_or(mine & 2);
+      int badA = 0, badB = 0;
+      if (iters > 0) {                                     // (the layer loop ended with a barrier)
+        const int quick = last_layer_bad<CNL>(post, p);
+        badA = __syncthreads_or(quick & 1); badB = __syncthreads_or(quick & 2);
+      }
+      if (lockstep ? !(badA | badB) : !(badA && badB)) {
+        const int mine = syndrome_bad<CNL>(post, hbA, hbB, p);
+        badA = __syncthreads_or(mine & 1); badB = __syncthreads_or(mine & 2);
+      }
       int go;
       if (lockstep) {
         if (tid == 0) {
@@ -335,9 +364,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
 #pragma unroll
             for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
           }
-          // Layers whose data bit-groups are disjoint need no barrier between them (the parity bit a check node shares
-          // with the next layer is read by the thread that wrote it).
-          if (p.sync_after[i]) __syncthreads();
+          __syncthreads();
         } else {
           // Two check nodes of this layer use the same bit: the reference runs j = 0..359 serially, so
           // the smaller j must finish that bit first.  Private edges go in parallel (before / after),
@@ -347,7 +374,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
             cn.begin(post, w);
             cn.template load<false>(eb, es, ns, cnt, i, tid, p.K, p.q);
           }
-          if (ns == 2) {
+          if (p.walked[i]) {
             // One pair of slots reads the same bit-group (the common case): slot 1 of check node j is slot 0 of check node
             // j + step, so the check nodes form runs j0, j0 + step, j0 + 2 step, ... (j0 < step) in which each one hands ONE
             // updated posterior to the next, and the last one of a run also shares a bit with the first one of another run.
@@ -420,7 +447,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
 #pragma unroll
             for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
           }
-          if (p.sync_after[i]) __syncthreads();
+          __syncthreads();
         }
       }
       ++iters;
@@ -529,18 +556,8 @@ static int get_code(t2b200_ctx* ctx, int code, LdpcDeviceCode** out)
     }
     p.ns[i] = s.ns[i]; p.cidx[i] = s.conflict_index[i]; p.cnt[i] = s.cnt[i]; p.nlev[i] = s.nlev[i];
     if (s.ns[i] > 10) { delete d; ctx->err = "LDPC layer with more than 10 shared edges"; return T2B200_ERR_ARG; }
-  }
-  {
-    // a barrier is needed before a layer that touches a bit-group some layer has touched since the last barrier
-    std::vector<char> dirty(s.K / 360 + 1, 0);
-    for (int i = 0; i < s.q; ++i) {
-      bool need = false;
-      for (int c = 0; c < s.cnt[i]; ++c) need = need || dirty[p.eg[i * d->cnl + c]];
-      if (i) p.sync_after[i - 1] = need;
-      if (need) std::fill(dirty.begin(), dirty.end(), 0);
-      for (int c = 0; c < s.cnt[i]; ++c) dirty[p.eg[i * d->cnl + c]] = 1;
-    }
-    p.sync_after[s.q - 1] = 1;                                  // the parity test reads everything
+    // (measured: the walk beats the level passes even for chains of three -- profiles/r02_ldpc_walk_threshold.txt)
+    p.walked[i] = s.ns[i] == 2;
   }
   std::vector<uint8_t> level = s.level; if (level.empty()) level.resize(360, 1);
   cudaError_t ce = cudaMalloc(&d->d_level, level.size());
