@@ -471,6 +471,15 @@ def run_t2b200(args):
         stream.synchronize()
         stage_ms = chain.stage_ms()
         chain.events = None
+        # ... and of the product path itself: the one-call frame pipeline alone on the GPU, events recorded by the library
+        eng.set_option(E.OPT_STAGE_TIMING, 1)
+        pipe_ms = {}
+        for i in range(5):
+            chain.decode_frames_fused(bufs[i % nbuf], want_status=False, out=outs[0])
+            for k, v in eng.frames_stage_ms().items():
+                pipe_ms.setdefault(k, []).append(v)
+        pipe_ms = {k: float(np.median(v)) for k, v in pipe_ms.items()}
+        eng.set_option(E.OPT_STAGE_TIMING, 0)
         eng2.close()
 
         # ---- LDPC stage alone on the LLRs of one batch (explains the chain number; roofline of the dominant kernel) ----
@@ -726,6 +735,12 @@ def run_t2b200(args):
                            'copies overlap the other\'s compute'},
             'gpu_launches': int(launches),
             'stages': stages,
+            'pipeline_stages': {'ms': {k: round(v, 4) for k, v in pipe_ms.items()},
+                                'bytes_per_cell': {'ti_deinterleave': 16, 'demap': 24},
+                                'note': 'device time of each stage inside one t2b200_frames_decode call running alone (events recorded by '
+                                        'the library, T2B200_OPT_STAGE_TIMING): derotation '
+                                        'folded into the time de-interleaver, demap = ordered sums (terms recomputed from the cells) + LLR pass; '
+                                        '"stages" above times the stand-alone stage entry points'},
             'ldpc_only': {'value': cw_step / (ldpc_ms * 1e-3), 'unit': 'codewords/s', 'ms': ldpc_ms,
                           'per_codeword_exit': {'value': cw_step / (native_ms * 1e-3), 'ms': native_ms,
                                                 'note': 'T2B200_LDPC_GROUP32 off: every codeword stops on its own'}},

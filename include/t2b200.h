@@ -76,7 +76,7 @@ const char* t2b200_version(void);
  * ~116, so the outer constellation levels always wrap and the reference's own LDPC stage cannot converge on
  * a clean AWGN signal (DESIGN.md "reference quirks").  1 = clamp to [-128,127] instead -- NOT bit-compatible
  * with the reference, provided so the engine is usable; parity tests run with 0.                         */
-enum { T2B200_OPT_DEMAP_SATURATE = 1, T2B200_OPT_LDPC_PLAIN_LAUNCH = 2, T2B200_OPT_BCH_CORRECT = 3 };
+enum { T2B200_OPT_DEMAP_SATURATE = 1, T2B200_OPT_LDPC_PLAIN_LAUNCH = 2, T2B200_OPT_BCH_CORRECT = 3, T2B200_OPT_STAGE_TIMING = 4 };
 /* T2B200_OPT_LDPC_PLAIN_LAUNCH (default 0): lock-step (GROUP32) decodes are launched cooperatively, which makes a decode
  * wait until the whole GPU is free.  1 = ordinary launch of the same grid: with TWO contexts on two streams taking turns
  * (bench.py, chain.py) the next decode starts on the SMs the previous one's last groups have left.  Do not run more than
@@ -85,6 +85,8 @@ enum { T2B200_OPT_DEMAP_SATURATE = 1, T2B200_OPT_LDPC_PLAIN_LAUNCH = 2, T2B200_O
 /* T2B200_OPT_BCH_CORRECT (default 0): the reference never decodes the BCH code ("TODO BCH decode", bch_decoder.cpp:136).
  * 1 = t2b200_frames_decode corrects up to t bit errors per BBFRAME (t2b200_bch_decode) between the LDPC stage and the
  * parity strip / descramble -- beyond the reference; off in every parity test.                                          */
+/* T2B200_OPT_STAGE_TIMING (default 0): 1 = t2b200_frames_decode brackets every stage with CUDA events on the context's
+ * stream; t2b200_frames_stage_ms reads the device times of the last call (it waits for that call to finish). */
 int t2b200_set_option(t2b200_ctx* ctx, int option, int value);
 /* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
 long long t2b200_launch_count(const t2b200_ctx* ctx);
@@ -275,6 +277,11 @@ int t2b200_frames_decode(t2b200_ctx* ctx, const float* iq, int n_frames, uint8_t
  * (dvbt2_demodulator.cpp:182-186, short_to_float = 2^-14 / 2^-12 / 2^-11 by device).  Half the bytes over PCIe and HBM. */
 int t2b200_frames_decode_i16(t2b200_ctx* ctx, const int16_t* iq, float scale, int n_frames, uint8_t* bits_out,
                              int32_t* trials_left, float* sro, float* phase, float* snr, int max_trials, unsigned ldpc_flags);
+/* Device time of every stage of the last t2b200_frames_decode[_i16] call made with T2B200_OPT_STAGE_TIMING on, in ms:
+ * [0] FFT, [1] equalise + frequency de-interleave, [2] time / cell de-interleave (+ derotation), [3] demap,
+ * [4] LDPC + BCH strip / descramble (+ opt-in BCH correction), [5] the whole call.  Measurement aid of bench.py. */
+int t2b200_frames_stage_ms(t2b200_ctx* ctx, float ms_out[6]);
+
 
 /* ---- multi-GPU: the LDPC / BCH stage sharded by codeword over the GPUs of one box --------------------- */
 /* FEC blocks are independent, so one rank demodulates (it holds the int8 LLRs of a pooled batch), every rank decodes a

@@ -174,6 +174,7 @@ int t2b200_set_option(t2b200_ctx* ctx, int option, int value)
   if (option == T2B200_OPT_DEMAP_SATURATE) { ctx->opt_demap_saturate = value != 0; return T2B200_OK; }
   if (option == T2B200_OPT_LDPC_PLAIN_LAUNCH) { ctx->opt_ldpc_plain_launch = value != 0; return T2B200_OK; }
   if (option == T2B200_OPT_BCH_CORRECT) { ctx->opt_bch_correct = value != 0; return T2B200_OK; }
+  if (option == T2B200_OPT_STAGE_TIMING) { ctx->opt_stage_timing = value != 0; return T2B200_OK; }
   ctx->err = "t2b200_set_option: unknown option";
   return T2B200_ERR_ARG;
 }

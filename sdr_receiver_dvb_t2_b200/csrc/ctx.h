@@ -33,6 +33,7 @@ struct t2b200_ctx {
   int opt_demap_saturate = 0;                 // T2B200_OPT_DEMAP_SATURATE
   int opt_ldpc_plain_launch = 0;              // T2B200_OPT_LDPC_PLAIN_LAUNCH
   int opt_bch_correct = 0;                    // T2B200_OPT_BCH_CORRECT
+  int opt_stage_timing = 0;                   // T2B200_OPT_STAGE_TIMING
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id
   float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes

@@ -11,10 +11,12 @@
 //                                    L0 = x, L1 = |x| - 8a, L2 = |L1| - 4a, L3 = |L2| - 2a (256-QAM; fewer for 64/16);
 //                                    round-to-nearest-even(L * precision); (int8) cast that WRAPS (QPSK saturates);
 //                                    store through address[] (:110-130)
-// B200 design: both stages are HBM-streaming permutations.  K3 is a coalesced read / scattered 4-byte
-// write pass whose working set (one TI block, <= 4.4 MB) lives in L2.  K4 runs one CTA per FECFRAME:
-// LLRs are produced into a 64.8 KB shared-memory image of the de-interleaved frame and leave the SM as
-// coalesced 16-byte stores, so the column-twist scatter never reaches HBM as byte writes.
+// B200 design: both stages are HBM-streaming permutations.  K3 is a gather pass (two 4-byte reads per output cell from the
+// L2-resident TI block, <= 4.4 MB, one coalesced 8-byte store) that also applies the demapper's derotation in the frame
+// pipeline, so the TI block is written once.  K4 is two passes over it: the order-dependent sums (one CTA per TI block and
+// sum, terms recomputed from the cells, nothing written but the sums) and the LLR pass, one CTA per FECFRAME: LLRs are
+// produced into a 64.8 KB shared-memory image of the de-interleaved frame and leave the SM as coalesced 16-byte stores, so
+// the column-twist scatter never reaches HBM as byte writes.  40 bytes of traffic per cell in all (was 72).
 #include "stages.h"
 #include "fec_tables.h"
 #include <algorithm>
@@ -43,9 +45,13 @@ constexpr float kNorm[4] = {0.707106781f, 0.316227766f, 0.15430335f, 0.076696499
 // memory cell that lands there, i.e. arrival index k = row * cols + column; the Q component comes from the cell that lands
 // on a + 1 (cyclic inside the FEC block).  Two coalesced table reads, two 4-byte gathers from the L2-resident TI block,
 // one coalesced 8-byte store -- no scattered stores.
+// ROT: the demapper's derotation (llr_demapper.cpp:555-557, _in[i] *= derotate) applied on the way out, so that the TI block
+// is written once, already derotated (frame pipeline; the stand-alone stage leaves the cells as the reference's
+// time_deinterleaver does).
+template <bool ROT>
 __global__ void ti_deinterleave_kernel(const float2* __restrict__ in, float2* __restrict__ out,
                                        const uint32_t* __restrict__ srcmap, const TiBlockDesc* __restrict__ blocks,
-                                       int rows, int cpf)
+                                       int rows, int cpf, float rc, float rs)
 {
   const TiBlockDesc b = blocks[blockIdx.y];
   const int cols = 5 * b.n_fec;
@@ -57,7 +63,9 @@ __global__ void ti_deinterleave_kernel(const float2* __restrict__ in, float2* __
     const int an = r == cpf - 1 ? a - (cpf - 1) : a + 1;
     const uint32_t s1 = __ldg(srcmap + a), s2 = __ldg(srcmap + an);
     const int k1 = (int)(s1 >> 16) * cols + (int)(s1 & 0xffffu), k2 = (int)(s2 >> 16) * cols + (int)(s2 & 0xffffu);
-    dst[a] = make_float2(__ldg(src + 2 * k1), __ldg(src + 2 * k2 + 1));
+    float2 v = make_float2(__ldg(src + 2 * k1), __ldg(src + 2 * k2 + 1));
+    if (ROT) v = make_float2(__fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs)), __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc)));
+    dst[a] = v;
   }
 }
 
@@ -95,29 +103,23 @@ __device__ __forceinline__ float slice_axis(float x, float a)
 
 
 // levels k*a must be the same floats the reference holds (norm_x_k = NORM * k.0f): computed as a*k in float.
-// Pass 1a: derotate in place + per-cell |s|^2 and |e|^2 of the hard decision, stored for the ordered sum.
+// (|s|^2, |e|^2) of the hard decision on one (derotated) cell: the two terms the reference accumulates
 template <int MOD>
-__global__ void demap_stats_kernel(float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
-                                   float2* __restrict__ terms, int rotate, float rc, float rs)
+__device__ __forceinline__ float2 demap_term(float2 v, float a)
+{
+  const float sx = slice_axis<MOD>(v.x, a), sy = slice_axis<MOD>(v.y, a);
+  const float ex = __fsub_rn(v.x, sx), ey = __fsub_rn(v.y, sy);
+  return make_float2(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+}
+
+// Pass 1a (stand-alone stage only): derotate in place, like the reference (llr_demapper.cpp:555-557), no FMA contraction
+__global__ void demap_derotate_kernel(float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks, float rc, float rs)
 {
   const DemapBlockDesc b = blocks[blockIdx.y];
   float2* c = cells + b.cell_off;
-  float2* t = terms + b.cell_off;
-  const float a = kNorm[MOD];
-  const int n_stat = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;      // llr_demapper.cpp:185
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < b.n_cells; k += gridDim.x * blockDim.x) {
-    float2 v = c[k];
-    if (rotate) {                       // _in[i] *= derotate (llr_demapper.cpp:555-557), no FMA contraction
-      const float re = __fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs));
-      const float im = __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc));
-      v = make_float2(re, im);
-      c[k] = v;
-    }
-    if (k < n_stat) {
-      const float sx = slice_axis<MOD>(v.x, a), sy = slice_axis<MOD>(v.y, a);
-      const float ex = __fsub_rn(v.x, sx), ey = __fsub_rn(v.y, sy);
-      t[k] = make_float2(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
-    }
+    const float2 v = c[k];
+    c[k] = make_float2(__fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs)), __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc)));
   }
 }
 
@@ -164,132 +166,130 @@ __device__ __forceinline__ int sum_apply(int S, uint32_t w)
   return min(S + q + (int)((w >> 30) & 1u) + (int)((w >> 31) & (uint32_t)(S + q) & 1u), kSumSat);
 }
 
+// One CTA per (TI block, sum): blockIdx.y = 0 accumulates |s|^2, 1 accumulates |e|^2 -- the two recurrences are independent.
+// The terms are recomputed from the (derotated) cells wherever they are needed; nothing but the two sums is written.
 template <int MOD>
-__global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const float2* __restrict__ terms,
+__global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const float2* __restrict__ cells,
                                                                          const DemapBlockDesc* __restrict__ blocks,
-                                                                         float* __restrict__ precision, float* __restrict__ snr,
-                                                                         const float* __restrict__ precision_in)
+                                                                         float* __restrict__ sums)
 {
-  __shared__ SumPair wt[2][kSumThreads / 32];      // warp totals
-  __shared__ float sh_s[2];
+  __shared__ SumPair wt[kSumThreads / 32];         // warp totals
+  __shared__ float sh_s;
   __shared__ int sh_cross[2];                      // first binade crossing of the pass (double-buffered by pass parity)
+  __shared__ float head[kSumSerialHead];
   int pass = 0;
+  const int which = blockIdx.y;
   const DemapBlockDesc b = blocks[blockIdx.x];
-  const float2* t = terms + b.cell_off;
-  const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;
+  const float2* c = cells + b.cell_off;
+  const float a = kNorm[MOD];
+  auto term = [&](int k) -> float {
+    const float2 t = demap_term<MOD>(__ldg(c + k), a);
+    return which ? t.y : t.x;
+  };
+  const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;           // llr_demapper.cpp:185
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ float2 head[kSumSerialHead];
   int base = min(n, kSumSerialHead);
-  for (int k = tid; k < base; k += kSumThreads) head[k] = __ldg(t + k);      // staged so that only the two FADD chains are serial
+  for (int k = tid; k < base; k += kSumThreads) head[k] = term(k);      // staged so that only the FADD chain is serial
   __syncthreads();
   if (tid == 0) {
-    float a = 0.0f, c = 0.0f;
+    float acc = 0.0f;
     int k = 0;
     for (; k + 8 <= base; k += 8) {
-      float2 v[8];
+      float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = head[k + u];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { a = __fadd_rn(a, v[u].x); c = __fadd_rn(c, v[u].y); }
+      for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
     }
-    for (; k < base; ++k) { a = __fadd_rn(a, head[k].x); c = __fadd_rn(c, head[k].y); }
-    sh_s[0] = a; sh_s[1] = c; sh_cross[0] = INT_MAX; sh_cross[1] = INT_MAX;
+    for (; k < base; ++k) acc = __fadd_rn(acc, head[k]);
+    sh_s = acc; sh_cross[0] = INT_MAX; sh_cross[1] = INT_MAX;
   }
   __syncthreads();
   while (base < n) {
-    const float s0 = sh_s[0], s1 = sh_s[1];
-    const uint32_t b0 = __float_as_uint(s0), b1 = __float_as_uint(s1);
-    const int es0 = (b0 >> 23) & 0xff, es1 = (b1 >> 23) & 0xff;
-    if (es0 == 0 || es0 == 255 || es1 == 0 || es1 == 255) {       // zero / denormal / non-finite sum: one plain addition
+    const float s0 = sh_s;
+    const uint32_t b0 = __float_as_uint(s0);
+    const int es0 = (b0 >> 23) & 0xff;
+    if (es0 == 0 || es0 == 255) {                                 // zero / denormal / non-finite sum: one plain addition
       __syncthreads();
-      if (tid == 0) { const float2 v = __ldg(t + base); sh_s[0] = __fadd_rn(s0, v.x); sh_s[1] = __fadd_rn(s1, v.y); }
+      if (tid == 0) sh_s = __fadd_rn(s0, term(base));
       __syncthreads();
       ++base;
       continue;
     }
-    const int S0 = (int)((b0 & 0x7fffffu) | 0x800000u), S1 = (int)((b1 & 0x7fffffu) | 0x800000u);
+    const int S0 = (int)((b0 & 0x7fffffu) | 0x800000u);
     const int m = min(kSumChunk, n - base);
     // A thread's 16 terms as a (delta if S starts even, delta if S starts odd) pair.  Without an exact tie (f == 1/2: about
     // one term in 2^(shift) -- rare) both deltas are the plain sum of q + [f > 1/2]; only a thread that saw a tie runs the
     // parity-tracking recurrence.
-    int d0 = 0, d1 = 0;
+    int d0 = 0;
     uint32_t ties = 0;
 #pragma unroll 8
     for (int i = 0; i < kSumE; ++i) {
       const int k = tid * kSumE + i;
-      float2 v = make_float2(0.0f, 0.0f);
-      if (k < m) v = __ldg(t + base + k);
-      const uint32_t w0 = sum_elem(es0, __float_as_uint(v.x)), w1 = sum_elem(es1, __float_as_uint(v.y));
+      const float t = k < m ? term(base + k) : 0.0f;
+      const uint32_t w0 = sum_elem(es0, __float_as_uint(t));
       d0 += (int)(w0 & 0x1ffffffu) + (int)((w0 >> 30) & 1u);
-      d1 += (int)(w1 & 0x1ffffffu) + (int)((w1 >> 30) & 1u);
-      ties |= w0 | w1;
+      ties |= w0;
     }
-    SumPair p0 = {min(d0, kSumSat), min(d0, kSumSat)}, p1 = {min(d1, kSumSat), min(d1, kSumSat)};
+    SumPair p0 = {min(d0, kSumSat), min(d0, kSumSat)};
     if (ties >> 31) {
-      int x00 = 0, x01 = 1, x10 = 0, x11 = 1;                     // pseudo-S started even / odd, per sum
+      int x00 = 0, x01 = 1;                                       // pseudo-S started even / odd
       for (int i = 0; i < kSumE; ++i) {
         const int k = tid * kSumE + i;
         if (k < m) {
-          const float2 v = __ldg(t + base + k);
-          const uint32_t w0 = sum_elem(es0, __float_as_uint(v.x)), w1 = sum_elem(es1, __float_as_uint(v.y));
+          const uint32_t w0 = sum_elem(es0, __float_as_uint(term(base + k)));
           x00 = sum_apply(x00, w0); x01 = sum_apply(x01, w0);
-          x10 = sum_apply(x10, w1); x11 = sum_apply(x11, w1);
         }
       }
-      p0.a0 = x00; p0.a1 = x01 - 1; p1.a0 = x10; p1.a1 = x11 - 1;
+      p0.a0 = x00; p0.a1 = x01 - 1;
     }
-    const SumPair own0 = p0, own1 = p1;
+    const SumPair own0 = p0;
     // inclusive scan inside the warp, warp totals through shared memory
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      SumPair o0, o1;
+      SumPair o0;
       o0.a0 = __shfl_up_sync(0xffffffffu, p0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, p0.a1, off);
-      o1.a0 = __shfl_up_sync(0xffffffffu, p1.a0, off); o1.a1 = __shfl_up_sync(0xffffffffu, p1.a1, off);
-      if (lane >= off) { p0 = sum_compose(o0, p0); p1 = sum_compose(o1, p1); }
+      if (lane >= off) p0 = sum_compose(o0, p0);
     }
-    if (lane == 31) { wt[0][warp] = p0; wt[1][warp] = p1; }
-    SumPair e0, e1;                                              // exclusive inside the warp
+    if (lane == 31) wt[warp] = p0;
+    SumPair e0;                                                  // exclusive inside the warp
     e0.a0 = __shfl_up_sync(0xffffffffu, p0.a0, 1); e0.a1 = __shfl_up_sync(0xffffffffu, p0.a1, 1);
-    e1.a0 = __shfl_up_sync(0xffffffffu, p1.a0, 1); e1.a1 = __shfl_up_sync(0xffffffffu, p1.a1, 1);
-    if (lane == 0) { e0.a0 = e0.a1 = 0; e1.a0 = e1.a1 = 0; }
+    if (lane == 0) e0.a0 = e0.a1 = 0;
     __syncthreads();
     // every warp scans the warp totals for itself (16 entries: four shuffle steps) -- cheaper than a second barrier
-    SumPair q0, q1;
+    SumPair q0;
     {
       constexpr int NWARP = kSumThreads / 32;
-      SumPair t0 = {0, 0}, t1 = {0, 0};
-      if (lane < NWARP) { t0 = wt[0][lane]; t1 = wt[1][lane]; }
+      SumPair t0 = {0, 0};
+      if (lane < NWARP) t0 = wt[lane];
 #pragma unroll
       for (int off = 1; off < NWARP; off <<= 1) {
-        SumPair o0, o1;
+        SumPair o0;
         o0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, off);
-        o1.a0 = __shfl_up_sync(0xffffffffu, t1.a0, off); o1.a1 = __shfl_up_sync(0xffffffffu, t1.a1, off);
-        if (lane >= off) { t0 = sum_compose(o0, t0); t1 = sum_compose(o1, t1); }
+        if (lane >= off) t0 = sum_compose(o0, t0);
       }
       // exclusive prefix of this warp = inclusive total of warp - 1
       const int srcl = warp == 0 ? 0 : warp - 1;
-      SumPair x0, x1;
+      SumPair x0;
       x0.a0 = __shfl_sync(0xffffffffu, t0.a0, srcl); x0.a1 = __shfl_sync(0xffffffffu, t0.a1, srcl);
-      x1.a0 = __shfl_sync(0xffffffffu, t1.a0, srcl); x1.a1 = __shfl_sync(0xffffffffu, t1.a1, srcl);
-      if (warp == 0) { x0.a0 = x0.a1 = 0; x1.a0 = x1.a1 = 0; }
-      q0 = sum_compose(x0, e0); q1 = sum_compose(x1, e1);
+      if (warp == 0) x0.a0 = x0.a1 = 0;
+      q0 = sum_compose(x0, e0);
     }
-    int Sa = sum_sat(S0, (S0 & 1) ? q0.a1 : q0.a0), Sb = sum_sat(S1, (S1 & 1) ? q1.a1 : q1.a0);
-    // S only grows: a binade is left inside this thread's range iff S is still inside before it and outside after it.
-    // Only that thread (at most one per sum and pass) walks its terms to find the addition that does it.
-    int my_cross = INT_MAX, Sa_before = Sa, Sb_before = Sb;
-    const int Sa_out = sum_sat(Sa, (Sa & 1) ? own0.a1 : own0.a0), Sb_out = sum_sat(Sb, (Sb & 1) ? own1.a1 : own1.a0);
-    if (Sa < (1 << 24) && Sb < (1 << 24)) {
-      if (Sa_out >= (1 << 24) || Sb_out >= (1 << 24)) {
+    int Sa = sum_sat(S0, (S0 & 1) ? q0.a1 : q0.a0);
+    // S only grows: the binade is left inside this thread's range iff S is still inside before it and outside after it.
+    // Only that thread (at most one per pass) walks its terms to find the addition that does it.
+    int my_cross = INT_MAX, Sa_before = Sa;
+    const int Sa_out = sum_sat(Sa, (Sa & 1) ? own0.a1 : own0.a0);
+    if (Sa < (1 << 24)) {
+      if (Sa_out >= (1 << 24)) {
         for (int i = 0; i < kSumE; ++i) {
           if (my_cross == INT_MAX && tid * kSumE + i < m) {
-            const float2 v = __ldg(t + base + tid * kSumE + i);   // second read of the thread's own 128 bytes: an L1 hit
-            const int na = sum_apply(Sa, sum_elem(es0, __float_as_uint(v.x))), nb = sum_apply(Sb, sum_elem(es1, __float_as_uint(v.y)));
-            if (na >= (1 << 24) || nb >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; Sb_before = Sb; }
-            else { Sa = na; Sb = nb; }
+            const int na = sum_apply(Sa, sum_elem(es0, __float_as_uint(term(base + tid * kSumE + i))));
+            if (na >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; }
+            else Sa = na;
           }
         }
-      } else { Sa = Sa_out; Sb = Sb_out; }
+      } else Sa = Sa_out;
     }
     if (tid == 0) sh_cross[(pass + 1) & 1] = INT_MAX;             // next pass's slot: last read before this pass's first barrier
     if (my_cross != INT_MAX) atomicMin(&sh_cross[pass & 1], my_cross);
@@ -297,29 +297,32 @@ __global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const
     const int cross = sh_cross[pass & 1];
     ++pass;
     if (cross == INT_MAX) {
-      if (tid == (m - 1) / kSumE) {                              // owner of the last element holds the totals
-        sh_s[0] = __uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa & 0x7fffffu));
-        sh_s[1] = __uint_as_float(((uint32_t)es1 << 23) | ((uint32_t)Sb & 0x7fffffu));
-      }
+      if (tid == (m - 1) / kSumE) sh_s = __uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa & 0x7fffffu));   // owner of the last element holds the total
       base += m;
     } else {
-      if (my_cross == cross && tid == cross / kSumE) {           // the crossing addition itself, in real float arithmetic
-        const float2 v = __ldg(t + base + cross);
-        sh_s[0] = __fadd_rn(__uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa_before & 0x7fffffu)), v.x);
-        sh_s[1] = __fadd_rn(__uint_as_float(((uint32_t)es1 << 23) | ((uint32_t)Sb_before & 0x7fffffu)), v.y);
-      }
+      if (my_cross == cross && tid == cross / kSumE)              // the crossing addition itself, in real float arithmetic
+        sh_s = __fadd_rn(__uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa_before & 0x7fffffu)), term(base + cross));
       base += cross + 1;
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    const float ss = sh_s[0], se = sh_s[1];
-    const float a8 = __fmul_rn(8.0f, kNorm[MOD]);
-    float p = __fdiv_rn(__fmul_rn(a8, ss), se);            // 8.0f * NORM * sum_s / sum_e, left to right
-    if (precision_in) p = precision_in[blockIdx.x];
-    precision[blockIdx.x] = p;
-    if (snr) snr[blockIdx.x] = (MOD == 0 ? 10.0f : 20.0f) * log10f(ss / se);
+  if (tid == 0) sums[2 * blockIdx.x + which] = sh_s;
+}
+
+// precision = 8.0f * NORM * sum_s / sum_e, left to right (llr_demapper.cpp:722-737); also written out (with the SNR estimate)
+// by the first CTA of each TI block
+template <int MOD>
+__device__ __forceinline__ float demap_precision(const float* __restrict__ sums, const float* __restrict__ precision_in, int blk,
+                                                 float* __restrict__ precision, float* __restrict__ snr, bool writer)
+{
+  const float ss = sums[2 * blk], se = sums[2 * blk + 1];
+  float p = __fdiv_rn(__fmul_rn(__fmul_rn(8.0f, kNorm[MOD]), ss), se);
+  if (precision_in) p = precision_in[blk];
+  if (writer) {
+    precision[blk] = p;
+    if (snr) snr[blk] = (MOD == 0 ? 10.0f : 20.0f) * log10f(ss / se);
   }
+  return p;
 }
 
 // (int8_t)(float) as x86-64 gcc compiles it: cvttss2si to int32 (0x80000000 when out of range), low byte.
@@ -335,7 +338,8 @@ __device__ __forceinline__ int wrap_i8(float r)
 // ---- K4 pass 2: one CTA per FECFRAME -----------------------------------------------------------
 template <int MOD, bool SAT>
 __global__ void demap_llr_kernel(const float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
-                                 const float* __restrict__ precision, const int32_t* __restrict__ address,
+                                 const float* __restrict__ sums, const float* __restrict__ precision_in,
+                                 float* __restrict__ precision, float* __restrict__ snr, const int32_t* __restrict__ address,
                                  int8_t* __restrict__ llr, int cpf, int fec_bits)
 {
   extern __shared__ __align__(16) int8_t frame[];
@@ -343,7 +347,7 @@ __global__ void demap_llr_kernel(const float2* __restrict__ cells, const DemapBl
   const DemapBlockDesc b = blocks[blockIdx.y];
   const int n_fec = b.n_cells / cpf;
   const float a = kNorm[MOD];
-  const float p = precision[blockIdx.y];
+  const float p = demap_precision<MOD>(sums, precision_in, blockIdx.y, precision, snr, blockIdx.x == 0 && threadIdx.x == 0);
   for (int f = blockIdx.x; f < n_fec; f += gridDim.x) {
     const float2* c = cells + b.cell_off + (size_t)f * cpf;
     for (int k = threadIdx.x; k < cpf; k += blockDim.x) {
@@ -373,7 +377,17 @@ __global__ void demap_llr_kernel(const float2* __restrict__ cells, const DemapBl
     __syncthreads();
     int4* dst = reinterpret_cast<int4*>(llr + ((size_t)b.first_fec + f) * fec_bits);
     const int4* src = reinterpret_cast<const int4*>(frame);
-    if ((((size_t)b.first_fec + f) * fec_bits) % 16 == 0) {
+    if ((fec_bits & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      // 64 800-bit frames: the finished image leaves the SM as ONE bulk copy of the TMA engine (cp.async.bulk shared -> global);
+      // the threads only wait until the engine has read the image out of shared memory
+      if (threadIdx.x == 0) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(frame);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(sa), "r"(fec_bits) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else if ((((size_t)b.first_fec + f) * fec_bits) % 16 == 0) {
       for (int k = threadIdx.x; k < fec_bits / 16; k += blockDim.x) dst[k] = src[k];
       for (int k = (fec_bits / 16) * 16 + threadIdx.x; k < fec_bits; k += blockDim.x)
         llr[((size_t)b.first_fec + f) * fec_bits + k] = frame[k];
@@ -471,13 +485,20 @@ static int upload_descs(t2b200_ctx* ctx, int slot, const void* h, size_t bytes, 
   return T2B200_OK;
 }
 
+// derotate_mod >= 0: the cells leave already derotated for that constellation (what t2_demap_device then expects)
 int t2_ti_device(t2b200_ctx* ctx, int plp, const float2* d_in, float2* d_out, const TiBlockDesc* d_desc, int n_ti_blocks,
-                 int max_cells)
+                 int max_cells, int derotate_mod)
 {
   if (!ctx->ti || !ctx->ti->plp.count(plp)) { ctx->err = "TI: PLP not configured"; return T2B200_ERR_STATE; }
   const TiPlp& p = ctx->ti->plp[plp];
   dim3 grid(std::min((max_cells + 255) / 256, ctx->sm_count * 8), n_ti_blocks);
-  ti_deinterleave_kernel<<<grid, 256, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec);
+  if (derotate_mod >= 0) {
+    const float th = -kRot[derotate_mod & 3];
+    const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
+    ti_deinterleave_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec, rc, rs);
+  } else {
+    ti_deinterleave_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec, 1.0f, 0.0f);
+  }
   T2_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return T2B200_OK;
@@ -511,37 +532,41 @@ extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cel
   if ((rc = t2_to_device(ctx, 0, cells_in, (size_t)off * 8, &din))) return rc;
   if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)off * 8, &dout))) return rc;
   if ((rc = upload_descs(ctx, 5, d.data(), d.size() * sizeof(TiBlockDesc), &ddesc))) return rc;
-  if ((rc = t2_ti_device(ctx, plp, (const float2*)din, (float2*)dout, (const TiBlockDesc*)ddesc, n_ti_blocks, max_cells))) return rc;
+  if ((rc = t2_ti_device(ctx, plp, (const float2*)din, (float2*)dout, (const TiBlockDesc*)ddesc, n_ti_blocks, max_cells, -1))) return rc;
   // (the descriptor upload above is a pageable-memory copy: the runtime has consumed the host vector when it returns)
   return t2_finish_out(ctx, cells_out, dout, (size_t)off * 8);
 }
 
 template <int MOD>
-static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_blocks, int max_cells, long long total_cells,
-                        int rotation, const int32_t* d_addr, int8_t* d_llr, int cpf, int fec_bits, int max_fec,
+static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_blocks, int max_cells,
+                        int rotation, bool derotated, const int32_t* d_addr, int8_t* d_llr, int cpf, int fec_bits, int max_fec,
                         float* d_prec, float* d_snr, const float* d_prec_in)
 {
-  const int gx = std::max(1, std::min((max_cells + 255) / 256, ctx->sm_count * 8));
-  void* d_terms;
+  void* d_sums;
   int rc0;
-  if ((rc0 = t2_dev_scratch(ctx, 4, (size_t)total_cells * sizeof(float2), &d_terms))) return rc0;
-  const float th = -kRot[MOD];
-  const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
-  demap_stats_kernel<MOD><<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, (float2*)d_terms, rotation != 0, rc, rs);
-  T2_CUDA(ctx, cudaGetLastError());
-  demap_ordered_sum_kernel<MOD><<<n_blocks, kSumThreads, 0, ctx->stream>>>((const float2*)d_terms, d_desc, d_prec, d_snr, d_prec_in);
+  if ((rc0 = t2_dev_scratch(ctx, 4, (size_t)n_blocks * 2 * sizeof(float), &d_sums))) return rc0;
+  if (rotation && !derotated) {
+    const int gx = std::max(1, std::min((max_cells + 255) / 256, ctx->sm_count * 8));
+    const float th = -kRot[MOD];
+    const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
+    demap_derotate_kernel<<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, rc, rs);
+    T2_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  demap_ordered_sum_kernel<MOD><<<dim3(n_blocks, 2), kSumThreads, 0, ctx->stream>>>(d_cells, d_desc, (float*)d_sums);
   T2_CUDA(ctx, cudaGetLastError());
   auto k = ctx->opt_demap_saturate ? demap_llr_kernel<MOD, true> : demap_llr_kernel<MOD, false>;
   const size_t smem = (size_t)((fec_bits + 15) & ~15);
   T2_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<dim3(std::min(max_fec, ctx->sm_count * 3), n_blocks), 512, smem, ctx->stream>>>(d_cells, d_desc, d_prec, d_addr, d_llr, cpf, fec_bits);
+  k<<<dim3(std::min(max_fec, ctx->sm_count * 3), n_blocks), 512, smem, ctx->stream>>>(d_cells, d_desc, (const float*)d_sums, d_prec_in,
+                                                                                     d_prec, d_snr, d_addr, d_llr, cpf, fec_bits);
   T2_CUDA(ctx, cudaGetLastError());
-  ctx->launches += 3;
+  ctx->launches += 2;
   return T2B200_OK;
 }
 
 int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_ti_blocks, int max_cells,
-                    long long total_cells, int max_fec, int mod, int rotation, int fec_type, int code_rate, int8_t* d_llr,
+                    int max_fec, int mod, int rotation, bool derotated, int fec_type, int code_rate, int8_t* d_llr,
                     float* d_prec, float* d_snr, const float* d_prec_in)
 {
   TiDemapState* st = state(ctx);
@@ -557,7 +582,7 @@ int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_de
     st->addr[key] = t;
   }
   const int32_t* daddr = mod ? st->addr[key].d_addr : nullptr;
-#define DM(M) demap_launch<M>(ctx, d_cells, d_desc, n_ti_blocks, max_cells, total_cells, rotation, daddr, d_llr, cpf, fec_bits, \
+#define DM(M) demap_launch<M>(ctx, d_cells, d_desc, n_ti_blocks, max_cells, rotation, derotated, daddr, d_llr, cpf, fec_bits, \
                               max_fec, d_prec, d_snr, d_prec_in)
   switch (mod) { case 0: return DM(0); case 1: return DM(1); case 2: return DM(2); default: return DM(3); }
 #undef DM
@@ -595,7 +620,7 @@ extern "C" int t2b200_demap(t2b200_ctx* ctx, float* ti_cells, int n_ti_blocks, c
                                  t2_is_device_ptr(precision_in) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     dpin = tmp;
   }
-  if ((rc = t2_demap_device(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, off, max_fec, mod, rotation,
+  if ((rc = t2_demap_device(ctx, (float2*)dcells, (const DemapBlockDesc*)ddesc, n_ti_blocks, max_cells, max_fec, mod, rotation, false,
                             fec_type, code_rate, (int8_t*)dllr, (float*)dprec, (float*)dsnr, (const float*)dpin))) return rc;
   auto copy_small = [&](float* dst, const void* src) -> int {
     if (!dst) return T2B200_OK;

@@ -72,18 +72,26 @@ __device__ __forceinline__ float atan2_approx_dev(float y, float x)      // DSP/
   return r;
 }
 
+// Symbol tables of one kind as a launch sees them: symbols r0 .. of a frame are of this kind, their cells go to
+// out + f * out_frame + out_off + (r - r0) * out_sym
+struct EqKind {
+  const PlanDev* plans; const int* plan_even; const int* plan_odd;
+  int first_symbol, n_symbols_kind, r0, pad;
+  long long out_off, out_sym;
+};
 struct EqParams {
   const float2* freq; float2* out; float* sro; float* phase; const int* idx_symbol;
-  const PlanDev* plans; const int* plan_even; const int* plan_odd;
   const float2* lut_cs;           // {cos, sin} of DSP/fast_math.h's tables, interleaved
-  int fft_size, l_nulls, n_out, first_symbol, n_symbols_kind;
+  int l_nulls;
   int n_symbols;                 // symbols in this launch
   int split;                     // CTAs per symbol
   // symbol s of the launch = symbol r = s % per_frame of frame f = s / per_frame (a plain batch is one "frame"):
-  //   spectrum at freq + f * in_frame + r * in_sym, cells to out + f * out_frame + r * out_sym, feedback floats at
-  //   [f * fb_frame + r]; idx_symbol == nullptr means idx = first_symbol + r
+  //   spectrum at freq + f * in_frame + r * in_sym, feedback floats at [f * fb_frame + r]; idx_symbol == nullptr means
+  //   idx = first_symbol of its kind + (r - r0)
   int per_frame;
-  long long in_frame, in_sym, out_frame, out_sym, fb_frame;
+  long long in_frame, in_sym, out_frame, fb_frame;
+  int n_kinds;                   // 1: a batch of one kind; 3 (2 without a frame-closing symbol): whole frames, P2 | data | FC
+  EqKind kind[3];
 };
 
 constexpr int kEqThreads = 256;
@@ -108,17 +116,20 @@ __global__ void __launch_bounds__(kEqThreads) equalize_kernel(const EqParams p)
   const int part = blockIdx.x % p.split;
   for (int s = blockIdx.x / p.split; s < p.n_symbols; s += gridDim.x / p.split) {
     const int fr = s / p.per_frame, rs = s - fr * p.per_frame;
-    const int idx = p.idx_symbol ? p.idx_symbol[s] : p.first_symbol + rs;
-    int rel = idx - p.first_symbol;
-    rel = min(max(rel, 0), p.n_symbols_kind - 1);
-    const PlanDev pl = p.plans[(idx & 1) ? p.plan_odd[rel] : p.plan_even[rel]];
+    const int kd = (p.n_kinds > 1 && rs >= p.kind[1].r0) ? ((p.n_kinds > 2 && rs >= p.kind[2].r0) ? 2 : 1) : 0;
+    const EqKind& K = p.kind[kd];
+    const int rk = rs - K.r0;
+    const int idx = p.idx_symbol ? p.idx_symbol[s] : K.first_symbol + rk;
+    int rel = idx - K.first_symbol;
+    rel = min(max(rel, 0), K.n_symbols_kind - 1);
+    const PlanDev pl = K.plans[(idx & 1) ? K.plan_odd[rel] : K.plan_even[rel]];
     float2* spec = chain + kEqChunk;
     float2* est = spec + kEqSpan;
     float* ang = reinterpret_cast<float*>(est + pl.n_pilots);
     float* amp = ang + pl.n_pilots;
     int* first = reinterpret_cast<int*>(amp + pl.n_pilots);
     const float2* cell = p.freq + (size_t)fr * p.in_frame + (size_t)rs * p.in_sym + p.l_nulls;
-    float2* out = p.out + (size_t)fr * p.out_frame + (size_t)rs * p.out_sym;
+    float2* out = p.out + (size_t)fr * p.out_frame + (size_t)K.out_off + (size_t)rk * K.out_sym;
     const size_t fb = (size_t)fr * p.fb_frame + rs;
 
     for (int i = threadIdx.x; i < pl.n_pilots; i += blockDim.x) {
@@ -381,7 +392,27 @@ extern "C" int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int
   return T2B200_OK;
 }
 
-// Device-level launch (all pointers device memory): n_symbols symbols, per_frame of them per frame (see EqParams).
+static void eq_fill_kind(EqKind& k, const SymbolTables* t, int r0, long long out_off, long long out_sym)
+{
+  k.plans = t->d_plans; k.plan_even = t->d_plan_even; k.plan_odd = t->d_plan_odd;
+  k.first_symbol = t->first_symbol; k.n_symbols_kind = t->n_symbols; k.r0 = r0; k.pad = 0;
+  k.out_off = out_off; k.out_sym = out_sym;
+}
+
+static int eq_launch(t2b200_ctx* ctx, EqParams& p, int max_pilots)
+{
+  p.lut_cs = reinterpret_cast<const float2*>(ctx->d_lut);
+  const size_t smem = (size_t)(kEqChunk + kEqSpan) * sizeof(float2) + (size_t)(max_pilots + 2) * 20;
+  T2_CUDA(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.split = kEqSplitDefault;
+  if (const char* e = getenv("T2B200_EQ_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.split = v; }   // development aid
+  equalize_kernel<<<p.n_symbols * p.split, kEqThreads, smem, ctx->stream>>>(p);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return T2B200_OK;
+}
+
+// Device-level launch (all pointers device memory): n_symbols symbols of one kind, per_frame of them per frame (see EqParams).
 int t2_equalize_device(t2b200_ctx* ctx, int kind, int n_symbols, int per_frame, const int* d_idx, const float2* d_freq,
                        long long in_frame, long long in_sym, float2* d_out, long long out_frame, long long out_sym,
                        float* d_sro, float* d_phase, long long fb_frame)
@@ -390,20 +421,14 @@ int t2_equalize_device(t2b200_ctx* ctx, int kind, int n_symbols, int per_frame, 
   if (!t) { ctx->err = "equalise: symbol tables not configured"; return T2B200_ERR_STATE; }
   if (n_symbols == 0) return T2B200_OK;
   EqParams p;
+  memset(&p, 0, sizeof(p));
   p.freq = d_freq; p.out = d_out; p.sro = d_sro; p.phase = d_phase; p.idx_symbol = d_idx;
-  p.plans = t->d_plans; p.plan_even = t->d_plan_even; p.plan_odd = t->d_plan_odd;
-  p.lut_cs = reinterpret_cast<const float2*>(ctx->d_lut);
-  p.fft_size = t->fft_size; p.l_nulls = t->l_nulls; p.n_out = t->n_out; p.first_symbol = t->first_symbol; p.n_symbols_kind = t->n_symbols;
+  p.l_nulls = t->l_nulls;
   p.n_symbols = n_symbols; p.per_frame = per_frame;
-  p.in_frame = in_frame; p.in_sym = in_sym; p.out_frame = out_frame; p.out_sym = out_sym; p.fb_frame = fb_frame;
-  const size_t smem = (size_t)(kEqChunk + kEqSpan) * sizeof(float2) + (size_t)(t->max_pilots + 2) * 20;
-  T2_CUDA(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  p.split = kEqSplitDefault;
-  if (const char* e = getenv("T2B200_EQ_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.split = v; }   // development aid
-  equalize_kernel<<<n_symbols * p.split, kEqThreads, smem, ctx->stream>>>(p);
-  T2_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
-  return T2B200_OK;
+  p.in_frame = in_frame; p.in_sym = in_sym; p.out_frame = out_frame; p.fb_frame = fb_frame;
+  p.n_kinds = 1;
+  eq_fill_kind(p.kind[0], t, 0, 0, out_sym);
+  return eq_launch(ctx, p, t->max_pilots);
 }
 
 extern "C" int t2b200_equalize(t2b200_ctx* ctx, int kind, int n_symbols, const int32_t* idx_symbol, const float* freq,

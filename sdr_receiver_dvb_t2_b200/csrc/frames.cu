@@ -21,6 +21,8 @@ struct FramePipe {
   uint8_t* d_kldpc = nullptr;              // LDPC information words of the opt-in BCH correction
   float* d_fb = nullptr;                   // sro | phase, [frames][len_frame] each
   int max_cells = 0, max_fec = 0;
+  cudaEvent_t ev[7] = {};                  // stage boundaries of the last call (T2B200_OPT_STAGE_TIMING)
+  bool timed = false;
 };
 
 static void pipe_free_buffers(FramePipe* p)
@@ -37,6 +39,7 @@ void t2_frames_free(t2b200_ctx* ctx)
 {
   if (!ctx->frames) return;
   pipe_free_buffers(ctx->frames);
+  for (auto& e : ctx->frames->ev) if (e) cudaEventDestroy(e);
   delete ctx->frames;
   ctx->frames = nullptr;
 }
@@ -172,11 +175,22 @@ static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale,
                                  ctx->stream));
     d_iq = p->d_iq;
   }
+  const bool timing = ctx->opt_stage_timing != 0;
+  auto mark = [&](int i) -> int {
+    if (!timing) return T2B200_OK;
+    if (!p->ev[i]) T2_CUDA(ctx, cudaEventCreate(&p->ev[i]));
+    T2_CUDA(ctx, cudaEventRecord(p->ev[i], ctx->stream));
+    return T2B200_OK;
+  };
+  p->timed = timing;
+  if ((rc = mark(0))) return rc;
   // K1 (int16 samples are converted on load: the first slice of the front-end, dvbt2_demodulator.cpp:182-186)
   if ((rc = t2_fft_device(ctx, N, i16 ? nullptr : static_cast<const float2*>(d_iq), F * L, p->d_freq, p->d_tmp,
                           i16 ? static_cast<const short2*>(d_iq) : nullptr, scale))) return rc;
+  if ((rc = mark(1))) return rc;
   // K2: every symbol kind writes its cells where the frame cell stream wants them
   float* d_sro = p->d_fb; float* d_ph = p->d_fb + (size_t)F * L;
+  // (one merged launch was measured 2x slower: the P2 symbols' dense pilots set the shared-memory footprint of every CTA)
   const long long frame_in = (long long)L * N;
   if ((rc = t2_equalize_device(ctx, T2B200_SYM_P2, F * c.n_p2, c.n_p2, nullptr, p->d_freq, frame_in, N, p->d_cells, p->per_frame,
                                c.c_p2, d_sro, d_ph, L))) return rc;
@@ -187,11 +201,14 @@ static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale,
       (rc = t2_equalize_device(ctx, T2B200_SYM_FC, F, 1, nullptr, p->d_freq + (size_t)(L - 1) * N, frame_in, N,
                                p->d_cells + (size_t)c.n_p2 * c.c_p2 + (size_t)p->n_data * c.c_data, p->per_frame, c.n_fc,
                                d_sro + (L - 1), d_ph + (L - 1), L))) return rc;
+  if ((rc = mark(2))) return rc;
   // K3, K4
-  if ((rc = t2_ti_device(ctx, c.plp, p->d_cells, p->d_tib, p->d_ti, F * nti, p->max_cells))) return rc;
+  if ((rc = t2_ti_device(ctx, c.plp, p->d_cells, p->d_tib, p->d_ti, F * nti, p->max_cells, c.rotation ? c.mod : -1))) return rc;
+  if ((rc = mark(3))) return rc;
   float* d_prec = p->d_prec; float* d_snr = p->d_prec + (size_t)F * nti;
-  if ((rc = t2_demap_device(ctx, p->d_tib, p->d_dm, F * nti, p->max_cells, (long long)F * c.n_blocks * p->cpf, p->max_fec, c.mod,
-                            c.rotation, c.fec_type, c.code_rate, p->d_llr, d_prec, d_snr, nullptr))) return rc;
+  if ((rc = t2_demap_device(ctx, p->d_tib, p->d_dm, F * nti, p->max_cells, p->max_fec, c.mod, c.rotation, true, c.fec_type,
+                            c.code_rate, p->d_llr, d_prec, d_snr, nullptr))) return rc;
+  if ((rc = mark(4))) return rc;
   // K5 + K6
   const int n_cw = F * c.n_blocks;
   const int k_out = (ldpc_flags & T2B200_LDPC_BCH_DESCRAMBLE) ? p->k_bch : t2b200_ldpc_k(p->code);
@@ -209,6 +226,7 @@ static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale,
     if ((rc = t2_bch_device(ctx, p->code, p->d_kldpc, t2b200_ldpc_k(p->code), n_cw, nullptr))) return rc;
     if ((rc = t2_bch_descramble_device(ctx, p->code, p->d_kldpc, n_cw, d_bits))) return rc;
   } else if ((rc = t2_ldpc_device(ctx, p->code, p->d_llr, n_cw, d_bits, d_tr, nullptr, max_trials > 0 ? max_trials : 25, ldpc_flags))) return rc;
+  if ((rc = mark(5))) return rc;
   // results
   bool sync = false;
   auto give = [&](void* dst, const void* src, size_t bytes) -> int {
@@ -223,6 +241,19 @@ static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale,
   if ((rc = give(sro, d_sro, 4 * (size_t)F * L))) return rc;
   if ((rc = give(phase, d_ph, 4 * (size_t)F * L))) return rc;
   if ((rc = give(snr, d_snr, 4 * (size_t)F * nti))) return rc;
+  if ((rc = mark(6))) return rc;
   if (sync) T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // host outputs are filled when the call returns
+  return T2B200_OK;
+}
+
+extern "C" int t2b200_frames_stage_ms(t2b200_ctx* ctx, float ms_out[6])
+{
+  if (!ctx || !ms_out) return T2B200_ERR_ARG;
+  FramePipe* p = ctx->frames;
+  if (!p || !p->timed || !p->ev[6]) { ctx->err = "t2b200_frames_stage_ms: no timed call (T2B200_OPT_STAGE_TIMING)"; return T2B200_ERR_STATE; }
+  T2_CUDA(ctx, cudaSetDevice(ctx->device));
+  T2_CUDA(ctx, cudaEventSynchronize(p->ev[6]));
+  for (int i = 0; i < 5; ++i) T2_CUDA(ctx, cudaEventElapsedTime(&ms_out[i], p->ev[i], p->ev[i + 1]));
+  T2_CUDA(ctx, cudaEventElapsedTime(&ms_out[5], p->ev[0], p->ev[6]));
   return T2B200_OK;
 }

@@ -31,6 +31,7 @@ namespace t2pair {
 
 #if defined(__CUDACC__)
 __constant__ uint32_t kFmaMinus1 = 0xffffffffu;          // see not_fma()
+__constant__ uint32_t kFmaOne = 1u;                       // see add_fma()
 #endif
 
 // ---- the handful of machine operations everything below is written in -------------------------------------------------
@@ -50,13 +51,16 @@ template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b)
 // Bitwise complement as a multiply-add, x * (-1) + (-1): issues on the FMA pipe -- the ALU pipe is the decoder's
 // bottleneck.  The -1 comes from constant memory so that ptxas cannot turn the IMAD back into an ALU instruction.
 __device__ __forceinline__ uint32_t not_fma(uint32_t x) { return x * kFmaMinus1 + kFmaMinus1; }
+// ... and an addition as x * 1 + y, for the edge addresses
+__device__ __forceinline__ uint32_t add_fma(uint32_t x, uint32_t y) { return x * kFmaOne + y; }
 T2_HD int mod360(int t) { return (int)__viaddmin_u32((unsigned)t, 0xfffffe98u, (unsigned)t); }    // t in [0, 720): t mod 360
 T2_HD uint32_t mod720(uint32_t t) { return __viaddmin_u32(t, 0xfffffd30u, t); }                       // t in [0, 1440): t mod 720
 // the pair's posteriors by 32-bit shared-memory address (kept in a register from the load to the store of an edge)
 typedef uint32_t post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return (uint32_t)__cvta_generic_to_shared(post); }
 T2_HD post_ref post_at(post_ref base, int a) { return base + 2u * (uint32_t)a; }
-T2_HD post_ref post_at_bytes(post_ref base, uint32_t b) { return base + b; }
+// byte offset 720 g + x behind the base: two multiply-adds
+T2_HD post_ref post_at_group(post_ref base, uint32_t g, uint32_t x) { return g * 720u + add_fma(x, base); }
 T2_HD uint32_t post_ld(post_ref r) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(r) : "memory"); return v; }
 T2_HD void post_st(post_ref r, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(r), "r"(v) : "memory"); }
 #else
@@ -90,12 +94,13 @@ T2_HD uint32_t prmt_any(uint32_t a, uint32_t b, uint32_t sel)
 }
 template <uint32_t SEL> T2_HD uint32_t prmt(uint32_t a, uint32_t b) { return prmt_any(a, b, SEL); }
 T2_HD uint32_t not_fma(uint32_t x) { return ~x; }
+T2_HD uint32_t add_fma(uint32_t x, uint32_t y) { return x + y; }
 T2_HD int mod360(int t) { return t >= 360 ? t - 360 : t; }
 T2_HD uint32_t mod720(uint32_t t) { return t >= 720 ? t - 720 : t; }
 typedef uint16_t* post_ref;
 T2_HD post_ref post_base(uint16_t* post) { return post; }
 T2_HD post_ref post_at(post_ref base, int a) { return base + a; }
-T2_HD post_ref post_at_bytes(post_ref base, uint32_t b) { return base + b / 2; }
+T2_HD post_ref post_at_group(post_ref base, uint32_t g, uint32_t x) { return base + (g * 720u + x) / 2; }
 T2_HD uint32_t post_ld(post_ref r) { return *r; }
 T2_HD void post_st(post_ref r, uint32_t v) { *r = (uint16_t)v; }
 #endif
@@ -230,7 +235,7 @@ struct CheckNodePair {
   // data slot C of check node j (j2 = 2 j): bit-group eg, cyclic shift es2 / 2 -> byte offset 720 eg + (2 j + es2) mod 720
   template <int C> T2_HD post_ref data_ref(const uint16_t* eg, const uint16_t* es2, uint32_t j2) const
   {
-    return post_at_bytes(post, (uint32_t)eg[C] * 720u + mod720(j2 + (uint32_t)es2[C]));
+    return post_at_group(post, (uint32_t)eg[C], mod720(add_fma(j2, (uint32_t)es2[C])));
   }
   // input of a slot that arrives in a register (chain walk)
   template <int SLOT> T2_HD void edge_in_value(uint32_t vv)

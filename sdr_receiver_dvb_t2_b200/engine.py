@@ -21,6 +21,7 @@ FEC_SHORT, FEC_NORMAL = 0, 1
 OPT_DEMAP_SATURATE = 1
 OPT_LDPC_PLAIN_LAUNCH = 2
 OPT_BCH_CORRECT = 3
+OPT_STAGE_TIMING = 4
 
 # every symbol include/t2b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -33,7 +34,7 @@ SYMBOLS = [
     't2b200_ts_reset', 't2b200_ts_packetize', 't2b200_frames_configure', 't2b200_frames_decode',
     't2b200_mode_init', 't2b200_pilot_tables', 't2b200_eq_configure_mode', 't2b200_frames_decode_i16',
     't2b200_comm_unique_id', 't2b200_comm_init', 't2b200_comm_destroy', 't2b200_ldpc_decode_sharded',
-    't2b200_bch_t', 't2b200_bch_decode',
+    't2b200_bch_t', 't2b200_bch_decode', 't2b200_frames_stage_ms',
 ]
 
 
@@ -104,6 +105,7 @@ def lib():
     L.t2b200_frames_configure.argtypes = [vp, C.POINTER(FrameCfg)]
     L.t2b200_frames_decode.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, u32]
     L.t2b200_frames_decode_i16.argtypes = [vp, vp, C.c_float, i32, vp, vp, vp, vp, vp, i32, u32]
+    L.t2b200_frames_stage_ms.argtypes = [vp, vp]
     L.t2b200_comm_unique_id.argtypes = [vp, C.c_size_t]
     L.t2b200_comm_init.argtypes = [vp, i32, i32, vp, C.c_size_t]
     L.t2b200_comm_destroy.argtypes = [vp]
@@ -188,6 +190,12 @@ class Engine:
 
     def set_option(self, option, value):
         self._chk(self.L.t2b200_set_option(self.h, option, int(value)))
+
+    def frames_stage_ms(self):
+        """device ms of every stage of the last frames_decode call made with OPT_STAGE_TIMING on (t2b200_frames_stage_ms)"""
+        ms = (C.c_float * 6)()
+        self._chk(self.L.t2b200_frames_stage_ms(self.h, ms))
+        return dict(zip(('fft', 'equalize', 'ti_deinterleave', 'demap', 'ldpc_bch', 'call'), [float(x) for x in ms]))
 
     @property
     def launches(self):

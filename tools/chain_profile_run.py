@@ -16,6 +16,6 @@ fr = np.stack([mod.frame(noise_cn_db=20.5)['time'] for _ in range(2)])
 x = torch.from_numpy(fr).cuda()[torch.arange(F) % 2].contiguous()
 chain = FrameChain(eng, tables, mod=3, cod=2, fec_type=1, n_blocks=202, ti_len=3)
 for _ in range(2):
-    r = chain.decode_frames(x)
+    r = chain.decode_frames_fused(x)        # the product path: one t2b200_frames_decode call
 torch.cuda.synchronize()
 print('ok', float((r['trials_left'] >= 0).float().mean()))
