@@ -13,13 +13,16 @@
 //                                    store through address[] (:110-130)
 // B200 design: both stages are HBM-streaming permutations.  K3 is a gather pass (two 4-byte reads per output cell from the
 // L2-resident TI block, <= 4.4 MB, one coalesced 8-byte store) that also applies the demapper's derotation in the frame
-// pipeline, so the TI block is written once.  K4 is two passes over it: the order-dependent sums (one CTA per TI block and
-// sum, terms recomputed from the cells, nothing written but the sums) and the LLR pass, one CTA per FECFRAME: LLRs are
+// pipeline, so the TI block is written once, and leaves tree-order chunk sums of the statistics terms.  K4 is two passes over
+// it: the order-dependent sums (every 2048-cell chunk in parallel as one integer increment for the predicted binade, then one
+// warp per TI block and sum stitching the chunks -- see "Pass 1b") and the LLR pass, one CTA per FECFRAME: LLRs are
 // produced into a 64.8 KB shared-memory image of the de-interleaved frame and leave the SM as coalesced 16-byte stores, so
 // the column-twist scatter never reaches HBM as byte writes.  40 bytes of traffic per cell in all (was 72).
 #include "stages.h"
 #include "fec_tables.h"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <climits>
 
@@ -45,27 +48,68 @@ constexpr float kNorm[4] = {0.707106781f, 0.316227766f, 0.15430335f, 0.076696499
 // memory cell that lands there, i.e. arrival index k = row * cols + column; the Q component comes from the cell that lands
 // on a + 1 (cyclic inside the FEC block).  Two coalesced table reads, two 4-byte gathers from the L2-resident TI block,
 // one coalesced 8-byte store -- no scattered stores.
-// ROT: the demapper's derotation (llr_demapper.cpp:555-557, _in[i] *= derotate) applied on the way out, so that the TI block
-// is written once, already derotated (frame pipeline; the stand-alone stage leaves the cells as the reference's
-// time_deinterleaver does).
-template <bool ROT>
-__global__ void ti_deinterleave_kernel(const float2* __restrict__ in, float2* __restrict__ out,
-                                       const uint32_t* __restrict__ srcmap, const TiBlockDesc* __restrict__ blocks,
-                                       int rows, int cpf, float rc, float rs)
+constexpr int kSumChunk = 2048;          // cells per chunk of the ordered sums (and per CTA step of the fused TI pass)
+constexpr int kChunkThreads = 256;
+
+// (sum over the CTA of v.x, of v.y) -> thread 0
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* red)
 {
+#pragma unroll
+  for (int off = 16; off; off >>= 1) { v.x += __shfl_down_sync(0xffffffffu, v.x, off); v.y += __shfl_down_sync(0xffffffffu, v.y, off); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < kChunkThreads / 32 ? red[lane] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int off = 4; off; off >>= 1) { v.x += __shfl_down_sync(0xffffffffu, v.x, off); v.y += __shfl_down_sync(0xffffffffu, v.y, off); }
+  }
+  __syncthreads();
+  return v;
+}
+
+template <int MOD> __device__ __forceinline__ float2 demap_term(float2 v, float a);
+
+// MOD >= 0 (frame pipeline): the demapper's derotation (llr_demapper.cpp:555-557, _in[i] *= derotate) is applied on the way
+// out, so that the TI block is written once, already derotated, and the pass also leaves per chunk of kSumChunk cells the
+// (tree-order) sums of the two statistics terms: the estimate the ordered-sum kernels predict the running sum's binade
+// from.  MOD < 0 (stand-alone stage): the cells leave as the reference's time_deinterleaver writes them.
+template <int MOD>
+__global__ void __launch_bounds__(kChunkThreads) ti_deinterleave_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                         const uint32_t* __restrict__ srcmap,
+                                                                         const TiBlockDesc* __restrict__ blocks, int rows, int cpf,
+                                                                         int rotate, float rc, float rs, float2* __restrict__ partial,
+                                                                         int chunks_max)
+{
+  __shared__ float2 red[kChunkThreads / 32];
   const TiBlockDesc b = blocks[blockIdx.y];
   const int cols = 5 * b.n_fec;
   const int n = cols * rows;
   const float* src = reinterpret_cast<const float*>(in + b.in_off);
   float2* dst = out + b.out_off;
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-    const int r = a % cpf;
-    const int an = r == cpf - 1 ? a - (cpf - 1) : a + 1;
-    const uint32_t s1 = __ldg(srcmap + a), s2 = __ldg(srcmap + an);
-    const int k1 = (int)(s1 >> 16) * cols + (int)(s1 & 0xffffu), k2 = (int)(s2 >> 16) * cols + (int)(s2 & 0xffffu);
-    float2 v = make_float2(__ldg(src + 2 * k1), __ldg(src + 2 * k2 + 1));
-    if (ROT) v = make_float2(__fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs)), __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc)));
-    dst[a] = v;
+  for (int c0 = blockIdx.x * kSumChunk; c0 < n; c0 += gridDim.x * kSumChunk) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < kSumChunk / kChunkThreads; ++u) {
+      const int a = c0 + threadIdx.x + u * kChunkThreads;
+      if (a < n) {
+        const int r = a % cpf;
+        const int an = r == cpf - 1 ? a - (cpf - 1) : a + 1;
+        const uint32_t s1 = __ldg(srcmap + a), s2 = __ldg(srcmap + an);
+        const int k1 = (int)(s1 >> 16) * cols + (int)(s1 & 0xffffu), k2 = (int)(s2 >> 16) * cols + (int)(s2 & 0xffffu);
+        float2 v = make_float2(__ldg(src + 2 * k1), __ldg(src + 2 * k2 + 1));
+        if (MOD >= 0) {
+          if (rotate) v = make_float2(__fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs)), __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc)));
+          const float2 t = demap_term<(MOD < 0 ? 0 : MOD)>(v, kNorm[MOD < 0 ? 0 : MOD]);
+          acc.x += t.x; acc.y += t.y;
+        }
+        dst[a] = v;
+      }
+    }
+    if (MOD >= 0) {
+      acc = block_sum2(acc, red);
+      if (threadIdx.x == 0) partial[(size_t)blockIdx.y * chunks_max + c0 / kSumChunk] = acc;
+    }
   }
 }
 
@@ -112,30 +156,52 @@ __device__ __forceinline__ float2 demap_term(float2 v, float a)
   return make_float2(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
 }
 
-// Pass 1a (stand-alone stage only): derotate in place, like the reference (llr_demapper.cpp:555-557), no FMA contraction
-__global__ void demap_derotate_kernel(float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks, float rc, float rs)
+// Pass 1a (stand-alone stage only): derotate in place, like the reference (llr_demapper.cpp:555-557; no FMA contraction), and
+// leave the chunk sums of the statistics terms (see ti_deinterleave_kernel)
+template <int MOD>
+__global__ void __launch_bounds__(kChunkThreads) demap_prepare_kernel(float2* __restrict__ cells, const DemapBlockDesc* __restrict__ blocks,
+                                                                       int rotate, float rc, float rs, float2* __restrict__ partial,
+                                                                       int chunks_max)
 {
+  __shared__ float2 red[kChunkThreads / 32];
   const DemapBlockDesc b = blocks[blockIdx.y];
   float2* c = cells + b.cell_off;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < b.n_cells; k += gridDim.x * blockDim.x) {
-    const float2 v = c[k];
-    c[k] = make_float2(__fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs)), __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc)));
+  for (int c0 = blockIdx.x * kSumChunk; c0 < b.n_cells; c0 += gridDim.x * kSumChunk) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < kSumChunk / kChunkThreads; ++u) {
+      const int k = c0 + threadIdx.x + u * kChunkThreads;
+      if (k < b.n_cells) {
+        float2 v = c[k];
+        if (rotate) {
+          v = make_float2(__fsub_rn(__fmul_rn(v.x, rc), __fmul_rn(v.y, rs)), __fadd_rn(__fmul_rn(v.x, rs), __fmul_rn(v.y, rc)));
+          c[k] = v;
+        }
+        const float2 t = demap_term<MOD>(v, kNorm[MOD]);
+        acc.x += t.x; acc.y += t.y;
+      }
+    }
+    acc = block_sum2(acc, red);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * chunks_max + c0 / kSumChunk] = acc;
   }
 }
 
-// Pass 1b: sum_s / sum_e exactly as the reference accumulates them -- float, in cell order (the one
-// order-dependent reduction of the receiver; every LLR of the TI block is scaled by its result, so a
-// tree sum would flip ~0.1 % of the LLRs by one LSB).  The serial recurrence s <- fl(s + t_k) is evaluated
-// EXACTLY by a parallel scan: while s stays inside one binade [2^e, 2^(e+1)) it is an integer S (units of
-// ulp = 2^(e-23)) and round-to-nearest-even addition of t >= 0 is S += q + [f > 1/2] + [f == 1/2 and S + q odd]
-// with q = floor(t / ulp), f = frac(t / ulp): an integer recurrence whose only state besides S is its parity.
-// So every run of elements is a pair (delta if S starts even, delta if S starts odd), pairs compose
-// associatively, and one CTA scans 8192 elements per pass.  The (rare: ~40 per TI block) additions that carry
-// s into the next binade are found by the scan, executed as one real float addition, and the scan resumes
-// behind them.  tools/ordered_sum_model.py is the bit-level model this kernel follows.
-constexpr int kSumThreads = 512, kSumE = 16, kSumChunk = kSumThreads * kSumE;   // <= 32 registers x 512 threads: fits next to a resident LDPC decoder
-constexpr int kSumSerialHead = 768;        // the sums double every few cells at first: no point scanning there
-constexpr int kSumSat = 1 << 26;           // deltas saturate far above 2^24 (= "left the binade")
+// Pass 1b: sum_s / sum_e exactly as the reference accumulates them -- float, in cell order (the one order-dependent
+// reduction of the receiver; every LLR of the TI block is scaled by its result, so a tree sum would flip ~0.1 % of the LLRs
+// by one LSB).  The serial recurrence s <- fl(s + t_k) is evaluated EXACTLY in parallel: while s stays inside one binade
+// [2^e, 2^(e+1)) it is an integer S (units of ulp = 2^(e-23)) and round-to-nearest-even addition of t >= 0 is
+// S += q + [f > 1/2] + [f == 1/2 and S + q odd] with q = floor(t / ulp), f = frac(t / ulp).  Without an exact tie
+// (f == 1/2: rare) the increment does not depend on S at all, so
+//   demap_sum_chunks_kernel (every chunk of kSumChunk cells of every TI block in parallel) predicts the binade the running sum
+//     is in when it reaches the chunk -- from the tree-order chunk sums the previous pass left -- and adds the chunk's
+//     increments up as one integer;
+//   demap_sum_stitch_kernel (one CTA per TI block and sum) adds the head of the block serially, then walks the chunks: a
+//     chunk whose prediction holds (same binade, no tie, no carry out of the binade) is ONE integer addition; the others
+//     -- the ~20 chunks in which the sum crosses a power of two, a chunk with a tie, a misprediction -- are redone exactly
+//     by the CTA (a scan over (increment if S even, increment if S odd) pairs; the crossing addition itself is a real float
+//     addition).
+// tools/ordered_sum_model.py is the bit-level model of the arithmetic.
+constexpr int kSumSat = 1 << 26;           // increments saturate far above 2^24 (= "left the binade")
 
 struct SumPair { int a0, a1; };            // S + a0 if S is even on entry, S + a1 if odd
 __device__ __forceinline__ int sum_sat(int a, int b) { return min(a + b, kSumSat); }
@@ -166,145 +232,218 @@ __device__ __forceinline__ int sum_apply(int S, uint32_t w)
   return min(S + q + (int)((w >> 30) & 1u) + (int)((w >> 31) & (uint32_t)(S + q) & 1u), kSumSat);
 }
 
-// One CTA per (TI block, sum): blockIdx.y = 0 accumulates |s|^2, 1 accumulates |e|^2 -- the two recurrences are independent.
-// The terms are recomputed from the (derotated) cells wherever they are needed; nothing but the two sums is written.
+struct SumChunk { int es[2]; int d[2]; };  // per chunk and sum: the binade it was evaluated for (-1: not evaluated), the increment
+                                           // (-1: the chunk holds an exact tie)
+
 template <int MOD>
-__global__ void __launch_bounds__(kSumThreads, 4) demap_ordered_sum_kernel(const float2* __restrict__ cells,
-                                                                         const DemapBlockDesc* __restrict__ blocks,
-                                                                         float* __restrict__ sums)
+__global__ void __launch_bounds__(kChunkThreads) demap_sum_chunks_kernel(const float2* __restrict__ cells,
+                                                                          const DemapBlockDesc* __restrict__ blocks,
+                                                                          const float2* __restrict__ partial, int chunks_max,
+                                                                          SumChunk* __restrict__ info)
 {
-  __shared__ SumPair wt[kSumThreads / 32];         // warp totals
-  __shared__ float sh_s;
-  __shared__ int sh_cross[2];                      // first binade crossing of the pass (double-buffered by pass parity)
-  __shared__ float head[kSumSerialHead];
-  int pass = 0;
-  const int which = blockIdx.y;
-  const DemapBlockDesc b = blocks[blockIdx.x];
-  const float2* c = cells + b.cell_off;
-  const float a = kNorm[MOD];
-  auto term = [&](int k) -> float {
-    const float2 t = demap_term<MOD>(__ldg(c + k), a);
-    return which ? t.y : t.x;
-  };
+  __shared__ float2 red[kChunkThreads / 32];
+  __shared__ int ired[kChunkThreads / 32][3];
+  __shared__ int s_es[2];
+  const DemapBlockDesc b = blocks[blockIdx.y];
   const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;           // llr_demapper.cpp:185
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int base = min(n, kSumSerialHead);
-  for (int k = tid; k < base; k += kSumThreads) head[k] = term(k);      // staged so that only the FADD chain is serial
-  __syncthreads();
-  if (tid == 0) {
-    float acc = 0.0f;
-    int k = 0;
-    for (; k + 8 <= base; k += 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = head[k + u];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
-    }
-    for (; k < base; ++k) acc = __fadd_rn(acc, head[k]);
-    sh_s = acc; sh_cross[0] = INT_MAX; sh_cross[1] = INT_MAX;
+  const int c = blockIdx.x + 1;                                        // chunk 0 is the serial head of the stitch kernel
+  const int c0 = c * kSumChunk;
+  if (c0 >= n) return;
+  // the running sums when the chunk is reached, to tree-order accuracy: enough to name their binade almost always
+  float2 pre = make_float2(0.f, 0.f);
+  for (int k = threadIdx.x; k < c; k += kChunkThreads) {
+    const float2 t = __ldg(partial + (size_t)blockIdx.y * chunks_max + k);
+    pre.x += t.x; pre.y += t.y;
   }
+  pre = block_sum2(pre, red);
+  if (threadIdx.x == 0) { s_es[0] = (__float_as_uint(pre.x) >> 23) & 0xff; s_es[1] = (__float_as_uint(pre.y) >> 23) & 0xff; }
   __syncthreads();
-  while (base < n) {
-    const float s0 = sh_s;
-    const uint32_t b0 = __float_as_uint(s0);
-    const int es0 = (b0 >> 23) & 0xff;
-    if (es0 == 0 || es0 == 255) {                                 // zero / denormal / non-finite sum: one plain addition
+  const int es0 = s_es[0], es1 = s_es[1];
+  const float2* cp = cells + b.cell_off + c0;
+  const float a = kNorm[MOD];
+  int d0 = 0, d1 = 0;
+  uint32_t ties = 0;
+#pragma unroll
+  for (int u = 0; u < kSumChunk / kChunkThreads; ++u) {
+    const int k = threadIdx.x + u * kChunkThreads;
+    if (c0 + k < n) {
+      const float2 t = demap_term<MOD>(__ldg(cp + k), a);
+      const uint32_t w0 = sum_elem(es0, __float_as_uint(t.x)), w1 = sum_elem(es1, __float_as_uint(t.y));
+      d0 = sum_sat(d0, (int)(w0 & 0x1ffffffu) + (int)((w0 >> 30) & 1u));
+      d1 = sum_sat(d1, (int)(w1 & 0x1ffffffu) + (int)((w1 >> 30) & 1u));
+      ties |= ((w0 >> 31) & 1u) | ((w1 >> 30) & 2u);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    d0 = sum_sat(d0, __shfl_down_sync(0xffffffffu, d0, off));
+    d1 = sum_sat(d1, __shfl_down_sync(0xffffffffu, d1, off));
+    ties |= __shfl_down_sync(0xffffffffu, ties, off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { ired[warp][0] = d0; ired[warp][1] = d1; ired[warp][2] = (int)ties; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kChunkThreads / 32; ++w) { d0 = sum_sat(d0, ired[w][0]); d1 = sum_sat(d1, ired[w][1]); ties |= (uint32_t)ired[w][2]; }
+    SumChunk o;
+    o.es[0] = (es0 == 0 || es0 == 255) ? -1 : es0; o.es[1] = (es1 == 0 || es1 == 255) ? -1 : es1;
+    o.d[0] = (ties & 1u) ? -1 : d0; o.d[1] = (ties & 2u) ? -1 : d1;
+    info[(size_t)blockIdx.y * chunks_max + c] = o;
+  }
+}
+
+// Exact evaluation of the chunk's terms buf[0 .. m) (staged in shared memory, skewed: see sum_slot) by the CTA, starting from
+// the running sum *sh_s (updated in place): every thread takes a run of kSumE consecutive terms as a (increment if S even,
+// increment if S odd) pair, the pairs compose associatively (warp scan + scan of the warp totals); the thread in whose run
+// the sum leaves the binade finds the addition that does it, which is then made in real float arithmetic, and the scan
+// resumes behind it.  All threads of the CTA call it; it ends with a barrier.
+constexpr int kStitchThreads = 256;
+constexpr int kSumE = kSumChunk / kStitchThreads;                               // terms per thread
+__device__ __forceinline__ int sum_slot(int k) { return k + k / kSumE; }        // the threads' runs start in different banks
+
+__device__ void sum_exact_cta(const float* __restrict__ buf, int m_total, float* sh_s, SumPair* wt, int* sh_cross)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int k0 = 0, pass = 0;
+  if (tid == 0) { sh_cross[0] = INT_MAX; sh_cross[1] = INT_MAX; }
+  __syncthreads();
+  while (k0 < m_total) {
+    const float s = *sh_s;
+    const uint32_t sb = __float_as_uint(s);
+    const int es = (sb >> 23) & 0xff;
+    if (es == 0 || es == 255) {                                     // zero / denormal / non-finite sum: one plain addition
       __syncthreads();
-      if (tid == 0) sh_s = __fadd_rn(s0, term(base));
+      if (tid == 0) *sh_s = __fadd_rn(s, buf[sum_slot(k0)]);
       __syncthreads();
-      ++base;
+      ++k0;
       continue;
     }
-    const int S0 = (int)((b0 & 0x7fffffu) | 0x800000u);
-    const int m = min(kSumChunk, n - base);
-    // A thread's 16 terms as a (delta if S starts even, delta if S starts odd) pair.  Without an exact tie (f == 1/2: about
-    // one term in 2^(shift) -- rare) both deltas are the plain sum of q + [f > 1/2]; only a thread that saw a tie runs the
-    // parity-tracking recurrence.
-    int d0 = 0;
-    uint32_t ties = 0;
-#pragma unroll 8
-    for (int i = 0; i < kSumE; ++i) {
-      const int k = tid * kSumE + i;
-      const float t = k < m ? term(base + k) : 0.0f;
-      const uint32_t w0 = sum_elem(es0, __float_as_uint(t));
-      d0 += (int)(w0 & 0x1ffffffu) + (int)((w0 >> 30) & 1u);
-      ties |= w0;
+    const int S0 = (int)((sb & 0x7fffffu) | 0x800000u);
+    const int lo = max(k0, tid * kSumE), hi = min(m_total, (tid + 1) * kSumE);
+    int x0 = 0, x1 = 1;                                             // pseudo-S started even / odd
+    for (int k = lo; k < hi; ++k) {
+      const uint32_t w = sum_elem(es, __float_as_uint(buf[sum_slot(k)]));
+      x0 = sum_apply(x0, w); x1 = sum_apply(x1, w);
     }
-    SumPair p0 = {min(d0, kSumSat), min(d0, kSumSat)};
-    if (ties >> 31) {
-      int x00 = 0, x01 = 1;                                       // pseudo-S started even / odd
-      for (int i = 0; i < kSumE; ++i) {
-        const int k = tid * kSumE + i;
-        if (k < m) {
-          const uint32_t w0 = sum_elem(es0, __float_as_uint(term(base + k)));
-          x00 = sum_apply(x00, w0); x01 = sum_apply(x01, w0);
-        }
-      }
-      p0.a0 = x00; p0.a1 = x01 - 1;
-    }
-    const SumPair own0 = p0;
-    // inclusive scan inside the warp, warp totals through shared memory
+    SumPair p = {x0, x1 - 1};
+    const SumPair own = p;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      SumPair o0;
-      o0.a0 = __shfl_up_sync(0xffffffffu, p0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, p0.a1, off);
-      if (lane >= off) p0 = sum_compose(o0, p0);
+      SumPair o;
+      o.a0 = __shfl_up_sync(0xffffffffu, p.a0, off); o.a1 = __shfl_up_sync(0xffffffffu, p.a1, off);
+      if (lane >= off) p = sum_compose(o, p);
     }
-    if (lane == 31) wt[warp] = p0;
-    SumPair e0;                                                  // exclusive inside the warp
-    e0.a0 = __shfl_up_sync(0xffffffffu, p0.a0, 1); e0.a1 = __shfl_up_sync(0xffffffffu, p0.a1, 1);
-    if (lane == 0) e0.a0 = e0.a1 = 0;
+    if (lane == 31) wt[warp] = p;
+    SumPair e;                                                      // exclusive inside the warp
+    e.a0 = __shfl_up_sync(0xffffffffu, p.a0, 1); e.a1 = __shfl_up_sync(0xffffffffu, p.a1, 1);
+    if (lane == 0) e.a0 = e.a1 = 0;
     __syncthreads();
-    // every warp scans the warp totals for itself (16 entries: four shuffle steps) -- cheaper than a second barrier
-    SumPair q0;
+    SumPair q;                                                      // every warp scans the warp totals for itself
     {
-      constexpr int NWARP = kSumThreads / 32;
-      SumPair t0 = {0, 0};
-      if (lane < NWARP) t0 = wt[lane];
+      constexpr int NWARP = kStitchThreads / 32;
+      SumPair t = {0, 0};
+      if (lane < NWARP) t = wt[lane];
 #pragma unroll
       for (int off = 1; off < NWARP; off <<= 1) {
-        SumPair o0;
-        o0.a0 = __shfl_up_sync(0xffffffffu, t0.a0, off); o0.a1 = __shfl_up_sync(0xffffffffu, t0.a1, off);
-        if (lane >= off) t0 = sum_compose(o0, t0);
+        SumPair o;
+        o.a0 = __shfl_up_sync(0xffffffffu, t.a0, off); o.a1 = __shfl_up_sync(0xffffffffu, t.a1, off);
+        if (lane >= off) t = sum_compose(o, t);
       }
-      // exclusive prefix of this warp = inclusive total of warp - 1
       const int srcl = warp == 0 ? 0 : warp - 1;
-      SumPair x0;
-      x0.a0 = __shfl_sync(0xffffffffu, t0.a0, srcl); x0.a1 = __shfl_sync(0xffffffffu, t0.a1, srcl);
-      if (warp == 0) x0.a0 = x0.a1 = 0;
-      q0 = sum_compose(x0, e0);
+      SumPair x;
+      x.a0 = __shfl_sync(0xffffffffu, t.a0, srcl); x.a1 = __shfl_sync(0xffffffffu, t.a1, srcl);
+      if (warp == 0) x.a0 = x.a1 = 0;
+      q = sum_compose(x, e);
     }
-    int Sa = sum_sat(S0, (S0 & 1) ? q0.a1 : q0.a0);
-    // S only grows: the binade is left inside this thread's range iff S is still inside before it and outside after it.
-    // Only that thread (at most one per pass) walks its terms to find the addition that does it.
+    int Sa = sum_sat(S0, (S0 & 1) ? q.a1 : q.a0);                   // S when this thread's run starts
     int my_cross = INT_MAX, Sa_before = Sa;
-    const int Sa_out = sum_sat(Sa, (Sa & 1) ? own0.a1 : own0.a0);
+    const int Sout = sum_sat(Sa, (Sa & 1) ? own.a1 : own.a0);
     if (Sa < (1 << 24)) {
-      if (Sa_out >= (1 << 24)) {
-        for (int i = 0; i < kSumE; ++i) {
-          if (my_cross == INT_MAX && tid * kSumE + i < m) {
-            const int na = sum_apply(Sa, sum_elem(es0, __float_as_uint(term(base + tid * kSumE + i))));
-            if (na >= (1 << 24)) { my_cross = tid * kSumE + i; Sa_before = Sa; }
-            else Sa = na;
-          }
+      if (Sout >= (1 << 24)) {                                      // S only grows: at most one thread per pass
+        for (int k = lo; k < hi; ++k) {
+          const int na = sum_apply(Sa, sum_elem(es, __float_as_uint(buf[sum_slot(k)])));
+          if (na >= (1 << 24)) { my_cross = k; Sa_before = Sa; break; }
+          Sa = na;
         }
-      } else Sa = Sa_out;
+      } else Sa = Sout;
     }
-    if (tid == 0) sh_cross[(pass + 1) & 1] = INT_MAX;             // next pass's slot: last read before this pass's first barrier
+    if (tid == 0) sh_cross[(pass + 1) & 1] = INT_MAX;               // next pass's slot: last read before this pass's first barrier
     if (my_cross != INT_MAX) atomicMin(&sh_cross[pass & 1], my_cross);
     __syncthreads();
     const int cross = sh_cross[pass & 1];
     ++pass;
     if (cross == INT_MAX) {
-      if (tid == (m - 1) / kSumE) sh_s = __uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa & 0x7fffffu));   // owner of the last element holds the total
-      base += m;
+      if (tid == (m_total - 1) / kSumE) *sh_s = __uint_as_float(((uint32_t)es << 23) | ((uint32_t)Sa & 0x7fffffu));   // owner of the last term holds the total
+      k0 = m_total;
     } else {
-      if (my_cross == cross && tid == cross / kSumE)              // the crossing addition itself, in real float arithmetic
-        sh_s = __fadd_rn(__uint_as_float(((uint32_t)es0 << 23) | ((uint32_t)Sa_before & 0x7fffffu)), term(base + cross));
-      base += cross + 1;
+      if (my_cross == cross)                                        // the crossing addition itself, in real float arithmetic
+        *sh_s = __fadd_rn(__uint_as_float(((uint32_t)es << 23) | ((uint32_t)Sa_before & 0x7fffffu)), buf[sum_slot(cross)]);
+      k0 = cross + 1;
     }
     __syncthreads();
+  }
+}
+
+constexpr int kStitchInfo = 1024;          // chunk records staged in shared memory (more chunks than that are read from global memory)
+
+template <int MOD>
+__global__ void __launch_bounds__(kStitchThreads) demap_sum_stitch_kernel(const float2* __restrict__ cells,
+                                                                           const DemapBlockDesc* __restrict__ blocks,
+                                                                           const SumChunk* __restrict__ info, int chunks_max,
+                                                                           float* __restrict__ sums)
+{
+  __shared__ float buf[kSumChunk + kStitchThreads];
+  __shared__ int2 inf[kStitchInfo];
+  __shared__ SumPair wt[kStitchThreads / 32];
+  __shared__ float sh_s;
+  __shared__ int sh_cross[2], sh_ch;
+  const int which = blockIdx.y, tid = threadIdx.x;
+  const DemapBlockDesc b = blocks[blockIdx.x];
+  const float2* c = cells + b.cell_off;
+  const float a = kNorm[MOD];
+  const int n = MOD == 0 ? min(b.n_cells, 2048) : b.n_cells;           // llr_demapper.cpp:185
+  const SumChunk* ci = info + (size_t)blockIdx.x * chunks_max;
+  const int nch = (n + kSumChunk - 1) / kSumChunk;
+  for (int k = 1 + tid; k < min(nch, kStitchInfo); k += kStitchThreads) inf[k] = make_int2(__ldg(&ci[k].es[which]), __ldg(&ci[k].d[which]));
+  // the head: the sums double every few cells at first -- plain serial additions, operands staged in shared memory
+  const int nh = min(n, kSumChunk);
+  for (int k = tid; k < nh; k += kStitchThreads) { const float2 t = demap_term<MOD>(__ldg(c + k), a); buf[k] = which ? t.y : t.x; }
+  __syncthreads();
+  int ch = 1;
+  if (tid == 0) {
+    float s = 0.0f;
+    int k = 0;
+    for (; k + 8 <= nh; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = buf[k + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+    }
+    for (; k < nh; ++k) s = __fadd_rn(s, buf[k]);
+    sh_s = s;
+  }
+  for (;;) {
+    // thread 0 takes the chunks whose prediction holds -- one integer addition each -- up to the next one that must be redone
+    if (tid == 0) {
+      float s = sh_s;
+      for (; ch < nch; ++ch) {
+        const int2 rec = ch < kStitchInfo ? inf[ch] : make_int2(__ldg(&ci[ch].es[which]), __ldg(&ci[ch].d[which]));
+        const uint32_t sb = __float_as_uint(s);
+        const int S = (int)((sb & 0x7fffffu) | 0x800000u);
+        if (!((int)((sb >> 23) & 0xff) == rec.x && rec.y >= 0 && S + rec.y < (1 << 24))) break;
+        s = __uint_as_float((sb & 0x7f800000u) | ((uint32_t)(S + rec.y) & 0x7fffffu));
+      }
+      sh_s = s; sh_ch = ch;
+    }
+    __syncthreads();
+    ch = sh_ch;
+    if (ch >= nch) break;
+    const int k0 = ch * kSumChunk, m = min(n, k0 + kSumChunk) - k0;
+    for (int k = tid; k < m; k += kStitchThreads) { const float2 t = demap_term<MOD>(__ldg(c + k0 + k), a); buf[sum_slot(k)] = which ? t.y : t.x; }
+    __syncthreads();
+    sum_exact_cta(buf, m, &sh_s, wt, sh_cross);
+    ++ch;
   }
   if (tid == 0) sums[2 * blockIdx.x + which] = sh_s;
 }
@@ -485,19 +624,30 @@ static int upload_descs(t2b200_ctx* ctx, int slot, const void* h, size_t bytes, 
   return T2B200_OK;
 }
 
-// derotate_mod >= 0: the cells leave already derotated for that constellation (what t2_demap_device then expects)
+static int sum_chunks_max(int max_cells) { return (max_cells + kSumChunk - 1) / kSumChunk; }
+constexpr int kPartialSlot = 11;       // scratch slot of the chunk sums handed from the fused TI pass to the demapper
+
+// fuse_mod >= 0 (frame pipeline): the cells leave derotated (if `rotate`) for that constellation and the chunk sums of the
+// statistics terms are left for t2_demap_device(..., prepared = true)
 int t2_ti_device(t2b200_ctx* ctx, int plp, const float2* d_in, float2* d_out, const TiBlockDesc* d_desc, int n_ti_blocks,
-                 int max_cells, int derotate_mod)
+                 int max_cells, int fuse_mod, int rotate)
 {
   if (!ctx->ti || !ctx->ti->plp.count(plp)) { ctx->err = "TI: PLP not configured"; return T2B200_ERR_STATE; }
   const TiPlp& p = ctx->ti->plp[plp];
-  dim3 grid(std::min((max_cells + 255) / 256, ctx->sm_count * 8), n_ti_blocks);
-  if (derotate_mod >= 0) {
-    const float th = -kRot[derotate_mod & 3];
-    const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
-    ti_deinterleave_kernel<true><<<grid, 256, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec, rc, rs);
+  const int cm = sum_chunks_max(max_cells);
+  dim3 grid(std::max(1, std::min(cm, ctx->sm_count * 8)), n_ti_blocks);
+  if (fuse_mod >= 0) {
+    void* d_part; int rc;
+    if ((rc = t2_dev_scratch(ctx, kPartialSlot, (size_t)n_ti_blocks * cm * sizeof(float2), &d_part))) return rc;
+    const float th = -kRot[fuse_mod & 3];
+    const float rc_ = (float)cos((double)th), rs_ = (float)sin((double)th);   // llr_demapper.cpp:34-41
+#define TI(M) ti_deinterleave_kernel<M><<<grid, kChunkThreads, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec, \
+                                                                              rotate, rc_, rs_, (float2*)d_part, cm)
+    switch (fuse_mod & 3) { case 0: TI(0); break; case 1: TI(1); break; case 2: TI(2); break; default: TI(3); break; }
+#undef TI
   } else {
-    ti_deinterleave_kernel<false><<<grid, 256, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec, 1.0f, 0.0f);
+    ti_deinterleave_kernel<-1><<<grid, kChunkThreads, 0, ctx->stream>>>(d_in, d_out, p.d_src, d_desc, p.rows, p.cells_per_fec, 0, 1.0f, 0.0f,
+                                                                        nullptr, cm);
   }
   T2_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
@@ -532,28 +682,37 @@ extern "C" int t2b200_ti_deinterleave(t2b200_ctx* ctx, int plp, const float* cel
   if ((rc = t2_to_device(ctx, 0, cells_in, (size_t)off * 8, &din))) return rc;
   if ((rc = t2_out_device(ctx, 1, cells_out, (size_t)off * 8, &dout))) return rc;
   if ((rc = upload_descs(ctx, 5, d.data(), d.size() * sizeof(TiBlockDesc), &ddesc))) return rc;
-  if ((rc = t2_ti_device(ctx, plp, (const float2*)din, (float2*)dout, (const TiBlockDesc*)ddesc, n_ti_blocks, max_cells, -1))) return rc;
+  if ((rc = t2_ti_device(ctx, plp, (const float2*)din, (float2*)dout, (const TiBlockDesc*)ddesc, n_ti_blocks, max_cells, -1, 0))) return rc;
   // (the descriptor upload above is a pageable-memory copy: the runtime has consumed the host vector when it returns)
   return t2_finish_out(ctx, cells_out, dout, (size_t)off * 8);
 }
 
 template <int MOD>
 static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_blocks, int max_cells,
-                        int rotation, bool derotated, const int32_t* d_addr, int8_t* d_llr, int cpf, int fec_bits, int max_fec,
+                        int rotation, bool prepared, const int32_t* d_addr, int8_t* d_llr, int cpf, int fec_bits, int max_fec,
                         float* d_prec, float* d_snr, const float* d_prec_in)
 {
-  void* d_sums;
+  void *d_sums, *d_part, *d_info;
   int rc0;
+  const int cm = sum_chunks_max(max_cells);
   if ((rc0 = t2_dev_scratch(ctx, 4, (size_t)n_blocks * 2 * sizeof(float), &d_sums))) return rc0;
-  if (rotation && !derotated) {
-    const int gx = std::max(1, std::min((max_cells + 255) / 256, ctx->sm_count * 8));
+  if ((rc0 = t2_dev_scratch(ctx, kPartialSlot, (size_t)n_blocks * cm * sizeof(float2), &d_part))) return rc0;
+  if ((rc0 = t2_dev_scratch(ctx, 12, (size_t)n_blocks * cm * sizeof(SumChunk), &d_info))) return rc0;
+  const int gx = std::max(1, std::min(cm, ctx->sm_count * 8));
+  if (!prepared) {                       // stand-alone stage: derotate in place + chunk sums (the frame pipeline's TI pass has done both)
     const float th = -kRot[MOD];
     const float rc = (float)cos((double)th), rs = (float)sin((double)th);   // llr_demapper.cpp:34-41
-    demap_derotate_kernel<<<dim3(gx, n_blocks), 256, 0, ctx->stream>>>(d_cells, d_desc, rc, rs);
+    demap_prepare_kernel<MOD><<<dim3(gx, n_blocks), kChunkThreads, 0, ctx->stream>>>(d_cells, d_desc, rotation != 0, rc, rs, (float2*)d_part, cm);
     T2_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
   }
-  demap_ordered_sum_kernel<MOD><<<dim3(n_blocks, 2), kSumThreads, 0, ctx->stream>>>(d_cells, d_desc, (float*)d_sums);
+  if (cm > 1) {
+    demap_sum_chunks_kernel<MOD><<<dim3(cm - 1, n_blocks), kChunkThreads, 0, ctx->stream>>>(d_cells, d_desc, (const float2*)d_part, cm,
+                                                                                           (SumChunk*)d_info);
+    T2_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  demap_sum_stitch_kernel<MOD><<<dim3(n_blocks, 2), kStitchThreads, 0, ctx->stream>>>(d_cells, d_desc, (const SumChunk*)d_info, cm, (float*)d_sums);
   T2_CUDA(ctx, cudaGetLastError());
   auto k = ctx->opt_demap_saturate ? demap_llr_kernel<MOD, true> : demap_llr_kernel<MOD, false>;
   const size_t smem = (size_t)((fec_bits + 15) & ~15);
@@ -566,7 +725,7 @@ static int demap_launch(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* 
 }
 
 int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_ti_blocks, int max_cells,
-                    int max_fec, int mod, int rotation, bool derotated, int fec_type, int code_rate, int8_t* d_llr,
+                    int max_fec, int mod, int rotation, bool prepared, int fec_type, int code_rate, int8_t* d_llr,
                     float* d_prec, float* d_snr, const float* d_prec_in)
 {
   TiDemapState* st = state(ctx);
@@ -582,7 +741,7 @@ int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_de
     st->addr[key] = t;
   }
   const int32_t* daddr = mod ? st->addr[key].d_addr : nullptr;
-#define DM(M) demap_launch<M>(ctx, d_cells, d_desc, n_ti_blocks, max_cells, rotation, derotated, daddr, d_llr, cpf, fec_bits, \
+#define DM(M) demap_launch<M>(ctx, d_cells, d_desc, n_ti_blocks, max_cells, rotation, prepared, daddr, d_llr, cpf, fec_bits, \
                               max_fec, d_prec, d_snr, d_prec_in)
   switch (mod) { case 0: return DM(0); case 1: return DM(1); case 2: return DM(2); default: return DM(3); }
 #undef DM

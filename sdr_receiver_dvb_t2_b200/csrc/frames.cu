@@ -203,7 +203,7 @@ static int frames_decode(t2b200_ctx* ctx, const void* iq, bool i16, float scale,
                                d_sro + (L - 1), d_ph + (L - 1), L))) return rc;
   if ((rc = mark(2))) return rc;
   // K3, K4
-  if ((rc = t2_ti_device(ctx, c.plp, p->d_cells, p->d_tib, p->d_ti, F * nti, p->max_cells, c.rotation ? c.mod : -1))) return rc;
+  if ((rc = t2_ti_device(ctx, c.plp, p->d_cells, p->d_tib, p->d_ti, F * nti, p->max_cells, c.mod, c.rotation))) return rc;
   if ((rc = mark(3))) return rc;
   float* d_prec = p->d_prec; float* d_snr = p->d_prec + (size_t)F * nti;
   if ((rc = t2_demap_device(ctx, p->d_tib, p->d_dm, F * nti, p->max_cells, p->max_fec, c.mod, c.rotation, true, c.fec_type,

@@ -12,10 +12,10 @@ int t2_equalize_device(t2b200_ctx* ctx, int kind, int n_symbols, int per_frame, 
                        long long in_frame, long long in_sym, float2* d_out, long long out_frame, long long out_sym,
                        float* d_sro, float* d_phase, long long fb_frame);
 int t2_ti_device(t2b200_ctx* ctx, int plp, const float2* d_in, float2* d_out, const TiBlockDesc* d_desc, int n_ti_blocks,
-                 int max_cells, int derotate_mod);
+                 int max_cells, int fuse_mod, int rotate);
 int t2_ti_geometry(t2b200_ctx* ctx, int plp, int* cells_per_fec, int* n_fec_max);
 int t2_demap_device(t2b200_ctx* ctx, float2* d_cells, const DemapBlockDesc* d_desc, int n_ti_blocks, int max_cells,
-                    int max_fec, int mod, int rotation, bool derotated, int fec_type, int code_rate, int8_t* d_llr,
+                    int max_fec, int mod, int rotation, bool prepared, int fec_type, int code_rate, int8_t* d_llr,
                     float* d_prec, float* d_snr, const float* d_prec_in);
 int t2_ldpc_device(t2b200_ctx* ctx, int code, const int8_t* d_llr, int n_cw, uint8_t* d_bits, int32_t* d_trials,
                    int32_t* d_iters, int max_trials, unsigned flags);

@@ -1,5 +1,9 @@
-"""Bit-level model of the exact parallel evaluation of the float recurrence s <- fl(s + t_k), t_k >= 0, used by
-demap_ordered_sum_kernel (sdr_receiver_dvb_t2_b200/csrc/demap.cu): run it to check the algorithm against a serial sum."""
+"""Bit-level model of the exact parallel evaluation of the float recurrence s <- fl(s + t_k), t_k >= 0, used by the
+ordered-sum kernels of the demapper (sdr_receiver_dvb_t2_b200/csrc/demap.cu): ordered_sum() is the pair scan a warp runs
+over one chunk (sum_exact_warp), stitched_sum() the whole scheme -- tree-order chunk sums predict the binade of the running
+sum, every chunk is added up as ONE integer for that binade (demap_sum_chunks_kernel), a serial walk over the chunks takes
+the integer where the prediction holds and falls back to the exact scan where it does not (demap_sum_stitch_kernel).  Run
+it to check the algorithm against a serial sum."""
 import numpy as np
 BIG=1<<26
 def elem(Es, tb):
@@ -63,6 +67,54 @@ def ordered_sum(t, CH=64, E=4):
     return s,passes
 
 
+def exact_range(t, k0, k1, s, CH=64, E=2):
+    """cells [k0, k1) added to s exactly (the warp's fallback): ordered_sum() started from s"""
+    n = k1; base = k0
+    while base < n:
+        sb = fbits(s); Es = (sb >> 23) & 0xff
+        if Es == 0 or Es == 255:
+            s = np.float32(s + t[base]); base += 1; continue
+        S = (sb & 0x7fffff) | 0x800000
+        m = min(CH, n - base); crossed = False
+        for k in range(m):
+            q, gt, tie = elem(Es, fbits(t[base + k]))
+            Sn = S + q + gt + (tie & ((S + q) & 1))
+            if Sn >= 1 << 24:
+                s = np.float32(frombits((Es << 23) | (S & 0x7fffff)) + t[base + k]); base += k + 1; crossed = True; break
+            S = Sn
+        if not crossed:
+            s = frombits((Es << 23) | (S & 0x7fffff)); base += m
+    return s
+
+
+def stitched_sum(t, chunk=64):
+    """returns (sum, number of chunks taken as one integer, number redone exactly)"""
+    n = len(t)
+    nch = (n + chunk - 1) // chunk
+    partial = [np.float32(np.sum(t[c * chunk:(c + 1) * chunk], dtype=np.float64)) for c in range(nch)]   # any order will do
+    info = []
+    for c in range(1, nch):
+        pre = np.float32(np.sum(partial[:c], dtype=np.float64))
+        es = (fbits(pre) >> 23) & 0xff
+        d = 0; tie_any = 0
+        for x in t[c * chunk:(c + 1) * chunk]:
+            q, gt, tie = elem(es, fbits(x))
+            d = sat(d + q + gt); tie_any |= tie
+        info.append((-1 if es in (0, 255) else es, -1 if tie_any else d))
+    s = np.float32(0)
+    for x in t[:chunk]:
+        s = np.float32(s + x)
+    fast = slow = 0
+    for c in range(1, nch):
+        es_c, d_c = info[c - 1]
+        sb = fbits(s); S = (sb & 0x7fffff) | 0x800000
+        if ((sb >> 23) & 0xff) == es_c and d_c >= 0 and S + d_c < 1 << 24:
+            s = frombits((sb & 0x7f800000) | ((S + d_c) & 0x7fffff)); fast += 1
+        else:
+            s = exact_range(t, c * chunk, min(n, (c + 1) * chunk), s); slow += 1
+    return s, fast, slow
+
+
 def serial(t):
     s = np.float32(0)
     for x in t:
@@ -93,6 +145,8 @@ def check(trials=300, seed=1, chunk=64, per_thread=4):
         a = serial(t)
         b, _ = ordered_sum(t, CH=chunk, E=per_thread)
         assert fbits(a) == fbits(b), (trial, trial % 5, n, a, b)
+        c, _, _ = stitched_sum(t, chunk=int(rng.choice([16, 64, 256])))
+        assert fbits(a) == fbits(c), ('stitched', trial, trial % 5, n, a, c)
     return trials
 
 
