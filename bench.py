@@ -569,7 +569,7 @@ def run_t2b200(args):
         sg = None
         if world > 1:
             # the exchange runs inside the library (t2b200_ldpc_decode_sharded: NCCL send / recv on a side stream, chunks of
-            # 1024 codewords double-buffered against the decode); torch.distributed only carries the rendezvous id
+            # 1152 codewords double-buffered against the decode); torch.distributed only carries the rendezvous id
             ident = [E.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ident, src=0)
             eng.comm_init(rank, world, ident[0])
@@ -774,7 +774,7 @@ def run_t2b200(args):
                                    'packed_bits': {'value': sg[1] / (sg_pk_ms * 1e-3), 'ms': sg_pk_ms},
                                    'note': 'SURVEY 8e scatter/gather through t2b200_ldpc_decode_sharded: rank 0 holds the LLRs, NCCL send/recv '
                                            'of int8[B/R][64800] out and [B/R][K_bch] bits back (byte per bit; packed_bits: K_bch/8) on a side '
-                                           'stream in 1024-codeword chunks double-buffered against the decode, every rank decodes its shard'}
+                                           'stream in 1152-codeword chunks double-buffered against the decode, every rank decodes its shard'}
         print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:

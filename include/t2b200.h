@@ -286,7 +286,7 @@ int t2b200_frames_stage_ms(t2b200_ctx* ctx, float ms_out[6]);
 /* ---- multi-GPU: the LDPC / BCH stage sharded by codeword over the GPUs of one box --------------------- */
 /* FEC blocks are independent, so one rank demodulates (it holds the int8 LLRs of a pooled batch), every rank decodes a
  * contiguous shard of whole 32-codeword groups and the BBFRAME bits return to that rank: ONE exchange each way, NCCL
- * send / recv over NVLink issued by the library on a side stream, in chunks of <= 1024 codewords double-buffered against
+ * send / recv over NVLink issued by the library on a side stream, in chunks of <= 1152 codewords double-buffered against
  * the decode.  One context (= one GPU) per process; NCCL is loaded at run time (libnccl.so.2).
  *   t2b200_comm_unique_id   rank 0 obtains the rendezvous id (ncclGetUniqueId, 128 bytes) and hands it to the other
  *                           ranks by any means (the tests use torch.distributed, the reference has no such step)

@@ -1,7 +1,7 @@
 // Multi-GPU FEC: FEC blocks are independent, so the LDPC / BCH stage of a pooled batch is sharded by codeword
 // across the GPUs of one box.  ONE exchange step each way -- the int8 LLRs of every rank's shard out from the demodulating
 // rank, the BBFRAME bits back -- as NCCL point-to-point transfers over NVLink / NVSwitch, issued from here (not from
-// Python): a side stream carries the transfers in chunks of <= 1024 codewords, double-buffered against the decode on the
+// Python): a side stream carries the transfers in chunks of <= 1152 codewords, double-buffered against the decode on the
 // context's stream, so a rank decodes chunk t-1 while chunk t arrives and the bits of chunk t-2 leave.
 //
 // NCCL is loaded at run time (dlopen "libnccl.so.2": in a torch process that is the NCCL torch itself uses), so
@@ -21,6 +21,7 @@ struct CommState {
   int8_t* in_buf = nullptr; uint8_t* out_buf = nullptr; size_t in_cap = 0, out_cap = 0;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;    // optional (NCCL >= 2.14)
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -31,7 +32,13 @@ struct CommState {
 
 namespace {
 
-constexpr int kChunk = 1024;          // codewords per transfer (32 lock-step groups)
+// Codewords per transfer: 36 lock-step groups = four full rounds of the nine group slots a B200 decodes at once (a
+// 1024-codeword chunk left a half-empty fourth round: 12 % of the remote ranks' decode time).
+constexpr int kChunk = 1152;
+// NCCL's send / recv kernels get at most this many CTAs: they then live on the four SMs the decoder's 144 CTAs leave free,
+// instead of holding SMs the (cooperatively launched) decoder must wait for.  ~100 GB/s over NVLink is several times what
+// the exchange needs (75 MB per chunk against 2.8 ms of decoding).
+constexpr int kNcclMaxCtas = 4;
 
 bool load_nccl(CommState* s, std::string& err)
 {
@@ -48,6 +55,7 @@ bool load_nccl(CommState* s, std::string& err)
   T2_SYM(Send, "ncclSend") T2_SYM(Recv, "ncclRecv") T2_SYM(GroupStart, "ncclGroupStart") T2_SYM(GroupEnd, "ncclGroupEnd")
   T2_SYM(GetErrorString, "ncclGetErrorString")
 #undef T2_SYM
+  s->CommInitRankConfig = reinterpret_cast<decltype(s->CommInitRankConfig)>(dlsym(s->dl, "ncclCommInitRankConfig"));
   return true;
 }
 
@@ -108,7 +116,13 @@ extern "C" int t2b200_comm_init(t2b200_ctx* ctx, int rank, int nranks, const voi
   s->rank = rank; s->nranks = nranks;
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof(id));
-  T2_NCCL(ctx, s, s->CommInitRank(&s->comm, nranks, id, rank));
+  if (s->CommInitRankConfig) {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.minCTAs = 1; cfg.maxCTAs = kNcclMaxCtas;
+    T2_NCCL(ctx, s, s->CommInitRankConfig(&s->comm, nranks, id, rank, &cfg));
+  } else {
+    T2_NCCL(ctx, s, s->CommInitRank(&s->comm, nranks, id, rank));
+  }
   T2_CUDA(ctx, cudaStreamCreateWithFlags(&s->s_comm, cudaStreamNonBlocking));
   for (cudaEvent_t* e : {&s->ev_start, &s->ev_done, &s->ev_in[0], &s->ev_in[1], &s->ev_dec[0], &s->ev_dec[1]})
     T2_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));

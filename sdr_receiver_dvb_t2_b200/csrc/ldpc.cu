@@ -79,6 +79,24 @@ __device__ __forceinline__ unsigned long long global_ns()
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// the stored messages: thread-private, re-read every iteration -> cached in L2 only, lines marked evict-last so that the
+// streaming traffic (LLRs in, bits out, the other stream's kernels) does not push them out to HBM
+__device__ __forceinline__ uint64_t state_policy()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint32_t state_ld(const uint32_t* p, uint64_t pol)
+{
+  uint32_t v;
+  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void state_st(uint32_t* p, uint32_t v, uint64_t pol)
+{
+  asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
 constexpr unsigned long long kWaitBudgetNs = 20ull * 1000 * 1000 * 1000;   // lock-step waits give up after 20 s (never seen: the lanes are co-resident)
 
 // Poll *w until pred(value); on time-out raise the error flag and return `fallback` so that the CTA leaves cleanly.
@@ -207,6 +225,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
   // (ld/st.cg, next layer's words prefetched a layer ahead), [layer][word][360] per resident CTA.
   uint32_t* const state = p.cn_state + (size_t)blockIdx.x * (size_t)(p.q * NSW * 360) + threadIdx.x;
   __shared__ int s_flag, s_group;
+  const uint64_t pol = state_policy();
 
   const int tid = threadIdx.x;
   const int GL = p.group_lanes;                  // codewords per lock-step group: 32, or 1 (every codeword on its own)
@@ -336,7 +355,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
       const bool stored = iters > 0 && owner;                    // first pass: all messages are zero, nothing to read
       uint32_t nw[NSW];
 #pragma unroll
-      for (int k = 0; k < NSW; ++k) nw[k] = stored ? __ldcg(state + k * 360) : 0u;
+      for (int k = 0; k < NSW; ++k) nw[k] = stored ? state_ld(state + k * 360, pol) : 0u;
       for (int i = 0; i < p.q; ++i) {
         uint32_t* const sp = state + (size_t)i * (NSW * 360);
         uint32_t w[NSW];
@@ -344,7 +363,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
         for (int k = 0; k < NSW; ++k) w[k] = nw[k];
         if (stored && i + 1 < p.q) {
 #pragma unroll
-          for (int k = 0; k < NSW; ++k) nw[k] = __ldcg(sp + (NSW + k) * 360);
+          for (int k = 0; k < NSW; ++k) nw[k] = state_ld(sp + (NSW + k) * 360, pol);
         }
         const int cnt = p.cnt[i];
         const int nl = p.nlev[i];
@@ -362,7 +381,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
               cn.template store<false>(0, cnt, i, tid, w);
             }
 #pragma unroll
-            for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
+            for (int k = 0; k < NSW; ++k) state_st(sp + k * 360, w[k], pol);
           }
           __syncthreads();
         } else {
@@ -445,7 +464,7 @@ __global__ void __maxnreg__((kLdpcRegs<CNL, MINB>)) ldpc_decode_kernel(const __g
           if (owner) {
             cn.template store<false>(ns, cnt, i, tid, w);
 #pragma unroll
-            for (int k = 0; k < NSW; ++k) __stcg(sp + k * 360, w[k]);
+            for (int k = 0; k < NSW; ++k) state_st(sp + k * 360, w[k], pol);
           }
           __syncthreads();
         }
