@@ -2,6 +2,7 @@
 
 Cross-compiles without a GPU.  Rebuilds only when a source is newer than the library.
 """
+import fcntl
 import glob
 import os
 import shutil
@@ -34,10 +35,23 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Several processes may get here at once (one rank per GPU under torchrun): the build runs under a file lock, the
+    library appears atomically (linked under a temporary name, then renamed), latecomers find it up to date."""
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir, verbose):
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -57,7 +71,9 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed for %s:\n%s' % (s, out))
     with open(os.path.join(objdir, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
-    subprocess.run([nvcc, '-shared', *ARCH, '-o', LIB, *objs, '-lcudart'], check=True)
+    tmp = LIB + '.tmp.%d' % os.getpid()
+    subprocess.run([nvcc, '-shared', *ARCH, '-o', tmp, *objs, '-lcudart'], check=True)
+    os.replace(tmp, LIB)
     if verbose:
         print('\n'.join(log))
     return LIB
