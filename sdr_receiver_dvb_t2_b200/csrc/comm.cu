@@ -10,12 +10,16 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 struct CommState {
   void* dl = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  bool wide = false;                  // more than two ranks: wide NCCL kernels, decoders on one group slot less (t2b200_comm_init)
   cudaStream_t s_comm = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_in[2] = {}, ev_dec[2] = {};
   int8_t* in_buf = nullptr; uint8_t* out_buf = nullptr; size_t in_cap = 0, out_cap = 0;
@@ -32,13 +36,9 @@ struct CommState {
 
 namespace {
 
-// Codewords per transfer: 36 lock-step groups = four full rounds of the nine group slots a B200 decodes at once (a
-// 1024-codeword chunk left a half-empty fourth round: 12 % of the remote ranks' decode time).
-constexpr int kChunk = 1152;
-// NCCL's send / recv kernels get at most this many CTAs: they then live on the four SMs the decoder's 144 CTAs leave free,
-// instead of holding SMs the (cooperatively launched) decoder must wait for.  ~100 GB/s over NVLink is several times what
-// the exchange needs (75 MB per chunk against 2.8 ms of decoding).
-constexpr int kNcclMaxCtas = 4;
+constexpr int kNcclMaxCtasDefault = 2;      // see t2b200_comm_init
+
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; }
 
 bool load_nccl(CommState* s, std::string& err)
 {
@@ -59,13 +59,19 @@ bool load_nccl(CommState* s, std::string& err)
   return true;
 }
 
-// contiguous shard of rank r: whole 32-codeword lock-step groups (the reference's batch, ldpc_decoder.h:28-32)
-void span_of(int n_cw, int r, int nranks, int* lo, int* hi)
+// contiguous shard of rank r: whole 32-codeword lock-step groups (the reference's batch, ldpc_decoder.h:28-32), in proportion
+// to the group slots each rank decodes on (weight[r])
+void span_of(int n_cw, int r, const std::vector<int>& weight, int* lo, int* hi)
 {
-  const int units = (n_cw + 31) / 32, base = units / nranks, extra = units % nranks;
-  const int lo_u = r * base + std::min(r, extra), hi_u = lo_u + base + (r < extra ? 1 : 0);
-  *lo = std::min(lo_u * 32, n_cw); *hi = std::min(hi_u * 32, n_cw);
+  const long long units = (n_cw + 31) / 32;
+  long long wsum = 0, wlo = 0;
+  for (size_t i = 0; i < weight.size(); ++i) { wsum += weight[i]; if ((int)i < r) wlo += weight[i]; }
+  const long long lo_u = units * wlo / wsum, hi_u = units * (wlo + weight[r]) / wsum;
+  *lo = (int)std::min<long long>(lo_u * 32, n_cw); *hi = (int)std::min<long long>(hi_u * 32, n_cw);
 }
+
+// more than two ranks (T2B200_SHARD_WIDE=0 / 1 forces it: development aid)
+bool wide_mode(int nranks) { const int e = env_int("T2B200_SHARD_WIDE", -1); return e >= 0 ? e != 0 : nranks > 2; }
 
 CommState g_loader;                   // t2b200_comm_unique_id needs NCCL before any context has a communicator
 
@@ -116,9 +122,17 @@ extern "C" int t2b200_comm_init(t2b200_ctx* ctx, int rank, int nranks, const voi
   s->rank = rank; s->nranks = nranks;
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof(id));
+  // NCCL's send / recv kernels share the SMs with the decoder.  Next to the decoder's full grid (9 group slots = 144 CTAs) only
+  // TWO NCCL CTAs find room (measured: with three or more the cooperative decoder launch and the NCCL kernel wait for each
+  // other and the exchange serialises with the decoding; profiles/r02_sharded_experiments.txt) -- ~70 GB/s, enough between
+  // two ranks.  With more ranks the root has to feed everybody (1.8 GB per 8 x 4032 codewords while one shard decodes):
+  // every rank then decodes on 8 of the 9 slots and NCCL gets 16 CTAs (~350 GB/s out of the root).  The setting must be the
+  // same on all ranks of a communicator (NCCL fails otherwise).
+  s->wide = wide_mode(nranks);
   if (s->CommInitRankConfig) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
-    cfg.minCTAs = 1; cfg.maxCTAs = kNcclMaxCtas;
+    const int max_ctas = env_int("T2B200_NCCL_MAX_CTAS", s->wide ? 16 : kNcclMaxCtasDefault);      // (development aid; 0: NCCL's default)
+    if (max_ctas > 0) { cfg.minCTAs = 1; cfg.maxCTAs = max_ctas; }
     T2_NCCL(ctx, s, s->CommInitRankConfig(&s->comm, nranks, id, rank, &cfg));
   } else {
     T2_NCCL(ctx, s, s->CommInitRank(&s->comm, nranks, id, rank));
@@ -160,17 +174,34 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
     if (!k_out) { ctx->err = "code has no BCH geometry"; return T2B200_ERR_ARG; }
   }
   const size_t row = (flags & T2B200_LDPC_PACK_BITS) ? (size_t)k_out / 8 : (size_t)k_out;
+  const bool trace = getenv("T2B200_SHARD_TRACE") != nullptr;      // (development aid: device times of every exchange / decode step)
+  std::vector<cudaEvent_t> tr;
+  auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tr.push_back(e); } };
+  // wide mode (see t2b200_comm_init): every decoder leaves 20 SMs to the NCCL kernels
+  const int full_slots = std::max(1, ctx->sm_count / 16);
+  const int slots = s->wide ? std::max(1, full_slots - 1) : full_slots;
+  struct SlotsCap { t2b200_ctx* c; int old; ~SlotsCap() { c->ldpc_slots_cap = old; } } cap_guard{ctx, ctx->ldpc_slots_cap};
+  ctx->ldpc_slots_cap = env_int("T2B200_SHARD_SLOTS", s->wide ? slots : 0);
+  std::vector<int> weight(s->nranks, 1);
+  // codewords per transfer: four full rounds of the group slots (a chunk that leaves a half-empty last round costs the remote
+  // ranks 12 % of their decode time)
+  const int kChunk = std::max(32, env_int("T2B200_SHARD_CHUNK", 4 * slots * 32) / 32 * 32);      // (development aid)
+  // chunk t of a shard: a short first chunk (one round of the nine group slots) so that the remote decoders start almost at
+  // once, full-size chunks behind it
+  const int kFirst = std::max(32, std::min(kChunk, env_int("T2B200_SHARD_FIRST", slots * 32) / 32 * 32));
   std::vector<int> lo(s->nranks), hi(s->nranks);
+  auto chunk_off = [&](int t) { return t <= 0 ? 0 : kFirst + (t - 1) * kChunk; };
+  auto chunk_n = [&](int r, int t) { return t < 0 ? 0 : std::max(0, std::min(chunk_off(t + 1), hi[r] - lo[r]) - chunk_off(t)); };
   int rounds = 0;
   for (int r = 0; r < s->nranks; ++r) {
-    span_of(n_cw, r, s->nranks, &lo[r], &hi[r]);
-    if (r != root) rounds = std::max(rounds, (hi[r] - lo[r] + kChunk - 1) / kChunk);
+    span_of(n_cw, r, weight, &lo[r], &hi[r]);
+    if (r != root) while (chunk_n(r, rounds)) ++rounds;
   }
-  auto chunk_n = [&](int r, int t) { return t < 0 ? 0 : std::max(0, std::min(kChunk, hi[r] - lo[r] - t * kChunk)); };
   int rc;
   // everything queued on the context's stream so far (the LLRs on the root, earlier users of the buffers) comes first
   T2_CUDA(ctx, cudaEventRecord(s->ev_start, ctx->stream));
   T2_CUDA(ctx, cudaStreamWaitEvent(s->s_comm, s->ev_start, 0));
+  mark(ctx->stream);
   if (is_root) {
     // The root's own shard decodes on the context's stream while the side stream moves the other shards.  The decode is
     // queued FIRST: its 144 CTAs then hold their SMs and the few CTAs of NCCL's send / recv kernels (which sit waiting for
@@ -186,12 +217,14 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
       for (int r = 0; r < s->nranks; ++r) {
         if (r == root) continue;
         if (const int n = chunk_n(r, t))
-          T2_NCCL(ctx, s, s->Send(llr + (size_t)(lo[r] + t * kChunk) * N, (size_t)n * N, ncclInt8, r, s->comm, s->s_comm));
+          T2_NCCL(ctx, s, s->Send(llr + (size_t)(lo[r] + chunk_off(t)) * N, (size_t)n * N, ncclInt8, r, s->comm, s->s_comm));
         if (const int n = chunk_n(r, t - 2))
-          T2_NCCL(ctx, s, s->Recv(bits_out + (size_t)(lo[r] + (t - 2) * kChunk) * row, (size_t)n * row, ncclUint8, r, s->comm, s->s_comm));
+          T2_NCCL(ctx, s, s->Recv(bits_out + (size_t)(lo[r] + chunk_off(t - 2)) * row, (size_t)n * row, ncclUint8, r, s->comm, s->s_comm));
       }
       T2_NCCL(ctx, s, s->GroupEnd());
+      mark(s->s_comm);
     }
+    mark(ctx->stream);
   } else {
     const int r = s->rank;
     if (s->in_cap < 2 * (size_t)kChunk * N) {
@@ -217,16 +250,25 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
       if (n_in) T2_NCCL(ctx, s, s->Recv(in, (size_t)n_in * N, ncclInt8, root, s->comm, s->s_comm));
       if (n_out) T2_NCCL(ctx, s, s->Send(out, (size_t)n_out * row, ncclUint8, root, s->comm, s->s_comm));
       T2_NCCL(ctx, s, s->GroupEnd());
+      mark(s->s_comm);
       if (n_in) {
         T2_CUDA(ctx, cudaEventRecord(s->ev_in[t & 1], s->s_comm));
         T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_in[t & 1], 0));
         if ((rc = t2_ldpc_device(ctx, code, in, n_in, out, nullptr, nullptr, max_trials, flags))) return rc;
         T2_CUDA(ctx, cudaEventRecord(s->ev_dec[t & 1], ctx->stream));
+        mark(ctx->stream);
       }
     }
   }
   // later work on the context's stream sees the gathered bits (root) / may re-use the buffers (others)
   T2_CUDA(ctx, cudaEventRecord(s->ev_done, s->s_comm));
   T2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, s->ev_done, 0));
+  if (trace) {
+    cudaStreamSynchronize(ctx->stream);
+    std::string line = "shard trace rank " + std::to_string(s->rank) + ":";
+    for (size_t i = 1; i < tr.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, tr[0], tr[i]); char b[32]; snprintf(b, sizeof b, " %.2f", ms); line += b; }
+    fprintf(stderr, "%s\n", line.c_str());
+    for (auto e : tr) cudaEventDestroy(e);
+  }
   return T2B200_OK;
 }

@@ -34,6 +34,8 @@ struct t2b200_ctx {
   int opt_ldpc_plain_launch = 0;              // T2B200_OPT_LDPC_PLAIN_LAUNCH
   int opt_bch_correct = 0;                    // T2B200_OPT_BCH_CORRECT
   int opt_stage_timing = 0;                   // T2B200_OPT_STAGE_TIMING
+  int ldpc_slots_cap = 0;                     // > 0: lock-step decodes use at most this many group slots (16 CTAs each): the sharded
+                                              // FEC stage leaves SMs to the NCCL kernels that way (comm.cu)
   std::map<int, LdpcDeviceCode*> ldpc;        // by code id
   float* d_lut = nullptr;                     // sin | cos tables of DSP/fast_math.h, 2 x 65536 floats
   uint8_t* d_prbs = nullptr;                  // BB descrambler PRBS, 54000 bytes

@@ -651,7 +651,8 @@ static int ldpc_launch(t2b200_ctx* ctx, LdpcDeviceCode* d, const int8_t* d_llr, 
   int grid;
   if (p.group_lanes > 1) {
     const int n_groups = (n_cw + 31) / 32;
-    const int slots = std::min(capacity / 16, n_groups);            // a lock-step group of 32 codewords = 16 CTAs
+    int slots = std::min(capacity / 16, n_groups);                  // a lock-step group of 32 codewords = 16 CTAs
+    if (ctx->ldpc_slots_cap > 0) slots = std::min(slots, ctx->ldpc_slots_cap);
     if (slots < 1) { ctx->err = "GPU cannot co-schedule one 32-lane group"; return T2B200_ERR_CUDA; }
     grid = slots * 16;
     p.gsync = ctx->d_group_sync + sync_off * kSyncStride;
