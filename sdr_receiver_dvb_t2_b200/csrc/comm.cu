@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -186,11 +187,20 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
   // codewords per transfer: four full rounds of the group slots (a chunk that leaves a half-empty last round costs the remote
   // ranks 12 % of their decode time)
   const int kChunk = std::max(32, env_int("T2B200_SHARD_CHUNK", 4 * slots * 32) / 32 * 32);      // (development aid)
-  // chunk t of a shard: a short first chunk (one round of the nine group slots) so that the remote decoders start almost at
-  // once, full-size chunks behind it
+  // chunk t of a shard: a short first chunk (one round of the group slots) so that the remote decoders start almost at once,
+  // then chunks that double up to kChunk (wide mode: 2 x kChunk; measured, profiles/r02_sharded_experiments.txt): every chunk ends with a tail in which group slots wait for the
+  // chunk's slowest lock-step group, so the fewer and larger the later chunks the better -- as long as a chunk still arrives
+  // while the one before it decodes
   const int kFirst = std::max(32, std::min(kChunk, env_int("T2B200_SHARD_FIRST", slots * 32) / 32 * 32));
+  const int kMaxChunk = kChunk * std::max(1, env_int("T2B200_SHARD_GROW", s->wide ? 2 : 1));
   std::vector<int> lo(s->nranks), hi(s->nranks);
-  auto chunk_off = [&](int t) { return t <= 0 ? 0 : kFirst + (t - 1) * kChunk; };
+  std::vector<int> offs(1, 0);                                    // chunk boundaries inside a shard (the same for every rank)
+  {
+    int longest = 0;
+    for (int r = 0; r < s->nranks; ++r) { int a, b; span_of(n_cw, r, weight, &a, &b); longest = std::max(longest, b - a); }
+    for (int sz = kFirst; offs.back() < longest; sz = std::min(2 * sz, kMaxChunk)) offs.push_back(offs.back() + sz);
+  }
+  auto chunk_off = [&](int t) { return t <= 0 ? 0 : t < (int)offs.size() ? offs[t] : INT_MAX / 2; };
   auto chunk_n = [&](int r, int t) { return t < 0 ? 0 : std::max(0, std::min(chunk_off(t + 1), hi[r] - lo[r]) - chunk_off(t)); };
   int rounds = 0;
   for (int r = 0; r < s->nranks; ++r) {
@@ -227,23 +237,23 @@ extern "C" int t2b200_ldpc_decode_sharded(t2b200_ctx* ctx, int code, int root, c
     mark(ctx->stream);
   } else {
     const int r = s->rank;
-    if (s->in_cap < 2 * (size_t)kChunk * N) {
+    if (s->in_cap < 2 * (size_t)kMaxChunk * N) {
       T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       cudaFree(s->in_buf); s->in_buf = nullptr; s->in_cap = 0;
-      T2_CUDA(ctx, cudaMalloc(&s->in_buf, 2 * (size_t)kChunk * N));
-      s->in_cap = 2 * (size_t)kChunk * N;
+      T2_CUDA(ctx, cudaMalloc(&s->in_buf, 2 * (size_t)kMaxChunk * N));
+      s->in_cap = 2 * (size_t)kMaxChunk * N;
     }
-    if (s->out_cap < 2 * (size_t)kChunk * row) {
+    if (s->out_cap < 2 * (size_t)kMaxChunk * row) {
       T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       cudaFree(s->out_buf); s->out_buf = nullptr; s->out_cap = 0;
-      T2_CUDA(ctx, cudaMalloc(&s->out_buf, 2 * (size_t)kChunk * row));
-      s->out_cap = 2 * (size_t)kChunk * row;
+      T2_CUDA(ctx, cudaMalloc(&s->out_buf, 2 * (size_t)kMaxChunk * row));
+      s->out_cap = 2 * (size_t)kMaxChunk * row;
     }
     for (int t = 0; t < rounds + 2; ++t) {
       const int n_in = chunk_n(r, t), n_out = chunk_n(r, t - 2);
       if (!n_in && !n_out) continue;
-      int8_t* in = s->in_buf + (size_t)(t & 1) * kChunk * N;
-      uint8_t* out = s->out_buf + (size_t)(t & 1) * kChunk * row;
+      int8_t* in = s->in_buf + (size_t)(t & 1) * kMaxChunk * N;
+      uint8_t* out = s->out_buf + (size_t)(t & 1) * kMaxChunk * row;
       // round t re-uses the buffers of round t - 2: its decode must be over (it is what the send below carries anyway)
       if (t >= 2) T2_CUDA(ctx, cudaStreamWaitEvent(s->s_comm, s->ev_dec[t & 1], 0));
       T2_NCCL(ctx, s, s->GroupStart());

@@ -21,8 +21,12 @@ N, K, KB = eng.ldpc_geometry(code)
 flags = E.LDPC_GROUP32 | E.LDPC_BCH_DESCRAMBLE
 llr = out = None
 if rank == 0:
-    base, _ = O.make_llr(code, 256, 2.9, seed=2)
-    llr = torch.from_numpy(np.tile(base, ((per * world + 255) // 256, 1))[:per * world].copy()).to(dev)
+    # lock-step groups of different difficulty (like demapped LLRs: the iteration count of a group is its slowest codeword's)
+    rng = np.random.default_rng(1)
+    pools = [O.make_llr(code, 32, eb, seed=2 + k)[0] for k, eb in enumerate((2.5, 2.7, 2.9, 2.9, 3.1, 3.3))]
+    pick = rng.integers(0, len(pools), (per + 31) // 32)
+    shard = np.concatenate([pools[k] for k in pick])[:per]
+    llr = torch.from_numpy(np.tile(shard, (world, 1))).to(dev)
     out = torch.empty((per * world, KB), dtype=torch.uint8, device=dev)
     one = torch.empty((per, KB), dtype=torch.uint8, device=dev)
     eng.ldpc_decode(code, llr[:per], flags=flags, out=one, want_status=False)
