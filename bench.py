@@ -690,6 +690,8 @@ def run_t2b200(args):
             import glob
             cands = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ldpc_v*.summary.csv')))
             for ln in open(cands[-1]):
+                if ln.startswith('#') or ln.count(',') < 2:
+                    continue
                 k, _, val = ln.strip().split(',')[:3]
                 if k == 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active':
                     ldpc_ncu['alu_pipe_busy_pct'] = float(val)
@@ -752,7 +754,7 @@ def run_t2b200(args):
                                      'note': 'wrapping cast: every group runs 25 trials and is dropped, as in the reference'},
             'roofline': {'bound': 'hbm', 'kernel': 'ldpc_decode_kernel', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'note': 'posteriors live in shared memory, check-node messages in L2: not HBM-bound by construction '
+                         'note': 'posteriors live in shared memory, stored messages in L2 (evict-last policy): not HBM-bound by construction '
                                  '(SURVEY 8d) -- the limiter is the ALU pipe under per-layer barriers (ncu below); '
                                  'algorithmic bytes = N + K_bch per codeword; streaming stages: see "stages"',
                          'ncu': ldpc_ncu},

@@ -92,9 +92,13 @@ def test_post_fft_chain_bit_exact_c32_256qam(engine):
     llr_o = np.concatenate(llr_o)
     assert np.array_equal(r['precision'].cpu().numpy(), np.array(prec_o, np.float32))
     assert np.array_equal(r['llr'].cpu().numpy(), llr_o)
-    tr, bits_o, _ = O.port_ldpc_decode(2, llr_o[:32], 25)
-    assert tr == -1 and (r['trials_left'].cpu().numpy()[:32] == -1).all()         # the reference drops this batch
-    assert np.array_equal(r['bits'].cpu().numpy()[:32], O.bch_strip_descramble(bits_o, 43200, 43040))
+    # every lock-step group of the frame (6 x 32 + the trailing 10), not just the first
+    tl, bits = r['trials_left'].cpu().numpy(), r['bits'].cpu().numpy()
+    for g0 in range(0, 202, 32):
+        g1 = min(g0 + 32, 202)
+        tr, bits_o, _ = O.port_ldpc_decode(2, llr_o[g0:g1], 25)
+        assert tr == -1 and (tl[g0:g1] == -1).all()                               # the reference drops every batch
+        assert np.array_equal(bits[g0:g1], O.bch_strip_descramble(bits_o, 43200, 43040))
 
 
 def test_c32_256qam_decodes_with_saturating_cast_option(engine):

@@ -16,7 +16,7 @@ def golden():
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'fec_ref.npz'))
 
 
-@pytest.mark.parametrize('name', ['A_s64_r35', 'D_sqpsk_r12', 'G_s64_r23', 'B_n16_r12', 'F_n64_r35', 'H_n256_r34'])
+@pytest.mark.parametrize('name', ['A_s64_r35', 'D_sqpsk_r12', 'G_s64_r23', 'B_n16_r12', 'F_n64_r35', 'H_n256_r34', 'E_n256_r23'])
 def test_port_ti_and_demap_match_reference_golden(name, golden):
     stream, blocks = config_input(name)
     if sha(stream) != str(golden[name + '_in_sha']):
