@@ -184,6 +184,56 @@ def ldpc_sweep_cpu(seconds_per_rate=2.0):
 _W = {}
 
 
+def frontend_bench(torch, t2, E, local, stream, peak, n_streams=64, calls=10):
+    """N2: the receiver front-end (int16 I/Q -> DC / IQ / NCO -> Farrow resampler -> half-band decimator) for
+    n_streams independent streams, one 32K + GI 1/128 symbol's worth of samples per stream and call, inputs and outputs
+    resident in HBM; the same chunk through the oracle port on one host core beside it."""
+    import numpy as np
+    dev = torch.device('cuda', local)
+    chunk_in = 32768 + 256                                  # est_chunk * resample * upsample at resample = 0.5
+    eng = t2.Engine(local, stream=stream.cuda_stream)
+    eng.frontend_configure(n_streams, chunk_in)
+    with torch.cuda.stream(stream):
+        iq = (torch.randn((2, n_streams, chunk_in), device=dev) * 2500.0).round().to(torch.int16)
+        out = torch.empty((n_streams, chunk_in // 2 + 8), dtype=torch.complex64, device=dev)
+    chunks = np.zeros(n_streams, E.FE_CHUNK)
+    chunks['len_in'], chunks['short_to_float'], chunks['c1'], chunks['c2'] = chunk_in, 2.0 ** -14, 0.002, 1.003
+    chunks['frequency_est_filtered'], chunks['phase_nco'], chunks['resample'] = 2.3e-7, 0.4, 0.5
+    for _ in range(3):
+        eng.frontend_execute(iq[0], iq[1], chunks, out=out)
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    e0.record(stream)
+    for _ in range(calls):
+        _, res = eng.frontend_execute(iq[0], iq[1], chunks, out=out)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / calls
+    launches = (eng.launches - l0) // calls
+    samples = n_streams * chunk_in
+    alg = samples * 4 + int(res['len_out'].sum()) * 8       # int16 I/Q in, complex64 out
+    r = {'streams': n_streams, 'input_samples_per_call': samples, 'ms_per_call': ms, 'msamples_per_s': samples / (ms * 1e-3) / 1e6,
+         'realtime_multiple_of_one_stream': samples / (ms * 1e-3) / (2 * 64e6 / 7), 'kernels_per_call': int(launches),
+         'algorithmic_bytes_per_call': alg, 'gb_s': alg / (ms * 1e-3) / 1e9, 'hbm_frac': alg / (ms * 1e-3) / 1e9 / peak,
+         'note': 'one t2b200_frontend_execute call per chunk (4 kernels + the read-back of the chunk lengths the host loop needs), '
+                 'device buffers; time includes that host round trip'}
+    try:
+        from oracle import pyoracle as O
+        fe = O.PortFrontend()
+        hi, hq = iq[0, 0].cpu().numpy(), iq[1, 0].cpu().numpy()
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 2.0:
+            fe.chunk(hi, hq, 2.0 ** -14, 0.002, 1.003, 2.3e-7, 0.4, 0.5)
+            n += 1
+        r['cpu_port_1core_msamples_per_s'] = n * chunk_in / (time.perf_counter() - t0) / 1e6
+    except Exception as e:
+        r['cpu_port_1core_msamples_per_s'] = 'failed: %s' % e
+    eng.close()
+    return r
+
+
 def workload_config(world):
     """`config` of the JSON line: identical in both arms (the driver compares them)"""
     return {'workload': '8MHz 32K ext PP7 GI1/128 SISO, 1 PLP 256-QAM rotated r2/3 64800, TI 67/67/68: whole hot path '
@@ -528,8 +578,12 @@ def run_t2b200(args):
             print('ts_packetize failed: %s' % e, file=sys.stderr)
 
         # ---- BASELINE configs 3 and 4 next to the headline (single-GPU runs only: they are not part of the scaling curve) ----
-        sweep, cfg4 = None, None
+        sweep, cfg4, fe_bench = None, None, None
         if world == 1 and not os.environ.get('T2B200_BENCH_SKIP_EXTRAS'):
+            try:
+                fe_bench = frontend_bench(torch, t2, E, local, stream, hbm_peak()[0])
+            except Exception as e:
+                fe_bench = 'failed: %s' % e
             try:
                 sweep = ldpc_sweep(torch, eng, E, dev, stream)
             except Exception as e:
@@ -765,7 +819,7 @@ def run_t2b200(args):
             line['extra'] = {'config3_ldpc_sweep': {'gpu': sweep, 'cpu_reference_all_cores': None,
                                                     'note': 'BASELINE config 3: 64800-bit codes, lock-step groups of 32 (reference batch semantics), '
                                                             'BCH strip + BB descramble fused, B codewords resident in HBM; all-zero codeword + BPSK/AWGN int8 LLRs'},
-                             'config4_16k_64qam_r35_short': cfg4}
+                             'config4_16k_64qam_r35_short': cfg4, 'n2_frontend': fe_bench}
             try:
                 line['extra']['config3_ldpc_sweep']['cpu_reference_all_cores'] = ldpc_sweep_cpu()
             except Exception as e:

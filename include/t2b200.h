@@ -283,6 +283,51 @@ int t2b200_frames_decode_i16(t2b200_ctx* ctx, const int16_t* iq, float scale, in
 int t2b200_frames_stage_ms(t2b200_ctx* ctx, float ms_out[6]);
 
 
+/* ---- N2: receiver front-end, the step in front of the FFT -------------------------------------------- */
+/* One chunk (about one OFDM symbol) of int16 I/Q of each of n_streams independent streams goes through what
+ * dvbt2_demodulator::execute does per chunk (dvbt2_demodulator.cpp:178-221): int16 -> float, DC removal
+ * (DSP/loop_filters.hh:58-73), the 1-bit IQ-imbalance statistics (:256-265) and correction (:191-192), the NCO
+ * derotation (:194-212, sin / cos tables of DSP/fast_math.h), the Farrow resampler (DSP/interpolator_farrow.hh:41-68) and
+ * the half-band decimator (DSP/filter_decimator.h:72-131).  The five per-sample recurrences of the reference are evaluated
+ * in closed form per chunk (csrc/frontend_kernels.h), so a launch is parallel over samples and streams; the loop filters
+ * and the symbol state machine stay the host's (the reference's dvbt2_demodulator, which hands the loop values in here).
+ * Parity: the NCO phase is reproduced exactly; samples agree with the reference to 2e-6 of the signal RMS (it is built
+ * -Ofast; DC average, resampler phase and statistics are summed in another order), chunk lengths exactly.
+ *   t2b200_frontend_configure   n_streams streams, chunks of at most max_chunk_in input samples (<= 262 144); resets them
+ *   t2b200_frontend_reset       dvbt2_demodulator::reset (:111-127) for one stream (-1: all): zero state, x1 = -0.5
+ *   t2b200_frontend_execute     one chunk per stream:
+ *     i_in, q_in   sample n of stream s at i_in[s * stream_stride + n * sample_step] (the reference's two pointers and its
+ *                  convert_input, dvbt2_demodulator.cpp:181-183); host or device memory
+ *     chunk        [n_streams] (host): what the host loop knows, see t2b200_fe_chunk
+ *     out          complex<float>[n_streams][out_stride]: the decimator output (out_decimator, :220)
+ *     result       [n_streams] (host): number of samples written, the chunk's contribution to theta1..3 (:256-265)
+ *   t2b200_frontend_get_state / _set_state   the carried state of one stream (tests, checkpointing)
+ *   t2b200_cp_correlate         guard-interval correlation of dvbt2_demodulator.cpp:321-330 for n_symbols buffered symbols
+ *                               (guard + fft_size samples each, symbol_stride apart): frequency_est[n_symbols]          */
+typedef struct {
+  int   len_in;                   /* chunk, dvbt2_demodulator.cpp:165-167 */
+  float short_to_float;           /* 2^-14 (sdrplay), 2^-12 (airspy), 2^-11 (plutosdr), :35-52 */
+  float c1, c2;                   /* IQ-imbalance correction of this execute() call, :240-243 */
+  float frequency_est_filtered;   /* NCO decrement per input sample, :194 */
+  float phase_nco;                /* after the per-chunk update of :170-176 */
+  float resample;                 /* (float)arbitrary_resample, :162-163, interpolator_farrow.hh:45 */
+} t2b200_fe_chunk;
+typedef struct { int len_out, len_interp; float theta1, theta2, theta3; } t2b200_fe_result;
+typedef struct {
+  float dc_re, dc_im, frequency_nco, x1;
+  float delay[3][2];              /* the last three derotated samples, newest first (delay_data_1.._3) */
+  float hist[63][2];              /* the 63 resampler outputs in front of the next one, oldest first (the decimator's buffer) */
+  int   parity, pad;              /* filter_decimator::execute's static d */
+} t2b200_fe_state;
+int t2b200_frontend_configure(t2b200_ctx* ctx, int n_streams, int max_chunk_in);
+int t2b200_frontend_reset(t2b200_ctx* ctx, int stream);
+int t2b200_frontend_execute(t2b200_ctx* ctx, const int16_t* i_in, const int16_t* q_in, long long stream_stride, int sample_step,
+                            const t2b200_fe_chunk* chunk, float* out, long long out_stride, t2b200_fe_result* result);
+int t2b200_frontend_get_state(t2b200_ctx* ctx, int stream, t2b200_fe_state* state);
+int t2b200_frontend_set_state(t2b200_ctx* ctx, int stream, const t2b200_fe_state* state);
+int t2b200_cp_correlate(t2b200_ctx* ctx, const float* symbols, int n_symbols, long long symbol_stride, int fft_size, int guard,
+                        float* frequency_est);
+
 /* ---- multi-GPU: the LDPC / BCH stage sharded by codeword over the GPUs of one box --------------------- */
 /* FEC blocks are independent, so one rank demodulates (it holds the int8 LLRs of a pooled batch), every rank decodes a
  * contiguous shard of whole 32-codeword groups and the BBFRAME bits return to that rank: ONE exchange each way, NCCL

@@ -56,6 +56,11 @@ def port():
         L.port_atan2_approx.argtypes = [C.c_float, C.c_float]
         L.port_atan2_approx.restype = C.c_float
         L.port_sincos_lut.argtypes = [C.c_void_p, C.c_void_p]
+        L.port_fe_reset.argtypes = [C.c_void_p]
+        L.port_fe_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        L.port_fe_cp_correlate.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.port_fe_cp_correlate.restype = C.c_float
         _port = L
     return _port
 
@@ -186,7 +191,8 @@ def ref_chain():
         L.ref_demod_feed.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_demod_params.argtypes = [_i32p]
         L.ref_tap_fft_arm.argtypes = [C.c_int]
-        for n in ('fft_in', 'fft_info'):
+        L.ref_tap_frontend_arm.argtypes = [C.c_int, C.c_int]
+        for n in ('fft_in', 'fft_info', 'fe_info', 'fe_derot', 'fe_interp', 'fe_decim'):
             f = getattr(L, 'ref_tap_' + n)
             f.argtypes = [C.c_void_p, C.c_longlong]
             f.restype = C.c_longlong
@@ -413,14 +419,48 @@ class PortTs:
         return None if n < 0 else out[:n].copy()
 
 
+class PortFrontend:
+    """oracle/port/frontend_port.c: the receiver front-end of one stream, chunk by chunk (dvbt2_demodulator.cpp:178-221).
+    The state is exposed as a numpy record so that a test can start from a state the reference reported."""
+    STATE = np.dtype([('dc_re', 'f4'), ('dc_im', 'f4'), ('frequency_nco', 'f4'), ('x1', 'f4'), ('delay', 'f4', (3, 2)),
+                      ('hist', 'f4', (63, 2)), ('parity', 'i4')])
+
+    def __init__(self):
+        self.L = port()
+        assert self.L.port_fe_state_size() == self.STATE.itemsize
+        self.state = np.zeros(1, self.STATE)
+        self.L.port_fe_reset(self.state.ctypes.data)
+        self.theta = np.zeros(3, np.float32)
+
+    def chunk(self, i16, q16, short_to_float, c1, c2, frequency_est_filtered, phase_nco, resample, stride=1):
+        """-> (decimator output complex64, resampler output complex64, derotated samples complex64)"""
+        i16 = np.ascontiguousarray(i16, np.int16)
+        q16 = np.ascontiguousarray(q16, np.int16)
+        n = len(i16) // stride
+        derot = np.empty(n, np.complex64)
+        interp = np.empty(int(n / max(float(np.float32(resample)), 0.2)) + 8, np.complex64)
+        out = np.empty(len(interp) // 2 + 2, np.complex64)
+        n_interp = C.c_int()
+        k = self.L.port_fe_chunk(self.state.ctypes.data, i16.ctypes.data, q16.ctypes.data, stride, n, short_to_float, c1, c2,
+                                 frequency_est_filtered, phase_nco, resample, derot.ctypes.data, interp.ctypes.data,
+                                 C.byref(n_interp), out.ctypes.data, self.theta.ctypes.data)
+        return out[:k].copy(), interp[:n_interp.value].copy(), derot
+
+
+def port_cp_correlate(sym, fft_size, guard):
+    sym = np.ascontiguousarray(sym, np.complex64)
+    return float(port().port_fe_cp_correlate(sym.ctypes.data, fft_size, guard))
+
+
 class RefDemod:
     """The reference's whole receiver, dvbt2_demodulator::execute (dvbt2_demodulator.cpp:145-254) down to the TS sink, fed
     with int16 I/Q in front-end sized chunks.  One instance per process (the stages keep static state).  Besides the
     taps of RefFec it records the FFT input window of every OFDM symbol (`in_fft`, dvbt2_demodulator.cpp:332)."""
 
-    def __init__(self, sample_rate=64e6 / 7, need_plp=0, tap_fft=True):
+    def __init__(self, sample_rate=64e6 / 7, need_plp=0, tap_fft=True, tap_frontend=(0, 0)):
         self.L = ref_chain()
         self.L.ref_demod_new(float(sample_rate), need_plp)
+        self.L.ref_tap_frontend_arm(int(tap_frontend[0]), int(tap_frontend[1]))
         self.L.ref_tap_fft_arm(1 if tap_fft else 0)
         self.status = []
 
@@ -430,6 +470,18 @@ class RefDemod:
         for a in range(0, len(i16), chunk):
             n = min(chunk, len(i16) - a)
             self.status.append(self.L.ref_demod_feed(n, i16[a:a + n].ctypes.data, q16[a:a + n].ctypes.data))
+
+    FE_INFO = ['len_in', 'len_interp', 'resample', 'phase_nco', 'frequency_est_filtered', 'c1', 'c2', 'frequency_nco_after',
+               'dc_re_after', 'dc_im_after', 'len_out', 'short_to_float', 'x1_after', 'n_interp_after']
+
+    def frontend_taps(self):
+        """Per chunk of dvbt2_demodulator::execute (oracle/ref_chain.cc, oracle_tap_farrow): the loop parameters and state
+        (FE_INFO) of every chunk; for the chunks of the armed window (first, count) the derotated samples (resampler input),
+        the resampler output and the decimator output, back to back."""
+        info = _tap(self.L, 'fe_info', np.float64).reshape(-1, 16)[:, :14]
+        info[:, 10] = np.floor(info[:, 10])
+        return {'info': info, 'derot': _tap(self.L, 'fe_derot', np.complex64), 'interp': _tap(self.L, 'fe_interp', np.complex64),
+                'decim': _tap(self.L, 'fe_decim', np.complex64)}
 
     def params(self):
         out = np.zeros(16, np.int32)

@@ -106,6 +106,46 @@ void bb_de_header::finished() {}
 void bb_de_header::ts_stage(QString) {}
 
 // ------------------------------------------------------------------------------------------
+// Front-end taps: oracle/tap/DSP/*.h wrap the reference's resampler and decimator and report every call
+// here.  At the resampler call of a chunk (dvbt2_demodulator.cpp:216-218) the demodulator's members still hold what
+// the per-sample loop of that chunk used (:170-213), so one record per chunk is: the chunk length, the loop parameters,
+// the loop state after the chunk, the derotated samples (the resampler's input), its output and the decimator's output.
+struct FeTap {
+  int first = 0, count = 0;                       // samples are kept for chunks first .. first + count - 1
+  long long n_interp = 0;                         // resampler outputs so far: its parity is the decimator's phase
+  std::vector<double> info;                       // FE_REC doubles per chunk, all chunks, see oracle_tap_farrow
+  std::vector<std::complex<float>> derot, interp, decim;
+};
+enum { FE_REC = 16 };
+static FeTap g_fe_tap;
+static dvbt2_demodulator* g_demod = nullptr;
+extern "C" void oracle_tap_farrow(int len_in, const void* in, double resample, int len_out, const void* out)
+{
+  if (g_fe_tap.count <= 0 || !g_demod) return;
+  const dvbt2_demodulator* d = g_demod;
+  const int idx = (int)(g_fe_tap.info.size() / FE_REC);
+  g_fe_tap.n_interp += len_out;
+  const double rec[FE_REC] = {(double)len_in, (double)len_out, resample, d->phase_nco, d->frequency_est_filtered, d->c1, d->c2,
+                              d->frequency_nco, d->exp_avg_dc_real.out, d->exp_avg_dc_imag.out, 0.0, (double)d->short_to_float,
+                              (double)d->interpolator.impl.x1, (double)g_fe_tap.n_interp, 0.0, 0.0};
+  g_fe_tap.info.insert(g_fe_tap.info.end(), rec, rec + FE_REC);
+  if (idx < g_fe_tap.first || idx >= g_fe_tap.first + g_fe_tap.count) return;
+  const std::complex<float>* a = static_cast<const std::complex<float>*>(in);
+  const std::complex<float>* b = static_cast<const std::complex<float>*>(out);
+  g_fe_tap.derot.insert(g_fe_tap.derot.end(), a, a + len_in);
+  g_fe_tap.interp.insert(g_fe_tap.interp.end(), b, b + len_out);
+}
+extern "C" void oracle_tap_decimator(int len_in, const void*, int len_out, const void* out)
+{
+  const int n = (int)(g_fe_tap.info.size() / FE_REC);
+  if (n == 0 || g_fe_tap.info[FE_REC * (n - 1) + 10] != 0.0 || g_fe_tap.info[FE_REC * (n - 1) + 1] != (double)len_in) return;
+  g_fe_tap.info[FE_REC * (n - 1) + 10] = (double)len_out + 0.5;   // + 0.5: marks the record complete even for len_out == 0
+  if (n - 1 < g_fe_tap.first || n - 1 >= g_fe_tap.first + g_fe_tap.count) return;
+  const std::complex<float>* b = static_cast<const std::complex<float>*>(out);
+  g_fe_tap.decim.insert(g_fe_tap.decim.end(), b, b + len_out);
+}
+
+// ------------------------------------------------------------------------------------------
 // Part 2: stage-level C API
 namespace {
 
@@ -337,10 +377,14 @@ TAP_GETTER(ref_tap_bb_len, g_taps.bb_len, int)
 TAP_GETTER(ref_tap_snr, g_taps.snr, float)
 TAP_GETTER(ref_tap_ts, OracleTsSink::get().bytes, char)
 TAP_GETTER(ref_tap_ts_datagrams, OracleTsSink::get().datagram_len, int)
+void ref_tap_frontend_arm(int first, int count) { g_fe_tap = FeTap(); g_fe_tap.first = first; g_fe_tap.count = count; }
+TAP_GETTER(ref_tap_fe_info, g_fe_tap.info, double)
+TAP_GETTER(ref_tap_fe_derot, g_fe_tap.derot, std::complex<float>)
+TAP_GETTER(ref_tap_fe_interp, g_fe_tap.interp, std::complex<float>)
+TAP_GETTER(ref_tap_fe_decim, g_fe_tap.decim, std::complex<float>)
 void ref_tap_clear() { g_taps.clear(); OracleTsSink::get().bytes.clear(); OracleTsSink::get().datagram_len.clear(); }
 
 // full receiver: dvbt2_demodulator::execute on int16 I/Q chunks (dvbt2_demodulator.cpp:145-254)
-static dvbt2_demodulator* g_demod = nullptr;
 static signal_estimate g_sig;
 
 // Tap on the FFT input of every OFDM symbol (the `in_fft` window of dvbt2_demodulator.cpp:332): the reference calls

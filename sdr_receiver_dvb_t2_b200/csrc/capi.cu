@@ -9,6 +9,7 @@ void t2_ts_free(t2b200_ctx* ctx);
 void t2_frames_free(t2b200_ctx* ctx);
 void t2_comm_free(t2b200_ctx* ctx);
 void t2_bch_free(t2b200_ctx* ctx);
+void t2_fe_free(t2b200_ctx* ctx);
 
 bool t2_is_device_ptr(const void* p)
 {
@@ -139,6 +140,7 @@ void t2b200_destroy(t2b200_ctx* ctx)
   t2_frames_free(ctx);
   t2_comm_free(ctx);
   t2_bch_free(ctx);
+  t2_fe_free(ctx);
   if (ctx->d_prbs) cudaFree(ctx->d_prbs);
   if (ctx->d_group_sync) cudaFree(ctx->d_group_sync);
   if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
@@ -192,3 +194,4 @@ __attribute__((weak)) void t2_ts_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_frames_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_comm_free(t2b200_ctx*) {}
 __attribute__((weak)) void t2_bch_free(t2b200_ctx*) {}
+__attribute__((weak)) void t2_fe_free(t2b200_ctx*) {}

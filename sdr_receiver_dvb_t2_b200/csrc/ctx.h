@@ -16,6 +16,7 @@ struct TsState;          // ts.cu
 struct FramePipe;        // frames.cu
 struct CommState;        // comm.cu
 struct BchState;         // bch.cu
+struct FeState;          // frontend.cu
 
 struct Scratch {
   void* p = nullptr; size_t cap = 0; bool pinned_host = false;
@@ -48,6 +49,7 @@ struct t2b200_ctx {
   TsState* ts = nullptr;
   FramePipe* frames = nullptr;
   BchState* bch = nullptr;                    // GF(2^16) / GF(2^14) tables of the opt-in BCH decoder
+  FeState* fe = nullptr;                      // receiver front-end streams (t2b200_frontend_configure)
   CommState* comm = nullptr;                  // NCCL communicator of the sharded FEC stage (t2b200_comm_init)
   // staging scratch, grown on demand
   Scratch dev[16];
@@ -81,3 +83,5 @@ int t2_out_device(t2b200_ctx* ctx, int slot, void* dst, size_t bytes, void** dpt
 int t2_finish_out(t2b200_ctx* ctx, void* dst, const void* dptr, size_t bytes);
 // T2B200_ERR_CUDA (and ctx->err) if a kernel raised the device error flag since the last check; synchronous
 int t2_check_device_flag(t2b200_ctx* ctx);
+// the {cos, sin} tables of DSP/fast_math.h on the device (ctx->d_lut), built on first use (equalizer.cu)
+int t2_ensure_lut(t2b200_ctx* ctx);

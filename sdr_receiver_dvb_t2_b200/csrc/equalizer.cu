@@ -309,7 +309,7 @@ void t2_eq_free(t2b200_ctx* ctx)
   if (ctx->d_lut) { cudaFree(ctx->d_lut); ctx->d_lut = nullptr; }
 }
 
-static int ensure_lut(t2b200_ctx* ctx)
+int t2_ensure_lut(t2b200_ctx* ctx)
 {
   if (ctx->d_lut) return T2B200_OK;
   std::vector<float> h(2 * 65536, 0.0f);                          // DSP/fast_math.h:25-40: entry 65535 stays 0; {cos, sin} pairs
@@ -331,7 +331,7 @@ extern "C" int t2b200_eq_configure(t2b200_ctx* ctx, int kind, int n_symbols, int
   }
   T2_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = ensure_lut(ctx))) return rc;
+  if ((rc = t2_ensure_lut(ctx))) return rc;
   T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   free_tables(ctx->sym[kind]); ctx->sym[kind] = nullptr;
   SymbolTables* t = new SymbolTables();

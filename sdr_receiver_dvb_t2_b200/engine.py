@@ -35,6 +35,8 @@ SYMBOLS = [
     't2b200_mode_init', 't2b200_pilot_tables', 't2b200_eq_configure_mode', 't2b200_frames_decode_i16',
     't2b200_comm_unique_id', 't2b200_comm_init', 't2b200_comm_destroy', 't2b200_ldpc_decode_sharded',
     't2b200_bch_t', 't2b200_bch_decode', 't2b200_frames_stage_ms',
+    't2b200_frontend_configure', 't2b200_frontend_reset', 't2b200_frontend_execute', 't2b200_frontend_get_state',
+    't2b200_frontend_set_state', 't2b200_cp_correlate',
 ]
 
 
@@ -51,6 +53,13 @@ class Mode(C.Structure):
                                        'n_p2', 'c_p2', 'c_data', 'n_fc', 'c_fc', 'l_fc', 'n_data', 'len_frame', 'dx', 'dy')] + \
                [(n, C.c_float) for n in ('amp_p2', 'amp_sp', 'amp_cp')]
 
+
+# t2b200_fe_state / t2b200_fe_chunk / t2b200_fe_result as numpy record types
+FE_STATE = np.dtype([('dc_re', 'f4'), ('dc_im', 'f4'), ('frequency_nco', 'f4'), ('x1', 'f4'), ('delay', 'f4', (3, 2)),
+                     ('hist', 'f4', (63, 2)), ('parity', 'i4'), ('pad', 'i4')])
+FE_CHUNK = np.dtype([('len_in', 'i4'), ('short_to_float', 'f4'), ('c1', 'f4'), ('c2', 'f4'), ('frequency_est_filtered', 'f4'),
+                     ('phase_nco', 'f4'), ('resample', 'f4')])
+FE_RESULT = np.dtype([('len_out', 'i4'), ('len_interp', 'i4'), ('theta', 'f4', (3,))])
 
 FFT_MODE = {'16K': 4, '32K': 5}
 GI_MODE = {'1/32': 0, '1/16': 1, '1/8': 2, '1/4': 3, '1/128': 4, '19/128': 5, '19/256': 6}
@@ -110,6 +119,12 @@ def lib():
     L.t2b200_comm_init.argtypes = [vp, i32, i32, vp, C.c_size_t]
     L.t2b200_comm_destroy.argtypes = [vp]
     L.t2b200_ldpc_decode_sharded.argtypes = [vp, i32, i32, vp, i32, vp, i32, u32]
+    L.t2b200_frontend_configure.argtypes = [vp, i32, i32]
+    L.t2b200_frontend_reset.argtypes = [vp, i32]
+    L.t2b200_frontend_execute.argtypes = [vp, vp, vp, C.c_longlong, i32, vp, vp, C.c_longlong, vp]
+    L.t2b200_frontend_get_state.argtypes = [vp, i32, vp]
+    L.t2b200_frontend_set_state.argtypes = [vp, i32, vp]
+    L.t2b200_cp_correlate.argtypes = [vp, vp, i32, C.c_longlong, i32, i32, vp]
     L.t2b200_mode_init.argtypes = [i32] * 6 + [C.POINTER(Mode)]
     L.t2b200_pilot_tables.argtypes = [C.POINTER(Mode), i32, vp, vp]
     L.t2b200_eq_configure_mode.argtypes = [vp, C.POINTER(Mode)]
@@ -196,6 +211,47 @@ class Engine:
         ms = (C.c_float * 6)()
         self._chk(self.L.t2b200_frames_stage_ms(self.h, ms))
         return dict(zip(('fft', 'equalize', 'ti_deinterleave', 'demap', 'ldpc_bch', 'call'), [float(x) for x in ms]))
+
+    # ---- N2: receiver front-end ----
+    def frontend_configure(self, n_streams, max_chunk_in):
+        self._chk(self.L.t2b200_frontend_configure(self.h, n_streams, max_chunk_in))
+        self._fe_streams = n_streams
+
+    def frontend_reset(self, stream=-1):
+        self._chk(self.L.t2b200_frontend_reset(self.h, stream))
+
+    def frontend_state(self, stream):
+        st = np.zeros(1, FE_STATE)
+        self._chk(self.L.t2b200_frontend_get_state(self.h, stream, st.ctypes.data))
+        return st[0]
+
+    def frontend_set_state(self, stream, state):
+        st = np.zeros(1, FE_STATE)
+        st[0] = state
+        self._chk(self.L.t2b200_frontend_set_state(self.h, stream, st.ctypes.data))
+
+    def frontend_execute(self, i_in, q_in, chunks, out=None, stream_stride=None, sample_step=1):
+        """i_in, q_in: int16 [n_streams][...] (numpy or torch cuda); chunks: FE_CHUNK[n_streams].
+        -> (out complex64 [n_streams][out_stride], results FE_RESULT[n_streams])"""
+        n = self._fe_streams
+        chunks = np.ascontiguousarray(chunks, FE_CHUNK)
+        assert len(chunks) == n
+        if stream_stride is None:
+            stream_stride = int(i_in.shape[1]) if len(i_in.shape) > 1 else 0
+        if out is None:
+            worst = int((int(chunks['len_in'].max()) + 1) / float(chunks['resample'].min()) + 2) // 2 + 2
+            out = _like(i_in, (n, worst), np.complex64)
+        res = np.zeros(n, FE_RESULT)
+        self._chk(self.L.t2b200_frontend_execute(self.h, _ptr(i_in), _ptr(q_in), stream_stride, sample_step, chunks.ctypes.data,
+                                                 _ptr(out), int(out.shape[1]), res.ctypes.data))
+        return out, res
+
+    def cp_correlate(self, symbols, fft_size, guard):
+        """symbols: complex64 [n][guard + fft_size] -> frequency_est float32[n] (dvbt2_demodulator.cpp:321-330)"""
+        est = _like(symbols, (symbols.shape[0],), np.float32)
+        self._chk(self.L.t2b200_cp_correlate(self.h, _ptr(symbols), int(symbols.shape[0]), int(symbols.shape[1]), fft_size, guard,
+                                             _ptr(est)))
+        return est
 
     @property
     def launches(self):

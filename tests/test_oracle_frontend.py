@@ -1,0 +1,49 @@
+"""The front-end oracle (oracle/port/frontend_port.c) pinned to the reference: against tests/golden/frontend_ref.npz (what
+the unmodified receiver computed for a window of chunks after lock, tools/make_golden_frontend.py) and, where the compiled
+reference is present, against a live run of it with every sample of the window compared."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from tests import fe_helpers as F
+
+
+def run_port(w, keep):
+    i16, q16, off = F.stream_input(w)
+    fe = O.PortFrontend()
+    for k, v in w['state'].items():
+        fe.state[k] = v
+    for k, row in enumerate(w['info']):
+        a, b = off[k], off[k + 1]
+        out, interp, derot = fe.chunk(i16[a:b], q16[a:b], **F.chunk_args(row))
+        assert len(interp) == int(row[F.COL['len_interp']])
+        F.check_against(w, k, derot, out, keep)
+        s = fe.state[0]
+        # the carried loop state follows the reference's exactly (NCO) / to float rounding (DC average)
+        assert np.float32(s['frequency_nco']) == np.float32(row[F.COL['frequency_nco_after']])
+        assert abs(s['dc_re'] - row[F.COL['dc_re_after']]) < 1e-9 and abs(s['x1'] - row[F.COL['x1_after']]) < 1e-6
+    return len(w['info'])
+
+
+def test_port_equals_the_golden_window():
+    assert run_port(F.load_golden(), F.KEEP) == F.COUNT - 1
+
+
+@pytest.mark.skipif(not O.have_ref('libref_chain.so'), reason='compiled reference not present')
+def test_port_equals_the_reference_live_and_the_fixture_is_current():
+    t = F.run_reference()
+    w = F.window(t)
+    w['iq_sha'] = str(t['iq_sha'])
+    assert run_port(w, 1) == F.COUNT - 1
+    g = F.load_golden()
+    assert g['iq_sha'] == w['iq_sha'] and np.array_equal(g['info'], w['info'])
+    assert all(np.array_equal(a[::F.KEEP], b) for a, b in zip(w['decim'], g['decim']))
+
+
+def test_cp_correlation_port_recovers_a_known_rotation():
+    rng = np.random.default_rng(0)
+    n, g = 16384, 512
+    sym = (rng.normal(size=n + g) + 1j * rng.normal(size=n + g)).astype(np.complex64)
+    sym[n:] = sym[:g] * np.exp(-0.2j)
+    est = O.port_cp_correlate(sym.astype(np.complex64), n, g)
+    assert abs(est * 2 * n + 0.2) < 0.02
