@@ -195,7 +195,7 @@ def frontend_bench(torch, t2, E, local, stream, peak, n_streams=64, calls=10):
     eng.frontend_configure(n_streams, chunk_in)
     with torch.cuda.stream(stream):
         iq = (torch.randn((2, n_streams, chunk_in), device=dev) * 2500.0).round().to(torch.int16)
-        out = torch.empty((n_streams, chunk_in // 2 + 8), dtype=torch.complex64, device=dev)
+        out = torch.empty((n_streams, chunk_in + 8), dtype=torch.complex64, device=dev)
     chunks = np.zeros(n_streams, E.FE_CHUNK)
     chunks['len_in'], chunks['short_to_float'], chunks['c1'], chunks['c2'] = chunk_in, 2.0 ** -14, 0.002, 1.003
     chunks['frequency_est_filtered'], chunks['phase_nco'], chunks['resample'] = 2.3e-7, 0.4, 0.5

@@ -150,7 +150,7 @@ def test_chunks_equal_the_oracle(resample):
             assert abs(nxt['x1'][s] - ps['x1']) < 1e-5 and abs(nxt['dc_re'][s] - ps['dc_re']) < 1e-8
             assert np.abs(nxt['delay'][s] - ps['delay']).max() <= 2e-6 * rms and np.abs(nxt['hist'][s] - ps['hist']).max() <= 2e-6 * rms
             theta[s] += res['theta'][s]                            # the reference adds sample by sample into one float per call
-            assert np.allclose(theta[s], ports[s].theta, rtol=3e-5, atol=1e-4 * rms), (k, s, theta[s], ports[s].theta)
+            assert np.abs(theta[s] - ports[s].theta).max() <= 3e-5 * max(np.abs(ports[s].theta).max(), rms)     # theta1 is a cancelling sum, (k, s, theta[s], ports[s].theta)
         states = nxt
 
 
