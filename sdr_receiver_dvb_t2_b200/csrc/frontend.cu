@@ -7,8 +7,8 @@
 // CPU against the oracle.
 //
 // Per call: fe_dc_partial_kernel (one CTA per 1 024 input samples: weighted tile sums of the DC average) ->
-// fe_plan_kernel (one thread per stream: state at every tile boundary, output counts) -> fe_derotate_kernel (one CTA per
-// 1 024 input samples) -> fe_resample_kernel (one CTA per 512 outputs + one per stream that commits the carried state).
+// fe_plan_kernel (one CTA per stream, the walk itself one thread: state at every tile boundary, output counts) -> fe_derotate_kernel (one CTA per
+// 1 024 input samples) -> fe_resample_kernel (one CTA per 1 024 outputs + one per stream that commits the carried state).
 // Algorithmic traffic per input sample at resample = 0.5: 4 B in, 8 B out; the derotated samples (8 B) make one round trip
 // through L2 between the two passes.
 #include "ctx.h"
@@ -33,11 +33,7 @@ struct FeState {
 };
 
 __global__ void __launch_bounds__(FE_THREADS) fe_dc_partial_kernel(FeArgs A) { fe_dc_partial_body(A, blockIdx.y, blockIdx.x); }
-__global__ void fe_plan_kernel(FeArgs A, int n_streams)
-{
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < n_streams) fe_plan_stream(A, s);          // every thread plans one stream
-}
+__global__ void __launch_bounds__(64) fe_plan_kernel(FeArgs A) { fe_plan_body(A, blockIdx.x); }
 __global__ void __launch_bounds__(FE_THREADS) fe_derotate_kernel(FeArgs A) { fe_derotate_body(A, blockIdx.y, blockIdx.x); }
 __global__ void __launch_bounds__(FE_THREADS) fe_resample_kernel(FeArgs A) { fe_resample_body(A, blockIdx.y, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(FE_THREADS) fe_cp_correlate_kernel(const float2* sym, long long stride, int fft_size, int guard, float* est)
@@ -86,7 +82,7 @@ extern "C" int t2b200_frontend_configure(t2b200_ctx* ctx, int n_streams, int max
   T2_CUDA(ctx, cudaMalloc(&f->d_plan, S * sizeof(FePlan)));
   T2_CUDA(ctx, cudaMalloc(&f->d_dc_part, S * FE_MAX_TILES * sizeof(double2)));
   T2_CUDA(ctx, cudaMalloc(&f->d_theta_part, S * FE_MAX_TILES * 3 * sizeof(double)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_derot, S * (size_t)max_chunk_in * sizeof(float2)));
+  T2_CUDA(ctx, cudaMalloc(&f->d_derot, S * ((size_t)max_chunk_in + 4) * sizeof(float2)));
   T2_CUDA(ctx, cudaMalloc(&f->d_result, S * sizeof(FeResult)));
   T2_CUDA(ctx, cudaMallocHost(&f->h_chunk, S * sizeof(FeChunk)));
   T2_CUDA(ctx, cudaMallocHost(&f->h_result, S * sizeof(FeResult)));
@@ -98,6 +94,7 @@ extern "C" int t2b200_frontend_configure(t2b200_ctx* ctx, int n_streams, int max
   T2_CUDA(ctx, cudaMemcpy(f->d_apow, apow.data(), apow.size() * sizeof(double), cudaMemcpyHostToDevice));
   T2_CUDA(ctx, cudaMemcpy(f->d_ainv, ainv.data(), ainv.size() * sizeof(double), cudaMemcpyHostToDevice));
   T2_CUDA(ctx, cudaMemcpy(f->d_h, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  T2_CUDA(ctx, cudaMemcpyToSymbol(fe_c_h, h.data(), h.size() * sizeof(float)));
   return t2b200_frontend_reset(ctx, -1);
 }
 
@@ -182,16 +179,16 @@ extern "C" int t2b200_frontend_execute(t2b200_ctx* ctx, const int16_t* i_in, con
   A.in_stride = stream_stride; A.step = sample_step;
   A.chunk = f->d_chunk; A.cur = f->d_state[f->cur]; A.next = f->d_state[f->cur ^ 1];
   A.plan = f->d_plan; A.dc_part = f->d_dc_part; A.theta_part = f->d_theta_part;
-  A.derot = f->d_derot; A.derot_stride = f->max_chunk;
+  A.derot = f->d_derot; A.derot_stride = f->max_chunk + 4;
   A.out = static_cast<float2*>(d_out); A.out_stride = out_stride;
   A.result = f->d_result; A.apow = f->d_apow; A.ainv = f->d_ainv;
   A.lut_cs = reinterpret_cast<const float2*>(ctx->d_lut); A.h = f->d_h;
-  const int nt_in = (max_in + FE_TILE_IN - 1) / FE_TILE_IN;
+  const int nt_in = max_in > 0 ? (max_in + FE_TILE_IN - 1) / FE_TILE_IN : 1;     // tile 0 always runs: it lays out the resampler's delay line
   if (nt_in > 0) {
     fe_dc_partial_kernel<<<dim3(nt_in, S), FE_THREADS, 0, ctx->stream>>>(A);
     ctx->launches++;
   }
-  fe_plan_kernel<<<(S + 63) / 64, 64, 0, ctx->stream>>>(A, S);
+  fe_plan_kernel<<<S, 64, 0, ctx->stream>>>(A);
   ctx->launches++;
   if (nt_in > 0) {
     fe_derotate_kernel<<<dim3(nt_in, S), FE_THREADS, 0, ctx->stream>>>(A);

@@ -45,15 +45,17 @@ FE_FN float fe_mul(float a, float b) { return a * b; }                // the emu
 FE_FN float fe_add(float a, float b) { return a + b; }
 FE_FN float fe_sub(float a, float b) { return a - b; }
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 #endif
 
 enum {
   FE_TILE_IN = 1024,         // input samples per CTA of the derotation pass
-  FE_TILE_OUT = 512,         // decimator outputs per CTA of the resampling pass
+  FE_TILE_OUT = 1024,        // decimator outputs per CTA of the resampling pass (four per thread)
   FE_THREADS = 256,
   FE_TAPS = 64,
   FE_MAX_SEG = 48,           // linear NCO segments kept per tile before the planner falls back to single steps
+  FE_MAX_CHUNK_SEG = 96,     // linear NCO segments of a whole chunk (more: every tile plans for itself)
   FE_MAX_TILES = 256         // input tiles per chunk (262 144 samples)
 };
 #define FE_DC_RATIO 1.0e-6f  /* dvbt2_demodulator.h:88 */
@@ -80,6 +82,9 @@ struct FePlan {              // written by fe_plan_body, read by the two passes
   float x1_next; int parity_next;
   float nco_next; float dc_re_next, dc_im_next;
   float nco_start[FE_MAX_TILES];         // frequency_nco before the first sample of the tile
+  int n_seg;                             // > 0: the NCO phase of the whole chunk as linear segments (fe_nco_run) ...
+  int seg_k0[FE_MAX_CHUNK_SEG]; float seg_v0[FE_MAX_CHUNK_SEG]; double seg_inc[FE_MAX_CHUNK_SEG];
+                                         // ... 0: the chunk needs more segments than that, every tile plans from nco_start
   double2 dc_start[FE_MAX_TILES];        // DC average before the first sample of the tile
 };
 
@@ -93,7 +98,7 @@ struct FeArgs {
   FePlan* plan;                                  // [n_streams]
   double2* dc_part;                              // [n_streams][FE_MAX_TILES]
   double* theta_part;                            // [n_streams][FE_MAX_TILES][3]
-  float2* derot; long long derot_stride;         // [n_streams][derot_stride]
+  float2* derot; long long derot_stride;         // [n_streams][derot_stride]: delay_data_3, _2, _1 of the carried state, then the chunk
   float2* out; long long out_stride;             // [n_streams][out_stride]
   FeResult* result;                              // [n_streams]
   const double* apow;                            // (1 - r)^k, k = 0 .. FE_TILE_IN
@@ -101,6 +106,13 @@ struct FeArgs {
   const float2* lut_cs;                          // {cos, sin} tables of DSP/fast_math.h
   const float* h;                                // the 64 decimator taps as floats
 };
+
+#ifdef __CUDACC__
+__constant__ float fe_c_h[FE_TAPS];                // the taps again: with compile-time indices they are operands, not loads
+#define FE_H(A, t) fe_c_h[t]
+#else
+#define FE_H(A, t) (A).h[t]
+#endif
 
 // ---- NCO ---------------------------------------------------------------------------------------------------------------
 FE_FN float fe_wrap(float x)
@@ -201,9 +213,12 @@ FE_FN void fe_dc_partial_body(const FeArgs& A, int s, int t)
 }
 
 // ---- pass 1: per stream, the state at every tile boundary and the output counts (one thread) ---------------------------
-FE_FN void fe_plan_stream(const FeArgs& A, int s)
+FE_FN void fe_plan_body(const FeArgs& A, int s)
 {
-  {
+  FE_SHARED double2 sh_w[FE_MAX_TILES];                      // the tile sums, fetched by all threads: the walk below is serial
+  FE_FOR(t, (A.chunk[s].len_in + FE_TILE_IN - 1) / FE_TILE_IN) sh_w[t] = A.dc_part[s * FE_MAX_TILES + t];
+  FE_SYNC();
+  FE_ONE() {
     const FeChunk ck = A.chunk[s];
     const FeStream st = A.cur[s];
     FePlan& P = A.plan[s];
@@ -217,17 +232,31 @@ FE_FN void fe_plan_stream(const FeArgs& A, int s)
       P.dc_start[t] = y0;
       const int L = n - t * FE_TILE_IN < FE_TILE_IN ? n - t * FE_TILE_IN : FE_TILE_IN;
       const double a = FE_LDG(A.apow + L);
-      const double2 w = A.dc_part[s * FE_MAX_TILES + t];
+      const double2 w = sh_w[t];
       yr = a * yr + w.x; yi = a * yi + w.y;
     }
     P.dc_re_next = (float)yr; P.dc_im_next = (float)yi;
-    // NCO at the tile boundaries
+    // NCO: the whole chunk in linear segments; the tile boundaries read off them
     float v = st.frequency_nco;
     const float c = -ck.frequency_est_filtered;
-    for (int t = 0; t < nt; ++t) {
-      P.nco_start[t] = v;
-      const int L = n - t * FE_TILE_IN < FE_TILE_IN ? n - t * FE_TILE_IN : FE_TILE_IN;
-      v = fe_nco_run(v, c, L, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    int ns = 0, nd = 0;
+    const float v_end = fe_nco_run(v, c, n, FE_MAX_CHUNK_SEG, P.seg_k0, P.seg_v0, P.seg_inc, &ns, &nd);
+    if (nd == n) {
+      P.n_seg = ns;
+      int g = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int k = t * FE_TILE_IN;
+        while (g + 1 < ns && P.seg_k0[g + 1] <= k) ++g;
+        P.nco_start[t] = ns ? (float)((double)P.seg_v0[g] + (double)(k - P.seg_k0[g]) * P.seg_inc[g]) : v;
+      }
+      v = v_end;
+    } else {                                                  // too many segments: tile by tile
+      P.n_seg = 0;
+      for (int t = 0; t < nt; ++t) {
+        P.nco_start[t] = v;
+        const int L = n - t * FE_TILE_IN < FE_TILE_IN ? n - t * FE_TILE_IN : FE_TILE_IN;
+        v = fe_nco_run(v, c, L, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+      }
     }
     P.nco_next = v;
     // resampler: output m sits at X_m = x1 + m d and is made while input floor(X_m + 1/2) is the newest sample
@@ -253,24 +282,31 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   FE_SHARED double2 sh_z[FE_TILE_IN];                    // prefix of x_j (1-r)^-j inside the thread's group of four
   FE_SHARED double2 sh_scan[2][FE_THREADS];
   FE_SHARED double sh_th[3][FE_THREADS];
-  FE_SHARED int sh_seg_k0[FE_MAX_SEG];
-  FE_SHARED float sh_seg_v0[FE_MAX_SEG];
-  FE_SHARED double sh_seg_inc[FE_MAX_SEG];
-  FE_SHARED int sh_nseg, sh_ndone;
+  FE_SHARED int sh_seg_k0[FE_MAX_CHUNK_SEG];
+  FE_SHARED float sh_seg_v0[FE_MAX_CHUNK_SEG];
+  FE_SHARED double sh_seg_inc[FE_MAX_CHUNK_SEG];
+  FE_SHARED int sh_nseg, sh_ndone, sh_base;
   const FeChunk ck = A.chunk[s];
   const int i0 = t * FE_TILE_IN;
+  if (t == 0) { FE_FOR(j, 3) A.derot[s * A.derot_stride + j] = A.cur[s].delay[2 - j]; }      // the resampler's delay line
   if (i0 >= ck.len_in) return;
   const int L = ck.len_in - i0 < FE_TILE_IN ? ck.len_in - i0 : FE_TILE_IN;
   const FePlan& P = A.plan[s];
   const int16_t* pi = A.i_in + s * A.in_stride;
   const int16_t* pq = A.q_in + s * A.in_stride;
   const float c = -ck.frequency_est_filtered;
-  // phase A: the NCO segments of this tile (one thread), the local prefix sums (all threads)
-  FE_ONE() {
-    int ns = 0, nd = 0;
-    float v = fe_nco_run(P.nco_start[t], c, L, FE_MAX_SEG, sh_seg_k0, sh_seg_v0, sh_seg_inc, &ns, &nd);
-    for (int k = nd; k < L; ++k) { v = fe_wrap(fe_add(v, c)); sh_phase[k] = v; }      // beyond FE_MAX_SEG segments: step by step
-    sh_nseg = ns; sh_ndone = nd;
+  // phase A: the NCO segments that cover this tile -- the chunk's (fe_plan_stream) or, if the chunk has too many, the tile's own
+  // (one thread); the local prefix sums of the DC average (all threads)
+  if (P.n_seg > 0) {
+    FE_FOR(g, P.n_seg) { sh_seg_k0[g] = P.seg_k0[g]; sh_seg_v0[g] = P.seg_v0[g]; sh_seg_inc[g] = P.seg_inc[g]; }
+    FE_ONE() { sh_nseg = P.n_seg; sh_ndone = L; sh_base = i0; }
+  } else {
+    FE_ONE() {
+      int ns = 0, nd = 0;
+      float v = fe_nco_run(P.nco_start[t], c, L, FE_MAX_SEG, sh_seg_k0, sh_seg_v0, sh_seg_inc, &ns, &nd);
+      for (int k = nd; k < L; ++k) { v = fe_wrap(fe_add(v, c)); sh_phase[k] = v; }      // beyond FE_MAX_SEG segments: step by step
+      sh_nseg = ns; sh_ndone = nd; sh_base = 0;
+    }
   }
   FE_FOR(k, FE_THREADS) {
     double2 acc; acc.x = 0.0; acc.y = 0.0;
@@ -281,7 +317,6 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
       sh_z[j] = acc;
     }
     sh_scan[0][k] = acc;
-    sh_th[0][k] = 0.0; sh_th[1][k] = 0.0; sh_th[2][k] = 0.0;
   }
   FE_SYNC();
   // phase B: inclusive scan of the 256 group sums (ping-pong), the phase of every sample from its segment
@@ -297,36 +332,41 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   }
   FE_FOR(i, L) {
     if (i < sh_ndone) {
-      int g = 0;
-      while (g + 1 < sh_nseg && sh_seg_k0[g + 1] <= i) ++g;       // sample i uses v_{i+1}: the segment with k0 < i + 1 <= k0 + len
-      sh_phase[i] = (float)((double)sh_seg_v0[g] + (double)(i + 1 - sh_seg_k0[g]) * sh_seg_inc[g]);
+      const int step_idx = sh_base + i + 1;                     // sample i uses v_{i+1}: the segment with k0 < i + 1 <= k0 + len
+      int lo = 0, hi = sh_nseg - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sh_seg_k0[mid] < step_idx) lo = mid; else hi = mid - 1; }
+      sh_phase[i] = (float)((double)sh_seg_v0[lo] + (double)(step_idx - sh_seg_k0[lo]) * sh_seg_inc[lo]);
     }
   }
   FE_SYNC();
-  // phase C: the samples
+  // phase C: the samples; thread k takes samples k, k + 256, ... (coalesced) and keeps its share of the statistics in registers
   const double2 y0 = P.dc_start[t];
-  FE_FOR(i, L) {
-    const int g = i >> 2;
-    double2 pre = sh_z[i];
-    if (g > 0) { pre.x += sh_scan[src][g - 1].x; pre.y += sh_scan[src][g - 1].y; }
-    const double a1 = FE_LDG(A.apow + i + 1), a0 = FE_LDG(A.apow + i);
-    const float dc_re = (float)(a1 * y0.x + (double)FE_DC_RATIO * a0 * pre.x);
-    const float dc_im = (float)(a1 * y0.y + (double)FE_DC_RATIO * a0 * pre.y);
-    float real = fe_sub(fe_mul((float)pi[(long long)(i0 + i) * A.step], ck.short_to_float), dc_re);
-    float imag = fe_sub(fe_mul((float)pq[(long long)(i0 + i) * A.step], ck.short_to_float), dc_im);
-    const float sr = real < 0 ? -1.0f : 1.0f, si = imag < 0 ? -1.0f : 1.0f;
-    sh_th[0][i & (FE_THREADS - 1)] -= (double)fe_mul(imag, sr);
-    sh_th[1][i & (FE_THREADS - 1)] += (double)fe_mul(real, sr);
-    sh_th[2][i & (FE_THREADS - 1)] += (double)fe_mul(imag, si);
-    real = fe_mul(real, ck.c2);
-    imag = fe_add(imag, fe_mul(ck.c1, real));
-    const float off_nco = fe_wrap(fe_sub(sh_phase[i], ck.phase_nco));
-    const int idx = (int)fe_add(fe_mul(off_nco, FE_K_TABLE), 32767.0f) & 65535;
-    const float2 cs = FE_LDG(A.lut_cs + idx);
-    float2 o;
-    o.x = fe_sub(fe_mul(real, cs.x), fe_mul(imag, cs.y));
-    o.y = fe_add(fe_mul(imag, cs.x), fe_mul(real, cs.y));
-    A.derot[s * A.derot_stride + i0 + i] = o;
+  FE_FOR(k, FE_THREADS) {
+    double th0 = 0.0, th1 = 0.0, th2 = 0.0;
+    for (int i = k; i < L; i += FE_THREADS) {
+      const int g = i >> 2;
+      double2 pre = sh_z[i];
+      if (g > 0) { pre.x += sh_scan[src][g - 1].x; pre.y += sh_scan[src][g - 1].y; }
+      const double a1 = FE_LDG(A.apow + i + 1), a0 = FE_LDG(A.apow + i);
+      const float dc_re = (float)(a1 * y0.x + (double)FE_DC_RATIO * a0 * pre.x);
+      const float dc_im = (float)(a1 * y0.y + (double)FE_DC_RATIO * a0 * pre.y);
+      float real = fe_sub(fe_mul((float)pi[(long long)(i0 + i) * A.step], ck.short_to_float), dc_re);
+      float imag = fe_sub(fe_mul((float)pq[(long long)(i0 + i) * A.step], ck.short_to_float), dc_im);
+      const float sr = real < 0 ? -1.0f : 1.0f, si = imag < 0 ? -1.0f : 1.0f;
+      th0 -= (double)fe_mul(imag, sr);
+      th1 += (double)fe_mul(real, sr);
+      th2 += (double)fe_mul(imag, si);
+      real = fe_mul(real, ck.c2);
+      imag = fe_add(imag, fe_mul(ck.c1, real));
+      const float off_nco = fe_wrap(fe_sub(sh_phase[i], ck.phase_nco));
+      const int idx = (int)fe_add(fe_mul(off_nco, FE_K_TABLE), 32767.0f) & 65535;
+      const float2 cs = FE_LDG(A.lut_cs + idx);
+      float2 o;
+      o.x = fe_sub(fe_mul(real, cs.x), fe_mul(imag, cs.y));
+      o.y = fe_add(fe_mul(imag, cs.x), fe_mul(real, cs.y));
+      A.derot[s * A.derot_stride + 3 + i0 + i] = o;
+    }
+    sh_th[0][k] = th0; sh_th[1][k] = th1; sh_th[2][k] = th2;
   }
   FE_SYNC();
   for (int step = FE_THREADS / 2; step > 0; step >>= 1) {
@@ -339,11 +379,10 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   }
 }
 
-// ---- pass 3: Farrow resampler + half-band decimator; one CTA per 512 outputs, one more per stream commits the state ----
+// ---- pass 3: Farrow resampler + half-band decimator; one CTA per 1 024 outputs, one more per stream commits the state ----
 FE_FN float2 fe_derot_at(const FeArgs& A, int s, long long i)
 {
-  if (i >= 0) return A.derot[s * A.derot_stride + i];
-  return A.cur[s].delay[-i - 1 < 3 ? -i - 1 : 2];
+  return A.derot[s * A.derot_stride + 3 + i];               // i >= -3: the row starts with the three samples before the chunk
 }
 
 FE_FN float2 fe_interp_at(const FeArgs& A, int s, int m, double x1, double d)
@@ -377,8 +416,7 @@ FE_FN float2 fe_interp_at(const FeArgs& A, int s, int m, double x1, double d)
 
 FE_FN void fe_resample_body(const FeArgs& A, int s, int tile, int n_tiles)
 {
-  FE_SHARED float2 sh_v[2 * FE_TILE_OUT + FE_TAPS];
-  FE_SHARED float sh_h[FE_TAPS];
+  FE_SHARED float4 sh_v4[(2 * FE_TILE_OUT + FE_TAPS) / 2 * 5 / 4 + 4];
   const FePlan& P = A.plan[s];
   const FeChunk ck = A.chunk[s];
   const double x1 = (double)A.cur[s].x1, d = (double)ck.resample;
@@ -403,26 +441,46 @@ FE_FN void fe_resample_body(const FeArgs& A, int s, int tile, int n_tiles)
   const int nk = P.n_out - k_lo < FE_TILE_OUT ? P.n_out - k_lo : FE_TILE_OUT;
   const int m_lo = P.m0 + 2 * k_lo - (FE_TAPS - 1);
   const int count = 2 * (nk - 1) + FE_TAPS;
-  FE_FOR(j, count) sh_v[j] = fe_interp_at(A, s, m_lo + j, x1, d);
-  FE_FOR(j, FE_TAPS) sh_h[j] = FE_LDG(A.h + j);
+  // resampler outputs of the tile into shared memory; 16 bytes of padding after every 64 (the decimator below reads 16-byte
+  // words at a stride of 64 bytes per thread)
+  float2* sh_v = reinterpret_cast<float2*>(sh_v4);
+  FE_FOR(j, count) sh_v[j + ((j >> 3) << 1)] = fe_interp_at(A, s, m_lo + j, x1, d);
   FE_SYNC();
-  FE_FOR(kk, nk) {
-    // filter_decimator.h:95-123: four 8-float lanes (one complex sample each), blocks of 16 samples, (m0 + m1) + (m2 + m3)
-    float lr[4], li[4];
-    for (int l = 0; l < 4; ++l) { lr[l] = 0.0f; li[l] = 0.0f; }
-    const float2* w = sh_v + 2 * kk;
-    for (int b = 0; b < 4; ++b)
-      for (int l = 0; l < 4; ++l) {
-        const int t0 = 16 * b + l;
-        const float2 s0 = w[t0], s1 = w[t0 + 4], s2 = w[t0 + 8], s3 = w[t0 + 12];
-        const float h0 = sh_h[t0], h1 = sh_h[t0 + 4], h2 = sh_h[t0 + 8], h3 = sh_h[t0 + 12];
-        lr[l] = fe_add(lr[l], fe_add(fe_add(fe_mul(s0.x, h0), fe_mul(s1.x, h1)), fe_add(fe_mul(s2.x, h2), fe_mul(s3.x, h3))));
-        li[l] = fe_add(li[l], fe_add(fe_add(fe_mul(s0.y, h0), fe_mul(s1.y, h1)), fe_add(fe_mul(s2.y, h2), fe_mul(s3.y, h3))));
+  // filter_decimator.h:95-123: four 8-float lanes (one complex sample each), blocks of 16 samples, (m0 + m1) + (m2 + m3) per lane
+  // and block, lanes added left to right at the end.  A thread makes FOUR consecutive outputs: their windows are 2 samples apart,
+  // so one block of the four windows is 22 samples held in registers (eleven 16-byte loads instead of 4 x 16 8-byte ones).
+  FE_FOR(g, (nk + 3) >> 2) {
+    float lr[4][4], li[4][4];
+    for (int o = 0; o < 4; ++o) for (int l = 0; l < 4; ++l) { lr[o][l] = 0.0f; li[o][l] = 0.0f; }
+    #pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float2 r[22];
+      #pragma unroll
+      for (int q = 0; q < 11; ++q) {
+        const int w4 = 4 * g + 8 * b + q;                       // 16-byte word of the unpadded window
+        const float4 x = sh_v4[w4 + (w4 >> 2)];
+        r[2 * q].x = x.x; r[2 * q].y = x.y; r[2 * q + 1].x = x.z; r[2 * q + 1].y = x.w;
       }
-    float2 o;
-    o.x = fe_add(fe_add(fe_add(lr[0], lr[1]), lr[2]), lr[3]);
-    o.y = fe_add(fe_add(fe_add(li[0], li[1]), li[2]), li[3]);
-    A.out[s * A.out_stride + k_lo + kk] = o;
+      #pragma unroll
+      for (int o = 0; o < 4; ++o)
+        #pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int t0 = 16 * b + l, j0 = 2 * o + l;
+          lr[o][l] = fe_add(lr[o][l], fe_add(fe_add(fe_mul(r[j0].x, FE_H(A, t0)), fe_mul(r[j0 + 4].x, FE_H(A, t0 + 4))),
+                                             fe_add(fe_mul(r[j0 + 8].x, FE_H(A, t0 + 8)), fe_mul(r[j0 + 12].x, FE_H(A, t0 + 12)))));
+          li[o][l] = fe_add(li[o][l], fe_add(fe_add(fe_mul(r[j0].y, FE_H(A, t0)), fe_mul(r[j0 + 4].y, FE_H(A, t0 + 4))),
+                                             fe_add(fe_mul(r[j0 + 8].y, FE_H(A, t0 + 8)), fe_mul(r[j0 + 12].y, FE_H(A, t0 + 12)))));
+        }
+    }
+    #pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (4 * g + o < nk) {
+        float2 v;
+        v.x = fe_add(fe_add(fe_add(lr[o][0], lr[o][1]), lr[o][2]), lr[o][3]);
+        v.y = fe_add(fe_add(fe_add(li[o][0], li[o][1]), li[o][2]), li[o][3]);
+        A.out[s * A.out_stride + k_lo + 4 * g + o] = v;
+      }
+    }
   }
 }
 

@@ -29,7 +29,7 @@ static inline void fe_make_tables(std::vector<double>& apow, std::vector<double>
   for (int i = 0; i < FE_TAPS; ++i) h[i] = (float)fe_h_fir[i];
 }
 
-// upper bound of the 512-output tiles any stream of the launch needs (the exact counts are only known on the device: they
+// upper bound of the FE_TILE_OUT-output tiles any stream of the launch needs (the exact counts are only known on the device: they
 // depend on the resampler phase carried in the stream state, which lies in [-0.5, 0.5 + d))
 static inline int fe_max_out_tiles(const FeChunk* chunk, int n_streams)
 {

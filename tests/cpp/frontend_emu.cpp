@@ -17,26 +17,26 @@ int emu_fe_chunk(int n_streams, const FeStream* cur, FeStream* next, const FeChu
 {
   int max_in = 0;
   for (int s = 0; s < n_streams; ++s) if (chunk[s].len_in > max_in) max_in = chunk[s].len_in;
-  const int nt_in = (max_in + FE_TILE_IN - 1) / FE_TILE_IN;
+  const int nt_in = max_in > 0 ? (max_in + FE_TILE_IN - 1) / FE_TILE_IN : 1;      // tile 0 always runs: it lays out the delay line
   if (nt_in > FE_MAX_TILES) return 1;
   std::vector<FePlan> plan(n_streams);
   std::vector<double2> dc_part((size_t)n_streams * FE_MAX_TILES);
   std::vector<double> theta_part((size_t)n_streams * FE_MAX_TILES * 3);
-  std::vector<float2> derot((size_t)n_streams * (max_in + 1));
+  std::vector<float2> derot((size_t)n_streams * (max_in + 4));
   std::vector<double> apow, ainv; std::vector<float> lut, h;
   fe_make_tables(apow, ainv, lut, h);
   FeArgs A;
   A.i_in = i_in; A.q_in = q_in; A.in_stride = in_stride; A.step = step; A.chunk = chunk; A.cur = cur; A.next = next;
   A.plan = plan.data(); A.dc_part = dc_part.data(); A.theta_part = theta_part.data();
-  A.derot = derot.data(); A.derot_stride = max_in + 1; A.out = reinterpret_cast<float2*>(out); A.out_stride = out_stride;
+  A.derot = derot.data(); A.derot_stride = max_in + 4; A.out = reinterpret_cast<float2*>(out); A.out_stride = out_stride;
   A.result = result; A.apow = apow.data(); A.ainv = ainv.data(); A.lut_cs = reinterpret_cast<const float2*>(lut.data()); A.h = h.data();
   for (int s = 0; s < n_streams; ++s) for (int t = 0; t < nt_in; ++t) fe_dc_partial_body(A, s, t);
-  for (int s = 0; s < n_streams; ++s) fe_plan_stream(A, s);
+  for (int s = 0; s < n_streams; ++s) fe_plan_body(A, s);
   for (int s = 0; s < n_streams; ++s) for (int t = 0; t < nt_in; ++t) fe_derotate_body(A, s, t);
   const int nt_out = fe_max_out_tiles(chunk, n_streams) + 1;
   for (int s = 0; s < n_streams; ++s) for (int t = 0; t < nt_out; ++t) fe_resample_body(A, s, t, nt_out);
   if (derot_out)
-    for (int s = 0; s < n_streams; ++s) std::memcpy(derot_out + 2 * (size_t)s * max_in, &derot[(size_t)s * (max_in + 1)], sizeof(float2) * chunk[s].len_in);
+    for (int s = 0; s < n_streams; ++s) std::memcpy(derot_out + 2 * (size_t)s * max_in, &derot[(size_t)s * (max_in + 4) + 3], sizeof(float2) * chunk[s].len_in);
   return 0;
 }
 

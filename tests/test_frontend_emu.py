@@ -154,6 +154,28 @@ def test_chunks_equal_the_oracle(resample):
         states = nxt
 
 
+def test_chunk_with_more_nco_segments_than_the_plan_holds():
+    """every step an exact tie (the decrement is half an ulp of the phase): no linear segments, the tiles plan for themselves
+    and fall back to single steps"""
+    rng = np.random.default_rng(9)
+    states = fresh_states(2)
+    states['frequency_nco'] = [1.0, -1.5]
+    ports = [O.PortFrontend() for _ in range(2)]
+    for s in range(2):
+        ports[s].state['frequency_nco'] = states['frequency_nco'][s]
+    chunks = np.zeros(2, CHUNK)
+    chunks['len_in'], chunks['short_to_float'], chunks['c2'], chunks['resample'] = [3000, 2500], 2.0 ** -14, 1.0, 0.5
+    chunks['frequency_est_filtered'] = [-2.0 ** -24, 2.0 ** -24]
+    i16 = rng.normal(0, 1500, (2, 3000)).astype(np.int16)
+    q16 = rng.normal(0, 1500, (2, 3000)).astype(np.int16)
+    nxt, outs, derots, res = emu_chunk(states, chunks, i16, q16)
+    for s in range(2):
+        n = chunks['len_in'][s]
+        po, _, pd = ports[s].chunk(i16[s, :n], q16[s, :n], 2.0 ** -14, 0.0, 1.0, float(chunks['frequency_est_filtered'][s]), 0.0, 0.5)
+        assert np.abs(derots[s] - pd).max() <= 2e-6 * 0.09 and np.abs(outs[s] - po).max() <= 2e-6 * 0.09
+        assert nxt['frequency_nco'][s].view(np.uint32) == ports[s].state[0]['frequency_nco'].view(np.uint32)
+
+
 def test_cp_correlation_equals_the_oracle():
     rng = np.random.default_rng(3)
     for n, g in ((16384, 512), (32768, 256), (32768, 1024)):

@@ -100,6 +100,29 @@ def test_golden_window_of_the_reference_receiver(engine):
         assert abs(s['dc_re'] - row[F.COL['dc_re_after']]) < 1e-8 and abs(s["x1"] - row[F.COL["x1_after"]]) < 1e-6
 
 
+def test_chunk_with_more_nco_segments_than_the_plan_holds(engine):
+    """every step an exact tie (the decrement is half an ulp of the phase): no linear segments, the tiles plan for themselves
+    and fall back to single steps"""
+    rng = np.random.default_rng(9)
+    engine.frontend_configure(2, 4000)
+    ports = [O.PortFrontend() for _ in range(2)]
+    for s, v in enumerate((1.0, -1.5)):
+        st = engine.frontend_state(s)
+        st['frequency_nco'] = v
+        engine.frontend_set_state(s, st)
+        ports[s].state['frequency_nco'] = v
+    chunks = np.zeros(2, E.FE_CHUNK)
+    chunks['len_in'], chunks['short_to_float'], chunks['c2'], chunks['resample'] = [3000, 2500], 2.0 ** -14, 1.0, 0.5
+    chunks['frequency_est_filtered'] = [-2.0 ** -24, 2.0 ** -24]
+    iq = rng.normal(0, 1500, (2, 2, 3000)).astype(np.int16)
+    out, res = engine.frontend_execute(iq[0], iq[1], chunks)
+    for s in range(2):
+        n = chunks['len_in'][s]
+        po, _, _ = ports[s].chunk(iq[0, s, :n], iq[1, s, :n], 2.0 ** -14, 0.0, 1.0, float(chunks['frequency_est_filtered'][s]), 0.0, 0.5)
+        assert res['len_out'][s] == len(po) and np.abs(out[s, :len(po)] - po).max() <= F.TOL * 0.09
+        assert np.float32(engine.frontend_state(s)['frequency_nco']).view(np.uint32) == ports[s].state[0]['frequency_nco'].view(np.uint32)
+
+
 def test_cp_correlation_equals_the_oracle(engine):
     rng = np.random.default_rng(3)
     for n, g in ((16384, 512), (32768, 256), (32768, 1024)):
