@@ -236,16 +236,22 @@ int t2b200_fft(t2b200_ctx* ctx, int n, const float* in, int batch, float* out);
 
 /* ---- N1: BBFRAME -> transport stream ---------------------------------------------------------- */
 /* Replaces bb_de_header::execute (bb_de_header.cpp:84-445) for a batch of BBFRAMEs of ONE PLP (the caller applies the
- * reference's need_plp filter), high-efficiency mode.
+ * reference's need_plp filter): high-efficiency mode (:332-428) and normal mode (:166-331: the sync byte on air is the
+ * CRC-8 of the previous packet, checked, replaced by 0x47, a mismatch sets that packet's transport_error_indicator).
+ * Batches of high-efficiency frames are built by a parallel scan; a batch with a normal-mode frame (also one a header bit
+ * error turned into normal mode) is switched on the device to a frame-by-frame path that follows the reference's
+ * byte-serial loop exactly, its quirks included: the CRC bytes are read without being counted against DFL (a frame reads a
+ * few bytes behind its data field; past the frame they read as zero), and a too-short SYNCD after a held-back tail leaves
+ * the packet index beyond 188 for good (:208-226).
  *   bbframes      uint8[n_frames][k_bch], one byte per bit: what t2b200_ldpc_decode(BCH_DESCRAMBLE) or
  *                 bch_decoder::execute emit (bch_decoder.cpp:139-160)
- *   ts_out        the datagrams the reference would send (bb_de_header.cpp:431-441), back to back
+ *   ts_out        the datagrams the reference would send (bb_de_header.cpp:431-441), back to back; writes are bounded by
+ *                 ts_cap (a header with an absurd SYNCD makes the reference write past its datagram buffer)
  *   datagram_len  int32[n_frames] or NULL: bytes of each frame's datagram (0 for a dropped frame)
- *   status        int32[n_frames] or NULL: 0 ok; 1 header CRC-8 error (dropped, :108-113); 2 SYNCD == 65535 (dropped,
- *                 :160-163); 3 normal-mode frame: NOT handled here (the reference's normal-mode path reads its CRC bytes
- *                 outside DFL): the frame is skipped and must go to the host bb_de_header; 4 the header announces a data
- *                 field longer than the frame (80 + DFL > k_bch): dropped without touching the carried state -- the
- *                 reference has no such check and would read past its buffer
+ *   status        int32[n_frames] or NULL: 0 high-efficiency frame; 3 normal-mode frame; dropped frames: 1 header CRC-8
+ *                 error (:108-113); 2 SYNCD == 65535 (:160-163); 4 the header announces a data field longer than the
+ *                 frame (80 + DFL > k_bch) -- dropped without touching the carried state; the reference has no such
+ *                 check and would read past its buffer
  *   total_out     bytes written to ts_out, or NULL (then the call stays asynchronous for device buffers)
  * The packet phase and the held-back tail (< 188 bytes) persist per PLP between calls; t2b200_ts_reset clears them. */
 int t2b200_ts_reset(t2b200_ctx* ctx, int plp);

@@ -413,7 +413,8 @@ class PortTs:
 
     def feed(self, bits):
         bits = np.ascontiguousarray(bits, np.uint8)
-        padded = np.concatenate([bits, np.zeros(4096, np.uint8)])      # normal mode reads its CRC bytes beyond DFL
+        padded = np.concatenate([bits, np.zeros(70000, np.uint8)])     # normal mode reads its CRC bytes beyond DFL; a frame entered with
+        # a packet index beyond 188 reads far past the frame (undefined in the reference): zeros here, as on the GPU
         out = np.zeros(len(bits) // 8 + 2 * 188 + 64, np.uint8)
         n = self.L.port_ts_frame(self.state.ctypes.data, padded.ctypes.data, len(bits), out.ctypes.data)
         return None if n < 0 else out[:n].copy()

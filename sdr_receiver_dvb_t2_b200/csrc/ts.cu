@@ -1,4 +1,5 @@
-// N1: BBFRAME -> MPEG transport stream re-packetiser on the GPU, high-efficiency mode.
+// N1: BBFRAME -> MPEG transport stream re-packetiser on the GPU: high-efficiency mode by a parallel scan (this
+// file), normal mode and mixed batches by the general path (ts_general.h, ts_general_kernel below).
 //
 // Reference semantics reproduced (bb_de_header.cpp, paths relative to the reference's src/DVB_T2):
 //   :70-82,101-113  CRC-8 of the 80 header bits: residue 0xAB => HEM, 0 => normal mode, else the frame is dropped
@@ -11,9 +12,12 @@
 // The reference walks the frame bit by bit; here the only serial part is the packet phase carried from frame to
 // frame: a one-thread scan over 12-byte header records turns every frame into a descriptor (where its datagram
 // starts, which bit ranges feed it, where the sync bytes fall), and one CTA per frame then builds the datagram
-// with one thread per output byte.  Normal-mode frames are reported (status 3) and left to the host
-// bb_de_header: the reference's normal-mode path reads its CRC bytes outside DFL and is not reproducible as such.
+// with one thread per output byte.  A batch with a normal-mode frame (status 3), or entered with normal mode's run-away
+// packet index, is switched ON THE DEVICE to the general path: ts_parse_kernel raises TsDevState::general, the three scan
+// kernels return at once and ts_general_kernel (one CTA, frame after frame: plan by one thread, segments by the warps,
+// CRC tasks by the threads) builds the datagrams exactly as the reference's byte-serial loop would.
 #include "ctx.h"
+#include "ts_general.h"
 #include <algorithm>
 
 namespace {
@@ -34,7 +38,8 @@ struct TsDesc {
   int main_bit, main_n, main_phase;
 };
 struct TsDevState {                                    // survives between calls (device memory)
-  int split, idx_packet, idx_buffer, pad;
+  int split, idx_packet, idx_buffer, general;          // general: this call runs on the general path (set by the parse kernel)
+  unsigned crc; int pad[3];                            // normal mode: CRC-8 of the packet piece in flight
   long long total;                                     // bytes emitted by the last call
   int tail_src, tail_bit, tail_ndata, tail_sync;       // where the held-back bytes of the last call live
   uint8_t buffer[PKT + 4];
@@ -78,10 +83,12 @@ __device__ __forceinline__ TsBody ts_body(int dfl, int idx_packet)
   return b;
 }
 
-__global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames, int k_bch, TsHdr* __restrict__ hdr)
+__global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames, int k_bch, TsHdr* __restrict__ hdr,
+                                TsDevState* __restrict__ st)
 {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n_frames) return;
+  if (f == 0 && st->idx_packet > PKT) st->general = 1;   // left behind by normal mode's resynchronisation (bb_de_header.cpp:208-226)
   const uint8_t* b = frames + (size_t)f * k_bch;
   unsigned reg = 0;                                      // bb_de_header.cpp:70-82
   for (int i = 0; i < 80; ++i) {
@@ -93,11 +100,12 @@ __global__ void ts_parse_kernel(const uint8_t* __restrict__ frames, int n_frames
   h.dfl = (int)field(b + 32, 16);
   h.syncd = (int)field(b + 56, 16);
   h.status = reg == 0xABu ? 0 : reg == 0u ? 3 : 1;
-  if (h.status == 0 && h.syncd == 65535) h.status = 2;
+  if (h.status != 1 && h.syncd == 65535) h.status = 2;
   // A header whose CRC-8 passes by chance (or a crafted one) can announce a data field longer than the frame: the reference
   // would walk off the end of its buffer (it has no such check); here the frame is dropped like a header CRC error, without
   // touching the carried packet state.
-  if (h.status == 0 && 80 + h.dfl > k_bch) h.status = 4;
+  if ((h.status == 0 || h.status == 3) && 80 + h.dfl > k_bch) h.status = 4;
+  if (h.status == 3) st->general = 1;                    // (same value from every thread that writes it)
   const TsBody body = ts_body(h.dfl - h.syncd, PKT);     // entered with a tail: the head completes a packet first
   h.main_n = body.M; h.main_out = body.T; h.ntail = body.split ? body.ntail : -1; h.tail_sync = body.tail_sync;
   h.end_packet = body.end_packet; h.end_buffer = body.end_buffer;
@@ -110,6 +118,7 @@ __global__ void __launch_bounds__(32) ts_scan_kernel(const TsHdr* __restrict__ h
 {
   __shared__ TsHdr sh[32];
   __shared__ TsDesc sd[32];
+  if (st->general) return;
   const int lane = threadIdx.x;
   int split = st->split, idx_packet = st->idx_packet, idx_buffer = st->idx_buffer;
   int tail_src = -1, tail_bit = 0, tail_ndata = 0, tail_sync = -1;   // the carried bytes of a previous call sit in st->buffer
@@ -191,9 +200,11 @@ __device__ __forceinline__ uint8_t tail_byte(const uint8_t* __restrict__ frame, 
 }
 
 __global__ void __launch_bounds__(256) ts_assemble_kernel(const uint8_t* __restrict__ frames, int k_bch,
-                                                          const TsDesc* __restrict__ desc, const uint8_t* __restrict__ carry0,
+                                                          const TsDesc* __restrict__ desc, const TsDevState* __restrict__ st,
                                                           uint8_t* __restrict__ out, long long cap)
 {
+  if (st->general) return;
+  const uint8_t* carry0 = st->buffer;
   const TsDesc d = desc[blockIdx.x];
   const uint8_t* me = frames + (size_t)blockIdx.x * k_bch;
   const int c1 = d.carry_len, c2 = c1 + d.head_n, c3 = c2 + d.head_f0;
@@ -217,10 +228,83 @@ __global__ void __launch_bounds__(256) ts_assemble_kernel(const uint8_t* __restr
 // keep the held-back bytes of the call's last frame for the next call
 __global__ void ts_save_tail_kernel(const uint8_t* __restrict__ frames, int k_bch, TsDevState* __restrict__ st)
 {
-  if (!st->split || st->tail_src < 0) return;            // nothing new held back (an older tail stays where it is)
+  if (st->general || !st->split || st->tail_src < 0) return;   // nothing new held back (an older tail stays where it is)
   const int n = st->tail_ndata + (st->tail_sync >= 0 ? 1 : 0);
   for (int j = threadIdx.x; j < n; j += blockDim.x)
     st->buffer[j] = tail_byte(frames + (size_t)st->tail_src * k_bch, st->tail_bit, st->tail_sync, j);
+}
+
+// ---- the general path (ts_general.h): one CTA walks the batch frame by frame ----
+__device__ __forceinline__ unsigned byte_at(const uint8_t* __restrict__ frame, int k_bch, int bit)
+{
+  unsigned v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v = (v << 1) | ((bit + i < k_bch ? frame[bit + i] : 0) & 1u);      // past the frame: zero
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ts_general_kernel(const uint8_t* __restrict__ frames, int n_frames, int k_bch,
+                                                         const TsHdr* __restrict__ hdr, TsDevState* __restrict__ st,
+                                                         uint8_t* __restrict__ out, long long cap, int32_t* __restrict__ dlen,
+                                                         int32_t* __restrict__ status)
+{
+  if (!st->general) return;
+  __shared__ TsgPlan P;
+  __shared__ TsgState S;
+  __shared__ uint8_t old_buf[PKT + 4], new_buf[PKT + 4];
+  __shared__ unsigned crc_in, crc_out;
+  __shared__ long long off;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { S.split = st->split; S.idx_packet = st->idx_packet; S.idx_buffer = st->idx_buffer; S.crc = st->crc; off = 0; }
+  for (int j = tid; j < PKT + 4; j += blockDim.x) new_buf[j] = st->buffer[j];
+  __syncthreads();
+  for (int f = 0; f < n_frames; ++f) {
+    const TsHdr h = hdr[f];
+    if (status && tid == 0) status[f] = h.status;
+    if (h.status != 0 && h.status != 3) { if (dlen && tid == 0) dlen[f] = 0; continue; }      // dropped: the state stays (uniform branch)
+    for (int j = tid; j < PKT + 4; j += blockDim.x) old_buf[j] = new_buf[j];
+    if (tid == 0) { crc_in = S.crc; crc_out = S.crc; tsg_plan_frame(S, h.status == 3, h.dfl, h.syncd, P); }
+    __syncthreads();
+    const uint8_t* me = frames + (size_t)f * k_bch;
+    const long long base = off;
+    for (int g = warp; g < P.n_seg; g += 8) {                           // one warp per segment
+      const TsgSeg sg = P.seg[g];
+      for (int j = lane; j < sg.n; j += 32) {
+        const uint8_t v = sg.kind == TSG_DATA ? (uint8_t)byte_at(me, k_bch, sg.src + 8 * j) : sg.kind == TSG_SYNC ? 0x47
+                        : sg.kind == TSG_FILL ? 0xF0 : old_buf[min(sg.src + j, PKT + 3)];
+        if (sg.to_buffer) { if (sg.dst + j < PKT + 4) new_buf[sg.dst + j] = v; }
+        else if (base + sg.dst + j < cap) out[base + sg.dst + j] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < P.n_task) {                                               // one thread per CRC task (they write disjoint bytes or the same bit)
+      const TsgTask t = P.task[tid];
+      if (t.check == -2) { if (t.tei >= 0 && base + t.tei < cap) out[base + t.tei] |= 0x80; }
+      else {
+        unsigned crc = t.chain ? crc_in : 0u;
+        for (int j = 0; j < t.n; ++j) crc = tsg_crc8_byte(crc, byte_at(me, k_bch, t.src + 8 * j));
+        if (t.check >= 0) {
+          if (byte_at(me, k_bch, t.check) != crc && t.tei >= 0 && base + t.tei < cap) out[base + t.tei] |= 0x80;
+        }
+        if (tid == P.n_task - 1) crc_out = t.check >= 0 ? 0u : crc;      // the last task leaves the carried CRC
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // (a flagged resynchronisation as the last task leaves the CRC as it was: crc_out was preset to crc_in; if an
+      // earlier task of the frame reset it, that task was a check and the value is 0)
+      if (P.n_task > 0 && P.task[P.n_task - 1].check == -2) { crc_out = crc_in; for (int i = 0; i < P.n_task - 1; ++i) if (P.task[i].check >= 0) crc_out = 0u; }
+      S.crc = crc_out;
+      if (dlen) dlen[f] = P.out_len;
+      off = base + P.out_len;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    st->split = S.split; st->idx_packet = S.idx_packet; st->idx_buffer = S.idx_buffer; st->crc = S.crc; st->total = off;
+    st->tail_src = -1; st->tail_bit = 0; st->tail_ndata = 0; st->tail_sync = -1;
+  }
+  for (int j = tid; j < PKT + 4; j += blockDim.x) st->buffer[j] = new_buf[j];
 }
 
 }  // namespace
@@ -277,16 +361,20 @@ extern "C" int t2b200_ts_packetize(t2b200_ctx* ctx, int plp, const uint8_t* bbfr
   if (status && (rc = t2_out_device(ctx, 3, status, 4 * (size_t)n_frames, &dstat))) return rc;
   if ((rc = t2_dev_scratch(ctx, 9, sizeof(TsHdr) * (size_t)n_frames, &dhdr))) return rc;
   if ((rc = t2_dev_scratch(ctx, 10, sizeof(TsDesc) * (size_t)n_frames, &ddesc))) return rc;
-  ts_parse_kernel<<<(n_frames + 127) / 128, 128, 0, ctx->stream>>>((const uint8_t*)din, n_frames, k_bch, (TsHdr*)dhdr);
+  T2_CUDA(ctx, cudaMemsetAsync(&st->general, 0, sizeof(int), ctx->stream));
+  ts_parse_kernel<<<(n_frames + 127) / 128, 128, 0, ctx->stream>>>((const uint8_t*)din, n_frames, k_bch, (TsHdr*)dhdr, st);
   T2_CUDA(ctx, cudaGetLastError());
   ts_scan_kernel<<<1, 32, 0, ctx->stream>>>((const TsHdr*)dhdr, n_frames, (TsDesc*)ddesc, st, (int32_t*)dlen, (int32_t*)dstat);
   T2_CUDA(ctx, cudaGetLastError());
-  ts_assemble_kernel<<<n_frames, 256, 0, ctx->stream>>>((const uint8_t*)din, k_bch, (const TsDesc*)ddesc, st->buffer,
+  ts_assemble_kernel<<<n_frames, 256, 0, ctx->stream>>>((const uint8_t*)din, k_bch, (const TsDesc*)ddesc, st,
                                                         (uint8_t*)dout, (long long)ts_cap);
   T2_CUDA(ctx, cudaGetLastError());
   ts_save_tail_kernel<<<1, 256, 0, ctx->stream>>>((const uint8_t*)din, k_bch, st);
   T2_CUDA(ctx, cudaGetLastError());
-  ctx->launches += 4;
+  ts_general_kernel<<<1, 256, 0, ctx->stream>>>((const uint8_t*)din, n_frames, k_bch, (const TsHdr*)dhdr, st, (uint8_t*)dout,
+                                                (long long)ts_cap, (int32_t*)dlen, (int32_t*)dstat);
+  T2_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 5;
   if (total_out) {
     T2_CUDA(ctx, cudaMemcpyAsync(total_out, &st->total, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

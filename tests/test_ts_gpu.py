@@ -22,13 +22,13 @@ def test_hem_datagrams_match_reference_golden_and_port(engine, case):
     ts, dl, st = engine.ts_packetize(frames)
     want = port_datagrams(frames)
     if case == 'hem_faults':
-        # frame 2's flipped CRC bit turns its residue into the normal-mode value: the GPU path reports it (status 3) and
-        # skips it, the reference decodes it as normal mode -- compare up to that frame, then the documented statuses
+        # frame 2's flipped CRC bit turns its residue into the normal-mode value: the reference decodes it as normal mode,
+        # and so does the general path the batch is switched to (status 3 = "normal-mode frame")
         assert st[2] == 3 and st[4] == 2
-        upto = 2
-        kept = np.concatenate([d for d in want[:upto]])
-        assert list(dl[:upto]) == [len(d) for d in want[:upto]]
-        assert np.array_equal(ts[:len(kept)], kept)
+        kept = [d for d in want if d is not None]
+        assert list(dl) == [0 if d is None else len(d) for d in want]
+        assert list(g[case + '_len']) == [len(d) for d in kept]
+        assert np.array_equal(ts, g[case + '_ts'])
         return
     assert (st == 0).all()
     assert list(dl) == [len(d) for d in want] == list(g[case + '_len'])
@@ -104,3 +104,58 @@ def test_oversize_dfl_is_dropped_without_touching_the_state(engine):
     assert dl[3] == 0 and dl[7] == 0 and list(dl) == list(dl2) and np.array_equal(ts, ts2)
     want = port_datagrams(ref)
     assert np.array_equal(ts, np.concatenate([d for d in want if d is not None]))
+
+
+NM_CASES = [c for c in CASES if not CASES[c]['hem']]
+
+
+@pytest.mark.parametrize('case', NM_CASES)
+def test_normal_mode_datagrams_match_reference_golden_and_port(engine, case):
+    """normal mode (bb_de_header.cpp:166-331): CRC-8 of every packet checked against the byte on air, sync bytes re-inserted,
+    the reference's reads behind the data field included -- byte for byte the golden datagrams of the reference"""
+    frames, _ = make(case)
+    g = np.load(GOLD)
+    engine.ts_reset(0)
+    ts, dl, st = engine.ts_packetize(frames)
+    want = port_datagrams(frames)
+    assert all(s in (2, 3) for s in st)
+    assert list(dl) == [0 if d is None else len(d) for d in want]
+    assert [n for n in dl if n] == list(g[case + '_len']) or list(g[case + '_len']) == [len(d) for d in want if d is not None]
+    assert np.array_equal(ts, g[case + '_ts'])
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_mixed_mode_streams_equal_the_oracle(engine, seed):
+    """HEM and NM stretches back to back with header faults of every kind and payload bit errors (transport_error_indicator
+    set by the CRC check), in one call and cut into three calls (the packet state, the held-back tail and the CRC in flight
+    carry over)"""
+    from tests.test_ts_general_emu import emu_datagrams, mixed_stream
+    frames = mixed_stream(seed)
+    frames = frames[:len(emu_datagrams(frames))]          # up to where the reference's behaviour is defined (see there)
+    want = port_datagrams(frames)
+    flat = np.concatenate([d for d in want if d is not None] + [np.zeros(0, np.uint8)])
+    engine.ts_reset(0)
+    ts, dl, st = engine.ts_packetize(frames)
+    assert list(dl) == [0 if d is None else len(d) for d in want]
+    assert np.array_equal(ts, flat)
+    engine.ts_reset(0)
+    parts = []
+    n = len(frames)
+    for a, b in ((0, n // 3), (n // 3, n // 3 + 1), (n // 3 + 1, n)):
+        if b > a:
+            parts.append(engine.ts_packetize(frames[a:b])[0])
+    assert np.array_equal(np.concatenate(parts), flat)
+
+
+def test_hem_batches_stay_on_the_parallel_path_after_a_normal_mode_batch(engine):
+    """a regular normal-mode batch leaves a regular packet state: the next pure-HEM call runs the parallel scan again and
+    continues from the carried tail"""
+    from tests.ts_helpers import bbframes
+    rng = np.random.default_rng(21)
+    nm, _ = bbframes(9552, 1100, 5, False, rng)
+    hem, _ = bbframes(9552, 1180, 6, True, rng)
+    want = port_datagrams(np.concatenate([nm, hem]))
+    engine.ts_reset(0)
+    a = engine.ts_packetize(nm)[0]
+    b = engine.ts_packetize(hem)[0]
+    assert np.array_equal(np.concatenate([a, b]), np.concatenate(want))
