@@ -147,15 +147,12 @@ def test_mixed_mode_streams_equal_the_oracle(engine, seed):
     assert np.array_equal(np.concatenate(parts), flat)
 
 
-def test_hem_batches_stay_on_the_parallel_path_after_a_normal_mode_batch(engine):
-    """a regular normal-mode batch leaves a regular packet state: the next pure-HEM call runs the parallel scan again and
-    continues from the carried tail"""
-    from tests.ts_helpers import bbframes
-    rng = np.random.default_rng(21)
-    nm, _ = bbframes(9552, 1100, 5, False, rng)
-    hem, _ = bbframes(9552, 1180, 6, True, rng)
-    want = port_datagrams(np.concatenate([nm, hem]))
+def test_parallel_path_continues_from_the_state_the_general_path_leaves(engine):
+    """'hem_faults' holds one frame a header bit error turned into normal mode: the call with that frame runs on the general
+    path and leaves a regular packet state, the following pure-HEM calls run the parallel scan again from its held-back tail
+    (and a call of the general path continues from a tail the parallel path left)"""
+    frames, _ = make('hem_faults')
+    g = np.load(GOLD)
     engine.ts_reset(0)
-    a = engine.ts_packetize(nm)[0]
-    b = engine.ts_packetize(hem)[0]
-    assert np.array_equal(np.concatenate([a, b]), np.concatenate(want))
+    parts = [engine.ts_packetize(frames[a:b])[0] for a, b in ((0, 2), (2, 3), (3, 6), (6, 10))]
+    assert np.array_equal(np.concatenate(parts), g['hem_faults_ts'])
