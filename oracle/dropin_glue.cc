@@ -82,6 +82,74 @@ int dropin_demod_feed(int len, int16_t* i_in, int16_t* q_in)
   g_sig.reset = false;
   return st;
 }
+// The same receiver with the FRONT-END on the GPU as well.  dvbt2_demodulator::execute keeps its per-sample
+// loop, resampler and decimator inline (dvbt2_demodulator.cpp:178-221), so they cannot be swapped by a header: this is the edit
+// a maintainer makes to execute() -- the chunking of :155-176 and the IQ-imbalance / level estimate of
+// :223-253 around ONE t2b200_frontend_execute call per chunk -- written against the demodulator's own members, with
+// symbol_acquisition (P1 detection, guard-interval correlation, loop filters, L1 parsing; unmodified) consuming what the GPU
+// returns.  The loop is closed through the GPU: the NCO / resampler values of chunk n + 1 come from what the GPU stages made of
+// chunk n.
+int dropin_demod_feed_gpu_frontend(int len, int16_t* i_in, int16_t* q_in)
+{
+  dvbt2_demodulator* d = g_demod;
+  t2b200_ctx* ctx = t2b200_dropin::context();
+  static std::vector<std::complex<float>> out;
+  if (out.empty()) {
+    out.resize(1 << 17);
+    if (t2b200_frontend_configure(ctx, 1, 1 << 17) != T2B200_OK) return -1;
+  }
+  g_sig.frequency_changed = true; g_sig.gain_changed = true;
+  const float two_pi = M_PI_X_2;
+  float theta1 = 0.0f, theta2 = 0.0f, theta3 = 0.0f;
+  int idx_in = 0;
+  while (idx_in < len) {
+    if (d->est_chunk == 0) {
+      if (d->next_symbol_type == SYMBOL_TYPE_P1) d->est_chunk += P1_LEN;
+      d->est_chunk += d->symbol_size;
+    }
+    double arbitrary_resample = d->resample - d->sample_rate_est_filtered;
+    if (arbitrary_resample > d->max_resample) arbitrary_resample = d->max_resample;
+    int chunk = static_cast<int>(std::nearbyint(d->est_chunk * arbitrary_resample * d->upsample));
+    if (chunk > len - idx_in) chunk = len - idx_in;
+    d->chunk = chunk;
+    d->phase_nco += d->phase_est_filtered;
+    while (d->phase_nco > two_pi) d->phase_nco -= two_pi;
+    while (d->phase_nco < -two_pi) d->phase_nco += two_pi;
+    t2b200_fe_chunk c;
+    c.len_in = chunk; c.short_to_float = d->short_to_float; c.c1 = d->c1; c.c2 = d->c2;
+    c.frequency_est_filtered = d->frequency_est_filtered; c.phase_nco = d->phase_nco; c.resample = (float)arbitrary_resample;
+    t2b200_fe_result r;
+    const long long at = (long long)idx_in * d->convert_input;
+    if (t2b200_frontend_execute(ctx, i_in + at, q_in + at, 0, d->convert_input, &c, reinterpret_cast<float*>(out.data()),
+                                (long long)out.size(), &r) != T2B200_OK) {
+      std::cerr << "t2b200_frontend_execute: " << t2b200_last_error(ctx) << std::endl;
+      return -1;
+    }
+    theta1 += r.theta1; theta2 += r.theta2; theta3 += r.theta3;
+    idx_in += chunk;
+    d->symbol_acquisition(r.len_out, out.data(), &g_sig);
+    if (g_sig.reset) {                                    // dvbt2_demodulator::reset (:111-127) cleared its loop state: so does the GPU's
+      t2b200_fe_state st;
+      t2b200_frontend_get_state(ctx, 0, &st);
+      st.dc_re = st.dc_im = st.frequency_nco = 0.0f;
+      t2b200_frontend_set_state(ctx, 0, &st);
+    }
+  }
+  const float a1 = theta1 / len, a2 = theta2 / len, a3 = theta3 / len;          // :223-232
+  d->c1 = a1 / a2;
+  const float ct = a3 / a2;
+  d->c2 = sqrtf(ct * ct - d->c1 * d->c1);
+  d->level_detect = a2 * a3;
+  if (g_sig.gain_changed) {
+    if (d->level_detect < d->level_min) { g_sig.gain_offset = 1; g_sig.change_gain = true; }
+    else if (d->level_detect > d->level_max) { g_sig.gain_offset = -1; g_sig.change_gain = true; }
+    else { g_sig.gain_offset = 0; g_sig.change_gain = false; }
+  }
+  g_sig.change_frequency = false; g_sig.change_gain = false;
+  const int st = (d->crc32_l1_pre ? 1 : 0) | (d->demodulator_init ? 2 : 0) | (d->deint_start ? 4 : 0) | (g_sig.reset ? 8 : 0);
+  g_sig.reset = false;
+  return st;
+}
 long long dropin_launches() { return t2b200_launch_count(t2b200_dropin::context()); }
 
 #define TAP_GETTER(NAME, VEC, TYPE)                                                   \

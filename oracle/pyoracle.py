@@ -505,10 +505,14 @@ class DropinDemod:
     classes of sdr_receiver_dvb_t2_b200/host/dropin (oracle/_ref/libdropin_chain.so): int16 I/Q in, TS datagrams out.
     Needs a GPU (the stage classes have no CPU fallback).  One instance per process."""
 
-    def __init__(self, sample_rate=64e6 / 7, need_plp=0):
+    def __init__(self, sample_rate=64e6 / 7, need_plp=0, gpu_frontend=False):
+        """gpu_frontend: the per-sample loop, resampler and decimator of dvbt2_demodulator::execute run on the GPU as well
+        (t2b200_frontend_execute, one call per chunk; oracle/dropin_glue.cc::dropin_demod_feed_gpu_frontend)"""
         L = C.CDLL(os.path.join(_HERE, '_ref', 'libdropin_chain.so'))
         L.dropin_demod_new.argtypes = [C.c_float, C.c_int]
         L.dropin_demod_feed.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.dropin_demod_feed_gpu_frontend.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        self._feed = L.dropin_demod_feed_gpu_frontend if gpu_frontend else L.dropin_demod_feed
         L.dropin_launches.restype = C.c_longlong
         for n in ('ts', 'ts_datagrams', 'bb_bits', 'bb_len'):
             f = getattr(L, 'dropin_tap_' + n)
@@ -523,7 +527,8 @@ class DropinDemod:
         q16 = np.ascontiguousarray(q16, np.int16)
         for a in range(0, len(i16), chunk):
             n = min(chunk, len(i16) - a)
-            self.status.append(self.L.dropin_demod_feed(n, i16[a:a + n].ctypes.data, q16[a:a + n].ctypes.data))
+            self.status.append(self._feed(n, i16[a:a + n].ctypes.data, q16[a:a + n].ctypes.data))
+            assert self.status[-1] >= 0
 
     def taps(self):
         def tap(name, dtype):

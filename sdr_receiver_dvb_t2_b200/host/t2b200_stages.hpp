@@ -207,26 +207,23 @@ class fec_chain {
 };
 
 // bb_de_header.h:41-108 -- execute(plp_id, l1_post, len_in, bits): one BBFRAME in, one datagram out (the reference sends it
-// with socket->writeDatagram, bb_de_header.cpp:431-441; here a sink callback receives it).  High-efficiency mode on the
-// GPU; a normal-mode frame (status 3) is reported to `unhandled` so that the host bb_de_header can take it.  need_plp as in
-// set_out (bb_de_header.cpp:502-529).
+// with socket->writeDatagram, bb_de_header.cpp:431-441; here a sink callback receives it).  High-efficiency mode (status 0)
+// and normal mode (status 3) are both built on the GPU.  need_plp as in set_out (bb_de_header.cpp:502-529).
 class bb_de_header {
  public:
   typedef std::function<void(const uint8_t* datagram, int len)> ts_sink;
-  typedef std::function<void(int plp_id, int len, uint8_t* bits)> frame_sink;
-  bb_de_header(context& c, ts_sink sink, frame_sink unhandled = nullptr) : c_(c), sink_(std::move(sink)), unhandled_(std::move(unhandled)) {}
+  bb_de_header(context& c, ts_sink sink) : c_(c), sink_(std::move(sink)) {}
   void set_out(int need_plp) { need_plp_ = need_plp; c_.check(t2b200_ts_reset(c_.get(), need_plp), "t2b200_ts_reset"); }
   void execute(int plp_id, int len_in, uint8_t* bits) {
     if (plp_id != need_plp_) return;                                          // bb_de_header.cpp:133-136
     out_.resize((size_t)len_in / 8 + 2 * 188 + 16);
     int32_t dl = 0, st = 0; long long total = 0;
     c_.check(t2b200_ts_packetize(c_.get(), plp_id, bits, 1, len_in, out_.data(), out_.size(), &dl, &st, &total), "t2b200_ts_packetize");
-    if (st == 3) { if (unhandled_) unhandled_(plp_id, len_in, bits); return; }
     if (st == 1) { std::fprintf(stderr, "Baseband header CRC8 error.\n"); return; }   // bb_de_header.cpp:109-112
-    if (st == 0) sink_(out_.data(), dl);                                      // (a zero-length datagram is sent too, like the reference)
+    if (st == 0 || st == 3) sink_(out_.data(), dl);                                      // (a zero-length datagram is sent too, like the reference)
   }
  private:
-  context& c_; ts_sink sink_; frame_sink unhandled_; int need_plp_ = 0; std::vector<uint8_t> out_;
+  context& c_; ts_sink sink_; int need_plp_ = 0; std::vector<uint8_t> out_;
 };
 
 }  // namespace t2b200

@@ -16,18 +16,18 @@ from oracle import pyoracle as O
 from tests import e2e_helpers as H
 
 
-def _worker(name, path):
+def _worker(name, path, gpu_frontend=False):
     i16, q16, _, _ = H.make_stream(name)
-    rx = O.DropinDemod()
+    rx = O.DropinDemod(gpu_frontend=gpu_frontend)
     rx.feed(i16, q16)
     t = rx.taps()
     np.savez(path, **t)
 
 
-def run_dropin(name):
+def run_dropin(name, gpu_frontend=False):
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, 'taps.npz')
-        p = mp.get_context('spawn').Process(target=_worker, args=(name, path))      # fresh process: static state in the reference's TUs
+        p = mp.get_context('spawn').Process(target=_worker, args=(name, path, gpu_frontend))      # fresh process: static state in the reference's TUs
         p.start()
         p.join()
         assert p.exitcode == 0, 'drop-in receiver died (exit code %s)' % p.exitcode
@@ -42,7 +42,7 @@ def test_dropin_library_is_built_and_links_the_product():
         pytest.skip('oracle/_ref/libdropin_chain.so not built (needs /root/reference)')
     import ctypes as C
     L = C.CDLL(so)
-    for sym in ('dropin_demod_new', 'dropin_demod_feed', 'dropin_tap_ts', 'dropin_tap_bb_bits', 't2b200_fft', 't2b200_equalize',
+    for sym in ('dropin_demod_new', 'dropin_demod_feed', 'dropin_demod_feed_gpu_frontend', 't2b200_frontend_execute', 'dropin_tap_ts', 'dropin_tap_bb_bits', 't2b200_fft', 't2b200_equalize',
                 't2b200_ti_deinterleave', 't2b200_demap', 't2b200_ldpc_decode', 't2b200_bch_descramble'):
         assert hasattr(L, sym), sym
 
@@ -56,3 +56,16 @@ def test_reference_receiver_with_gpu_stages_emits_the_golden_ts(name):
     assert len(t['bb_len']) == g['n_bbframes']
     assert len(t['ts']) == g['ts_bytes'] and list(t['ts_datagrams']) and len(t['ts_datagrams']) == g['n_datagrams']
     assert H.sha(t['ts']) == g['ts_sha']
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(H.CONFIGS))
+def test_gpu_frontend_in_the_closed_loop_emits_the_golden_ts(name):
+    """N2 end to end: int16 I/Q -> t2b200_frontend_execute per chunk (DC / IQ / NCO / resampler / decimator on the GPU) -> the
+    reference's unmodified symbol_acquisition (P1, guard-interval correlation, loop filters, L1) -> GPU stages -> TS.  The
+    synchronisation loops are closed through the GPU front-end, and the TS is still the all-reference run's, byte for byte."""
+    g = H.golden()[name]
+    t = run_dropin(name, gpu_frontend=True)
+    assert int(t['launches']) > 0
+    assert len(t['bb_len']) == g['n_bbframes'] and len(t['ts_datagrams']) == g['n_datagrams']
+    assert len(t['ts']) == g['ts_bytes'] and H.sha(t['ts']) == g['ts_sha']
