@@ -119,30 +119,22 @@ __device__ __forceinline__ float slice_axis(float x, float a)
 {
   // nearest constellation level the way the reference's if-ladders pick it (strict > / < tests)
   if (MOD == 0) return x > 0 ? a : -a;
-  if (MOD == 1) {
-    if (x > 0) return x > 2 * a ? 3 * a : a;
-    return x < -(2 * a) ? -(3 * a) : -a;
-  }
-  if (MOD == 2) {
-    if (x > 0) {
-      if (x > 4 * a) return x > 6 * a ? 7 * a : 5 * a;
-      return x > 2 * a ? 3 * a : a;
-    }
-    if (x < -(4 * a)) return x > 6 * a ? -(7 * a) : -(5 * a);   // llr_demapper.cpp:407,427: never -7a
-    return x < -(2 * a) ? -(3 * a) : -a;
-  }
-  // 256-QAM
+  // Branch-free: the reference's ladders (strict > on the positive side, strict < on the negative one, x == 0 on the negative
+  // side) pick level 2 n + 1 with n = the number of thresholds 2a, 4a, .. that |x| exceeds; (2 n + 1) a as one rounding of the
+  // exact product, which is what a * k.0f is (2a is exact, so the FMA rounds the same real number)
   const float ax = fabsf(x);
-  float s;
-  if (x > 0) {
-    if (x > 8 * a) { if (x > 12 * a) s = x > 14 * a ? 15 * a : 13 * a; else s = x > 10 * a ? 11 * a : 9 * a; }
-    else { if (x > 4 * a) s = x > 6 * a ? 7 * a : 5 * a; else s = x > 2 * a ? 3 * a : a; }
-    return s;
+  float n = ax > 2 * a ? 1.f : 0.f;
+  if (MOD >= 2) n += ax > 4 * a ? 1.f : 0.f;
+  if (MOD == 2) n += (x > 0 && ax > 6 * a) ? 1.f : 0.f;         // llr_demapper.cpp:407,427: the negative side never reaches -7a
+  if (MOD == 3) {
+    n += ax > 6 * a ? 1.f : 0.f;
+    n += ax > 8 * a ? 1.f : 0.f;
+    n += ax > 10 * a ? 1.f : 0.f;
+    n += ax > 12 * a ? 1.f : 0.f;
+    n += ax > 14 * a ? 1.f : 0.f;
   }
-  (void)ax;
-  if (x < -(8 * a)) { if (x < -(12 * a)) s = x < -(14 * a) ? 15 * a : 13 * a; else s = x < -(10 * a) ? 11 * a : 9 * a; }
-  else { if (x < -(4 * a)) s = x < -(6 * a) ? 7 * a : 5 * a; else s = x < -(2 * a) ? 3 * a : a; }
-  return -s;
+  const float s = __fmaf_rn(n, 2 * a, a);
+  return x > 0 ? s : -s;
 }
 
 

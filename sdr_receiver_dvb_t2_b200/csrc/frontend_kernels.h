@@ -31,6 +31,7 @@
 #define FE_SYNC() __syncthreads()
 #define FE_ONE() if (threadIdx.x == 0)
 #define FE_LDG(p) __ldg(p)
+#define FE_UNROLL4 _Pragma("unroll 4")
 FE_FN float fe_mul(float a, float b) { return __fmul_rn(a, b); }      // never contracted into an FMA: the CPU does not either
 FE_FN float fe_add(float a, float b) { return __fadd_rn(a, b); }
 FE_FN float fe_sub(float a, float b) { return __fsub_rn(a, b); }
@@ -41,6 +42,7 @@ FE_FN float fe_sub(float a, float b) { return __fsub_rn(a, b); }
 #define FE_SYNC()
 #define FE_ONE()
 #define FE_LDG(p) (*(p))
+#define FE_UNROLL4
 FE_FN float fe_mul(float a, float b) { return a * b; }                // the emulation is built with -ffp-contract=off
 FE_FN float fe_add(float a, float b) { return a + b; }
 FE_FN float fe_sub(float a, float b) { return a - b; }
@@ -285,7 +287,7 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   FE_SHARED int sh_seg_k0[FE_MAX_CHUNK_SEG];
   FE_SHARED float sh_seg_v0[FE_MAX_CHUNK_SEG];
   FE_SHARED double sh_seg_inc[FE_MAX_CHUNK_SEG];
-  FE_SHARED int sh_nseg, sh_ndone, sh_base;
+  FE_SHARED int sh_nseg, sh_ndone, sh_base, sh_g0;
   const FeChunk ck = A.chunk[s];
   const int i0 = t * FE_TILE_IN;
   if (t == 0) { FE_FOR(j, 3) A.derot[s * A.derot_stride + j] = A.cur[s].delay[2 - j]; }      // the resampler's delay line
@@ -299,13 +301,18 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   // (one thread); the local prefix sums of the DC average (all threads)
   if (P.n_seg > 0) {
     FE_FOR(g, P.n_seg) { sh_seg_k0[g] = P.seg_k0[g]; sh_seg_v0[g] = P.seg_v0[g]; sh_seg_inc[g] = P.seg_inc[g]; }
-    FE_ONE() { sh_nseg = P.n_seg; sh_ndone = L; sh_base = i0; }
+    FE_ONE() {
+      sh_nseg = P.n_seg; sh_ndone = L; sh_base = i0;
+      int lo = 0, hi = P.n_seg - 1;                              // the segment of the tile's first sample: k0 < i0 + 1
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (P.seg_k0[mid] < i0 + 1) lo = mid; else hi = mid - 1; }
+      sh_g0 = lo;
+    }
   } else {
     FE_ONE() {
       int ns = 0, nd = 0;
       float v = fe_nco_run(P.nco_start[t], c, L, FE_MAX_SEG, sh_seg_k0, sh_seg_v0, sh_seg_inc, &ns, &nd);
       for (int k = nd; k < L; ++k) { v = fe_wrap(fe_add(v, c)); sh_phase[k] = v; }      // beyond FE_MAX_SEG segments: step by step
-      sh_nseg = ns; sh_ndone = nd; sh_base = 0;
+      sh_nseg = ns; sh_ndone = nd; sh_base = 0; sh_g0 = 0;
     }
   }
   FE_FOR(k, FE_THREADS) {
@@ -333,8 +340,8 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   FE_FOR(i, L) {
     if (i < sh_ndone) {
       const int step_idx = sh_base + i + 1;                     // sample i uses v_{i+1}: the segment with k0 < i + 1 <= k0 + len
-      int lo = 0, hi = sh_nseg - 1;
-      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sh_seg_k0[mid] < step_idx) lo = mid; else hi = mid - 1; }
+      int lo = sh_g0;                                           // the tile's first segment; a tile rarely spans more than two
+      while (lo + 1 < sh_nseg && sh_seg_k0[lo + 1] < step_idx) ++lo;
       sh_phase[i] = (float)((double)sh_seg_v0[lo] + (double)(step_idx - sh_seg_k0[lo]) * sh_seg_inc[lo]);
     }
   }
@@ -342,7 +349,7 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
   // phase C: the samples; thread k takes samples k, k + 256, ... (coalesced) and keeps its share of the statistics in registers
   const double2 y0 = P.dc_start[t];
   FE_FOR(k, FE_THREADS) {
-    double th0 = 0.0, th1 = 0.0, th2 = 0.0;
+    float th0 = 0.0f, th1 = 0.0f, th2 = 0.0f;                    // four samples per thread in float, the tree below in double
     for (int i = k; i < L; i += FE_THREADS) {
       const int g = i >> 2;
       double2 pre = sh_z[i];
@@ -353,9 +360,9 @@ FE_FN void fe_derotate_body(const FeArgs& A, int s, int t)
       float real = fe_sub(fe_mul((float)pi[(long long)(i0 + i) * A.step], ck.short_to_float), dc_re);
       float imag = fe_sub(fe_mul((float)pq[(long long)(i0 + i) * A.step], ck.short_to_float), dc_im);
       const float sr = real < 0 ? -1.0f : 1.0f, si = imag < 0 ? -1.0f : 1.0f;
-      th0 -= (double)fe_mul(imag, sr);
-      th1 += (double)fe_mul(real, sr);
-      th2 += (double)fe_mul(imag, si);
+      th0 -= fe_mul(imag, sr);
+      th1 += fe_mul(real, sr);
+      th2 += fe_mul(imag, si);
       real = fe_mul(real, ck.c2);
       imag = fe_add(imag, fe_mul(ck.c1, real));
       const float off_nco = fe_wrap(fe_sub(sh_phase[i], ck.phase_nco));
@@ -444,6 +451,7 @@ FE_FN void fe_resample_body(const FeArgs& A, int s, int tile, int n_tiles)
   // resampler outputs of the tile into shared memory; 16 bytes of padding after every 64 (the decimator below reads 16-byte
   // words at a stride of 64 bytes per thread)
   float2* sh_v = reinterpret_cast<float2*>(sh_v4);
+  FE_UNROLL4
   FE_FOR(j, count) sh_v[j + ((j >> 3) << 1)] = fe_interp_at(A, s, m_lo + j, x1, d);
   FE_SYNC();
   // filter_decimator.h:95-123: four 8-float lanes (one complex sample each), blocks of 16 samples, (m0 + m1) + (m2 + m3) per lane
