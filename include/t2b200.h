@@ -333,6 +333,16 @@ int t2b200_frontend_get_state(t2b200_ctx* ctx, int stream, t2b200_fe_state* stat
 int t2b200_frontend_set_state(t2b200_ctx* ctx, int stream, const t2b200_fe_state* state);
 int t2b200_cp_correlate(t2b200_ctx* ctx, const float* symbols, int n_symbols, long long symbol_stride, int fft_size, int guard,
                         float* frequency_est);
+/* The sliding correlator of p1_symbol::execute (p1_symbol.cpp:75-178, block diagram :56-74): for every sample of a block the
+ * product of the two branch sums (`out`) and its squared magnitude (`correlation`), which the reference compares with its
+ * begin / end thresholds.  Closed form (window sums as differences of prefix sums) instead of the reference's delay lines and
+ * running sums: agreement to 1e-5 of the correlation peak.  Stateless: the caller hands over what the reference keeps in its
+ * buffers -- the 2046 samples in front of the block (NULL: zeros, i.e. after reset_buffer) and the position of the block's
+ * first sample in the 1024-step frequency-shift table (the reference's static idx_fq_shift).  The threshold state machine, the
+ * 1K FFT of the detected symbol (t2b200_fft) and the S1 / S2 decoding stay with the caller.
+ *   samples complex<float>[n]; history complex<float>[2046] or NULL; correlation float[n]; out complex<float>[n] or NULL */
+int t2b200_p1_correlate(t2b200_ctx* ctx, const float* samples, int n, const float* history, int fq_index,
+                        float* correlation, float* out);
 
 /* ---- multi-GPU: the LDPC / BCH stage sharded by codeword over the GPUs of one box --------------------- */
 /* FEC blocks are independent, so one rank demodulates (it holds the int8 LLRs of a pooled batch), every rank decodes a

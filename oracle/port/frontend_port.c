@@ -180,3 +180,66 @@ float port_fe_cp_correlate(const float* sym, int fft_size, int guard)
   }
   return atan2_approx(si, sr) / (float)(fft_size << 1);
 }
+
+/* ---- P1 correlator (DVB_T2/p1_symbol.cpp:75-178, the chain block diagram at :56-74; DSP/buffers.hh) ----------------------
+ * data -> x exp(-j 2 pi f_sh t) [fq_shift, :30-35] -> delay Tc -> conj-multiply with data -> running sum over Tc -> delay 2 Tb -+
+ * data -> delay Tb -> conj-multiply with the shifted data -> running sum over Tb -> delay 2 ---------------------------------x-> out
+ * correlation = |out|^2.  delay_buffer<T, D> returns the sample written D steps earlier; sum_of_buffer<T, LEN> holds the sum of
+ * the last LEN - 1 inputs (it subtracts the slot it is about to overwrite NEXT, buffers.hh:33-39). */
+#define P1_C 542
+#define P1_B 482
+typedef struct {
+  float fq[1024][2];
+  int idx_fq, ready;
+  float dc[P1_C + 1][2]; int ic;          /* delay_c */
+  float db[P1_B + 1][2]; int ib;          /* delay_b */
+  float dx[2 * P1_B + 1][2]; int ix;      /* delay_b_x2 */
+  float d2[3][2]; int i2;                 /* delay_2 */
+  float sc[P1_C][2], sum_c[2]; int isc;   /* average_c */
+  float sb[P1_B][2], sum_b[2]; int isb;   /* average_b */
+} port_p1_state;
+
+int port_p1_state_size(void) { return (int)sizeof(port_p1_state); }
+void port_p1_reset(port_p1_state* s)
+{
+  memset(s, 0, sizeof(*s));
+  const float angle_shift = TWO_PI_F / 1024.0f;
+  float angle = 0.0f;
+  for (int i = 0; i < 1024; ++i) { s->fq[i][0] = sinf(angle); s->fq[i][1] = cosf(angle); angle += angle_shift; }   /* :30-35 */
+  s->ready = 1;
+}
+static void p1_delay(float (*buf)[2], int len, int* idx, const float in[2], float out[2])
+{
+  buf[*idx][0] = in[0]; buf[*idx][1] = in[1];
+  *idx = (*idx + 1) % len;
+  out[0] = buf[*idx][0]; out[1] = buf[*idx][1];
+}
+static void p1_sum(float (*buf)[2], int len, int* idx, float sum[2], const float in[2])
+{
+  buf[*idx][0] = in[0]; buf[*idx][1] = in[1];
+  *idx = (*idx + 1) % len;
+  sum[0] = sum[0] - buf[*idx][0] + in[0];
+  sum[1] = sum[1] - buf[*idx][1] + in[1];
+}
+/* n samples -> correlation[n] and out[n] (complex) */
+void port_p1_correlate(port_p1_state* s, const float* in, int n, float* correlation, float* out)
+{
+  for (int i = 0; i < n; ++i) {
+    const float d[2] = {in[2 * i], in[2 * i + 1]};
+    const float* f = s->fq[s->idx_fq];
+    s->idx_fq = (s->idx_fq + 1) & 0x3FF;
+    const float sh[2] = {d[0] * f[0] - d[1] * f[1], d[0] * f[1] + d[1] * f[0]};
+    float c[2], b[2], a[2], dd[2];
+    p1_delay(s->dc, P1_C + 1, &s->ic, sh, c);
+    const float avc[2] = {d[0] * c[0] + d[1] * c[1], d[1] * c[0] - d[0] * c[1]};          /* data * conj(c) */
+    p1_delay(s->db, P1_B + 1, &s->ib, d, b);
+    const float avb[2] = {sh[0] * b[0] + sh[1] * b[1], sh[1] * b[0] - sh[0] * b[1]};      /* shifted * conj(b) */
+    p1_sum(s->sc, P1_C, &s->isc, s->sum_c, avc);
+    p1_sum(s->sb, P1_B, &s->isb, s->sum_b, avb);
+    p1_delay(s->dx, 2 * P1_B + 1, &s->ix, s->sum_c, a);
+    p1_delay(s->d2, 3, &s->i2, s->sum_b, dd);
+    const float o[2] = {a[0] * dd[0] - a[1] * dd[1], a[0] * dd[1] + a[1] * dd[0]};
+    correlation[i] = o[0] * o[0] + o[1] * o[1];
+    if (out) { out[2 * i] = o[0]; out[2 * i + 1] = o[1]; }
+  }
+}

@@ -61,6 +61,8 @@ def port():
                                     C.c_float, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
         L.port_fe_cp_correlate.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.port_fe_cp_correlate.restype = C.c_float
+        L.port_p1_reset.argtypes = [C.c_void_p]
+        L.port_p1_correlate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _port = L
     return _port
 
@@ -192,6 +194,7 @@ def ref_chain():
         L.ref_demod_params.argtypes = [_i32p]
         L.ref_tap_fft_arm.argtypes = [C.c_int]
         L.ref_tap_frontend_arm.argtypes = [C.c_int, C.c_int]
+        L.ref_p1_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         for n in ('fft_in', 'fft_info', 'fe_info', 'fe_derot', 'fe_interp', 'fe_decim'):
             f = getattr(L, 'ref_tap_' + n)
             f.argtypes = [C.c_void_p, C.c_longlong]
@@ -446,6 +449,30 @@ class PortFrontend:
                                  frequency_est_filtered, phase_nco, resample, derot.ctypes.data, interp.ctypes.data,
                                  C.byref(n_interp), out.ctypes.data, self.theta.ctypes.data)
         return out[:k].copy(), interp[:n_interp.value].copy(), derot
+
+
+class PortP1:
+    """oracle/port/frontend_port.c: p1_symbol's sliding correlator (p1_symbol.cpp:75-178), state carried between calls"""
+
+    def __init__(self):
+        self.L = port()
+        self.state = np.zeros(self.L.port_p1_state_size(), np.uint8)
+        self.L.port_p1_reset(self.state.ctypes.data)
+
+    def correlate(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        corr = np.empty(len(x), np.float32)
+        out = np.empty(len(x), np.complex64)
+        self.L.port_p1_correlate(self.state.ctypes.data, x.ctypes.data, len(x), corr.ctypes.data, out.ctypes.data)
+        return corr, out
+
+
+def ref_p1_trace(x):
+    """the reference's own correlator, sample by sample (oracle/ref_chain.cc::ref_p1_trace) -> correlation float32[n]"""
+    x = np.ascontiguousarray(x, np.complex64)
+    corr = np.empty(len(x), np.float32)
+    ref_chain().ref_p1_trace(x.ctypes.data, len(x), corr.ctypes.data)
+    return corr
 
 
 def port_cp_correlate(sym, fft_size, guard):

@@ -362,6 +362,24 @@ int ref_demap_address(int fec_normal, int mod, int code_rate, int* out)
   return 1;
 }
 
+// p1_symbol's sliding correlator (p1_symbol.cpp:75-178) sample by sample: the thresholds are pushed out of reach so that the
+// detection branch never fires, and the `correlation` member is read after every sample
+int ref_p1_trace(const float* in, int n, float* correlation)
+{
+  static p1_symbol* p1 = nullptr;
+  if (!p1) p1 = make_zeroed<p1_symbol>();
+  p1->reset_buffer();
+  std::vector<complex> buf(4 * P1_LEN);
+  dvbt2_parameters d; std::memset(&d, 0, sizeof(d));
+  for (int i = 0; i < n; ++i) {
+    complex x(in[2 * i], in[2 * i + 1]);
+    int consume = 0, idx_sym = 0; double cfo = 0; bool dec = false, rst = false;
+    p1->execute(true, 3.0e+30f, 1, &x, consume, buf.data(), idx_sym, d, cfo, dec, rst);
+    correlation[i] = p1->correlation;
+  }
+  return 0;
+}
+
 // tap read-out: returns element count; copies up to max elements when dst != null
 #define TAP_GETTER(NAME, VEC, TYPE)                                                   \
   long long NAME(TYPE* dst, long long max) {                                          \

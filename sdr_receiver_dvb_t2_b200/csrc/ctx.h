@@ -50,9 +50,10 @@ struct t2b200_ctx {
   FramePipe* frames = nullptr;
   BchState* bch = nullptr;                    // GF(2^16) / GF(2^14) tables of the opt-in BCH decoder
   FeState* fe = nullptr;                      // receiver front-end streams (t2b200_frontend_configure)
+  float* d_p1_fq = nullptr;                   // p1_symbol's frequency-shift table, 1024 x {sin, cos}
   CommState* comm = nullptr;                  // NCCL communicator of the sharded FEC stage (t2b200_comm_init)
   // staging scratch, grown on demand
-  Scratch dev[16];
+  Scratch dev[24];
   Scratch pin[8];
 };
 

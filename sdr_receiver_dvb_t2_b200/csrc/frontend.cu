@@ -41,8 +41,15 @@ __global__ void __launch_bounds__(FE_THREADS) fe_cp_correlate_kernel(const float
   fe_cp_correlate_body(sym + blockIdx.x * stride, fft_size, guard, est + blockIdx.x);
 }
 
+__global__ void __launch_bounds__(FE_P1_THREADS) fe_p1_correlate_kernel(const float2* x, int n, const float2* hist, const float2* fq, int i0,
+                                                                        double2* prefix, float* correlation, float2* out)
+{
+  fe_p1_correlate_body(x, n, hist, fq, i0, prefix, correlation, out);
+}
+
 void t2_fe_free(t2b200_ctx* ctx)
 {
+  if (ctx->d_p1_fq) { cudaFree(ctx->d_p1_fq); ctx->d_p1_fq = nullptr; }
   FeState* f = ctx->fe;
   if (!f) return;
   for (auto& p : f->d_state) if (p) cudaFree(p);
@@ -223,4 +230,33 @@ extern "C" int t2b200_cp_correlate(t2b200_ctx* ctx, const float* symbols, int n_
   ctx->launches++;
   T2_CUDA(ctx, cudaGetLastError());
   return t2_finish_out(ctx, frequency_est, d_est, (size_t)n_symbols * sizeof(float));
+}
+
+extern "C" int t2b200_p1_correlate(t2b200_ctx* ctx, const float* samples, int n, const float* history, int fq_index,
+                                   float* correlation, float* out)
+{
+  if (!ctx || !samples || !correlation || n < 0 || n > (1 << 22)) {
+    if (ctx) ctx->err = "t2b200_p1_correlate: bad argument";
+    return T2B200_ERR_ARG;
+  }
+  if (n == 0) return T2B200_OK;
+  if (!ctx->d_p1_fq) {
+    std::vector<float> fq; fe_make_p1_table(fq);
+    T2_CUDA(ctx, cudaMalloc(&ctx->d_p1_fq, fq.size() * sizeof(float)));
+    T2_CUDA(ctx, cudaMemcpy(ctx->d_p1_fq, fq.data(), fq.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  int rc;
+  const void *d_x, *d_h = nullptr; void *d_c, *d_o = nullptr, *d_p;
+  if ((rc = t2_to_device(ctx, 13, samples, (size_t)n * sizeof(float2), &d_x))) return rc;
+  if (history && (rc = t2_to_device(ctx, 14, history, (size_t)FE_P1_HISTORY * sizeof(float2), &d_h))) return rc;
+  if ((rc = t2_out_device(ctx, 15, correlation, (size_t)n * sizeof(float), &d_c))) return rc;
+  if (out && (rc = t2_out_device(ctx, 16, out, (size_t)n * sizeof(float2), &d_o))) return rc;
+  if ((rc = t2_dev_scratch(ctx, 17, 2 * ((size_t)n + FE_P1_LEAD + 1) * sizeof(double2), &d_p))) return rc;
+  fe_p1_correlate_kernel<<<1, FE_P1_THREADS, 0, ctx->stream>>>(static_cast<const float2*>(d_x), n, static_cast<const float2*>(d_h),
+                                                               reinterpret_cast<const float2*>(ctx->d_p1_fq), fq_index & 1023,
+                                                               static_cast<double2*>(d_p), static_cast<float*>(d_c), static_cast<float2*>(d_o));
+  ctx->launches++;
+  T2_CUDA(ctx, cudaGetLastError());
+  if (out && (rc = t2_finish_out(ctx, out, d_o, (size_t)n * sizeof(float2)))) return rc;
+  return t2_finish_out(ctx, correlation, d_c, (size_t)n * sizeof(float));
 }

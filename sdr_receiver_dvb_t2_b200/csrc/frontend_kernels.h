@@ -527,3 +527,88 @@ FE_FN void fe_cp_correlate_body(const float2* sym, int fft_size, int guard, floa
   }
   FE_ONE() { *frequency_est = fe_atan2_approx((float)sh_i[0], (float)sh_r[0]) / (float)(fft_size << 1); }
 }
+
+// ---- P1 correlator (p1_symbol.cpp:75-178; the chain block diagram at :56-74; DSP/buffers.hh) -----------------------------
+// The reference pushes every sample through two delay lines, two running sums and two more delays.  In closed form, with
+// s[i] = x[i] fq[(i0 + i) mod 1024] (the frequency shift, :30-35), pc[i] = x[i] conj(s[i - 542]), pb[i] = s[i] conj(x[i - 482]):
+//   out[i] = (sum of pc over the 541 samples up to i - 964) * (sum of pb over the 481 samples up to i - 2),  correlation = |out|^2
+// (sum_of_buffer<LEN> holds LEN - 1 terms: it subtracts the slot it will overwrite next, buffers.hh:33-39).  The window sums are
+// differences of prefix sums kept in double; one CTA scans the block (P1 search runs on one symbol's worth of samples per frame).
+enum { FE_P1_THREADS = 512, FE_P1_HISTORY = 2046, FE_P1_LEAD = 1505 };   // samples before the block that still matter; prefix origin
+
+FE_FN float2 fe_p1_x(const float2* x, const float2* hist, int j)
+{
+  if (j >= 0) return x[j];
+  if (hist && j >= -FE_P1_HISTORY) return hist[FE_P1_HISTORY + j];
+  float2 z; z.x = 0.f; z.y = 0.f;
+  return z;
+}
+FE_FN float2 fe_p1_shift(const float2* x, const float2* hist, const float2* fq, int i0, int j)
+{
+  const float2 d = fe_p1_x(x, hist, j), f = fq[(i0 + j) & 1023];
+  float2 r;
+  r.x = fe_sub(fe_mul(d.x, f.x), fe_mul(d.y, f.y));
+  r.y = fe_add(fe_mul(d.x, f.y), fe_mul(d.y, f.x));
+  return r;
+}
+// element j of the two product sequences (j >= -FE_P1_LEAD + 1)
+FE_FN void fe_p1_terms(const float2* x, const float2* hist, const float2* fq, int i0, int j, float2& pc, float2& pb)
+{
+  const float2 d = fe_p1_x(x, hist, j), sh = fe_p1_shift(x, hist, fq, i0, j);
+  const float2 c = fe_p1_shift(x, hist, fq, i0, j - 542), b = fe_p1_x(x, hist, j - 482);
+  pc.x = fe_add(fe_mul(d.x, c.x), fe_mul(d.y, c.y)); pc.y = fe_sub(fe_mul(d.y, c.x), fe_mul(d.x, c.y));
+  pb.x = fe_add(fe_mul(sh.x, b.x), fe_mul(sh.y, b.y)); pb.y = fe_sub(fe_mul(sh.y, b.x), fe_mul(sh.x, b.y));
+}
+
+// prefix: double2[2][n + FE_P1_LEAD + 1] scratch (inclusive prefix sums of pc / pb from j = -FE_P1_LEAD + 1; entry 0 is zero)
+FE_FN void fe_p1_correlate_body(const float2* x, int n, const float2* hist, const float2* fq, int i0, double2* prefix,
+                                float* correlation, float2* out)
+{
+  FE_SHARED double2 sh_c[2][FE_P1_THREADS], sh_b[2][FE_P1_THREADS];
+  const int total = n + FE_P1_LEAD;                          // elements j = -FE_P1_LEAD + 1 .. n - 1, stored at j + FE_P1_LEAD
+  const int per = (total + FE_P1_THREADS - 1) / FE_P1_THREADS;
+  double2* Pc = prefix; double2* Pb = prefix + (total + 1);
+  FE_FOR(t, FE_P1_THREADS) {
+    double2 ac, ab; ac.x = ac.y = ab.x = ab.y = 0.0;
+    for (int e = t * per + 1; e <= (t + 1) * per && e <= total; ++e) {
+      float2 pc, pb;
+      fe_p1_terms(x, hist, fq, i0, e - FE_P1_LEAD, pc, pb);
+      ac.x += pc.x; ac.y += pc.y; ab.x += pb.x; ab.y += pb.y;
+    }
+    sh_c[0][t] = ac; sh_b[0][t] = ab;
+  }
+  FE_SYNC();
+  int src = 0;
+  for (int off = 1; off < FE_P1_THREADS; off <<= 1) {
+    FE_FOR(t, FE_P1_THREADS) {
+      double2 vc = sh_c[src][t], vb = sh_b[src][t];
+      if (t >= off) { vc.x += sh_c[src][t - off].x; vc.y += sh_c[src][t - off].y; vb.x += sh_b[src][t - off].x; vb.y += sh_b[src][t - off].y; }
+      sh_c[src ^ 1][t] = vc; sh_b[src ^ 1][t] = vb;
+    }
+    FE_SYNC();
+    src ^= 1;
+  }
+  FE_FOR(t, FE_P1_THREADS) {
+    double2 ac, ab; ac.x = ac.y = ab.x = ab.y = 0.0;
+    if (t > 0) { ac = sh_c[src][t - 1]; ab = sh_b[src][t - 1]; }
+    if (t == 0) { Pc[0] = ac; Pb[0] = ab; }
+    for (int e = t * per + 1; e <= (t + 1) * per && e <= total; ++e) {
+      float2 pc, pb;
+      fe_p1_terms(x, hist, fq, i0, e - FE_P1_LEAD, pc, pb);
+      ac.x += pc.x; ac.y += pc.y; ab.x += pb.x; ab.y += pb.y;
+      Pc[e] = ac; Pb[e] = ab;
+    }
+  }
+  FE_SYNC();
+  FE_FOR(i, n) {
+    const int ec = i - 964 + FE_P1_LEAD, eb = i - 2 + FE_P1_LEAD;      // prefix entries of the window ends
+    float2 a, d;
+    a.x = (float)(Pc[ec].x - Pc[ec - 541].x); a.y = (float)(Pc[ec].y - Pc[ec - 541].y);
+    d.x = (float)(Pb[eb].x - Pb[eb - 481].x); d.y = (float)(Pb[eb].y - Pb[eb - 481].y);
+    float2 o;
+    o.x = fe_sub(fe_mul(a.x, d.x), fe_mul(a.y, d.y));
+    o.y = fe_add(fe_mul(a.x, d.y), fe_mul(a.y, d.x));
+    correlation[i] = fe_add(fe_mul(o.x, o.x), fe_mul(o.y, o.y));
+    if (out) out[i] = o;
+  }
+}

@@ -41,3 +41,12 @@ static inline int fe_max_out_tiles(const FeChunk* chunk, int n_streams)
   }
   return (worst + FE_TILE_OUT - 1) / FE_TILE_OUT;
 }
+
+// p1_symbol's frequency-shift table (p1_symbol.cpp:30-35): {sin, cos} of an angle accumulated in float
+static inline void fe_make_p1_table(std::vector<float>& fq)
+{
+  fq.resize(2 * 1024);
+  const float angle_shift = FE_TWO_PI_F / 1024.0f;
+  float angle = 0.0f;
+  for (int i = 0; i < 1024; ++i) { fq[2 * i] = sinf(angle); fq[2 * i + 1] = cosf(angle); angle += angle_shift; }
+}

@@ -36,7 +36,7 @@ SYMBOLS = [
     't2b200_comm_unique_id', 't2b200_comm_init', 't2b200_comm_destroy', 't2b200_ldpc_decode_sharded',
     't2b200_bch_t', 't2b200_bch_decode', 't2b200_frames_stage_ms',
     't2b200_frontend_configure', 't2b200_frontend_reset', 't2b200_frontend_execute', 't2b200_frontend_get_state',
-    't2b200_frontend_set_state', 't2b200_cp_correlate',
+    't2b200_frontend_set_state', 't2b200_cp_correlate', 't2b200_p1_correlate',
 ]
 
 
@@ -125,6 +125,7 @@ def lib():
     L.t2b200_frontend_get_state.argtypes = [vp, i32, vp]
     L.t2b200_frontend_set_state.argtypes = [vp, i32, vp]
     L.t2b200_cp_correlate.argtypes = [vp, vp, i32, C.c_longlong, i32, i32, vp]
+    L.t2b200_p1_correlate.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.t2b200_mode_init.argtypes = [i32] * 6 + [C.POINTER(Mode)]
     L.t2b200_pilot_tables.argtypes = [C.POINTER(Mode), i32, vp, vp]
     L.t2b200_eq_configure_mode.argtypes = [vp, C.POINTER(Mode)]
@@ -252,6 +253,14 @@ class Engine:
         self._chk(self.L.t2b200_cp_correlate(self.h, _ptr(symbols), int(symbols.shape[0]), int(symbols.shape[1]), fft_size, guard,
                                              _ptr(est)))
         return est
+
+    def p1_correlate(self, samples, history=None, fq_index=0):
+        """samples complex64[n], history complex64[2046] or None -> (correlation float32[n], out complex64[n]) (p1_symbol.cpp:75-178)"""
+        n = int(samples.shape[0])
+        corr = _like(samples, (n,), np.float32)
+        out = _like(samples, (n,), np.complex64)
+        self._chk(self.L.t2b200_p1_correlate(self.h, _ptr(samples), n, _ptr(history), fq_index, _ptr(corr), _ptr(out)))
+        return corr, out
 
     @property
     def launches(self):

@@ -58,6 +58,14 @@ void emu_nco_run(float v, float c, int n, float* values, int* n_segments)
 // the same recurrence without segments: only the end value (as fe_plan_body walks tile boundaries)
 float emu_nco_end(float v, float c, int n) { return fe_nco_run(v, c, n, 0, nullptr, nullptr, nullptr, nullptr, nullptr); }
 
+void emu_p1_correlate(const float* x, int n, const float* hist, int i0, float* correlation, float* out)
+{
+  std::vector<float> fq; fe_make_p1_table(fq);
+  std::vector<double2> prefix(2 * (size_t)(n + FE_P1_LEAD + 1));
+  fe_p1_correlate_body(reinterpret_cast<const float2*>(x), n, reinterpret_cast<const float2*>(hist),
+                       reinterpret_cast<const float2*>(fq.data()), i0, prefix.data(), correlation, reinterpret_cast<float2*>(out));
+}
+
 void emu_cp_correlate(const float* sym, int fft_size, int guard, float* est)
 {
   fe_cp_correlate_body(reinterpret_cast<const float2*>(sym), fft_size, guard, est);

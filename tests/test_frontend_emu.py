@@ -42,6 +42,7 @@ def emu():
         _lib.emu_fe_chunk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                       C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         _lib.emu_cp_correlate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        _lib.emu_p1_correlate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         assert _lib.emu_fe_state_size() == STREAM.itemsize
     return _lib
 
@@ -187,3 +188,38 @@ def test_cp_correlation_equals_the_oracle():
         want = O.port_cp_correlate(sym, n, g)
         assert abs(est.value - want) <= 1e-5 * abs(want)
         assert abs(est.value * 2 * n - 0.37) < 0.03
+
+
+def p1_test_signal(n, seed, p1_at=5000):
+    """noise with a P1-like structure (C | A | B with the frequency-shifted repetitions of EN 302 755) at p1_at"""
+    rng = np.random.default_rng(seed)
+    x = (rng.normal(0, 0.02, n) + 1j * rng.normal(0, 0.02, n))
+    a = (rng.normal(0, 0.1, 1024) + 1j * rng.normal(0, 0.1, 1024))
+    sh = np.exp(2j * np.pi * np.arange(1024) / 1024)
+    sym = np.concatenate([(a * sh)[:542], a, (a * sh)[542:]])
+    x[p1_at:p1_at + 2048] += sym
+    return x.astype(np.complex64)
+
+
+def test_p1_correlator_equals_the_oracle_across_blocks():
+    """the closed-form correlator against the oracle's delay lines and running sums, in one block and cut into blocks with the
+    history handed over; 1e-5 of the peak (the reference's running sums drift in float)"""
+    x = p1_test_signal(16000, 4)
+    want, want_out = O.PortP1().correlate(x)
+    peak = want.max()
+    assert np.argmax(want) > 5000 and peak > 100 * np.median(want)
+    for cuts in ([0, 16000], [0, 3000, 3001, 9500, 16000]):
+        got = np.empty(len(x), np.float32)
+        out = np.empty(len(x), np.complex64)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            hist = np.zeros(2046, np.complex64)
+            h = x[max(0, a - 2046):a]
+            if len(h):
+                hist[-len(h):] = h
+            blk = np.ascontiguousarray(x[a:b])
+            c, o = np.empty(b - a, np.float32), np.empty(b - a, np.complex64)
+            emu().emu_p1_correlate(blk.ctypes.data, b - a, hist.ctypes.data, a & 1023, c.ctypes.data, o.ctypes.data)
+            got[a:b], out[a:b] = c, o
+        assert np.abs(got - want).max() <= 1e-5 * peak
+        assert np.abs(out - want_out).max() <= 1e-5 * np.sqrt(peak)
+        assert np.argmax(got) == np.argmax(want)

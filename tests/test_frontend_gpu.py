@@ -134,6 +134,34 @@ def test_cp_correlation_equals_the_oracle(engine):
         assert np.abs(est - want).max() <= 1e-5 * np.abs(want).max()
 
 
+def test_p1_correlator_equals_the_oracle_across_blocks(engine):
+    """t2b200_p1_correlate against the oracle's delay lines and running sums (p1_symbol.cpp:75-178), one block and several
+    blocks with the history handed over, host and device buffers; 1e-5 of the peak"""
+    import torch
+    from tests.test_frontend_emu import p1_test_signal
+    x = p1_test_signal(40000, 4, p1_at=21000)
+    want, want_out = O.PortP1().correlate(x)
+    peak = want.max()
+    for cuts, dev in (([0, 40000], False), ([0, 3000, 3001, 22000, 40000], True)):
+        got = np.empty(len(x), np.float32)
+        out = np.empty(len(x), np.complex64)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            hist = np.zeros(2046, np.complex64)
+            h = x[max(0, a - 2046):a]
+            if len(h):
+                hist[-len(h):] = h
+            blk = np.ascontiguousarray(x[a:b])
+            if dev:
+                c, o = engine.p1_correlate(torch.from_numpy(blk).cuda(), torch.from_numpy(hist).cuda(), a & 1023)
+                engine.sync()                                     # device buffers keep the call asynchronous (include/t2b200.h)
+                c, o = c.cpu().numpy(), o.cpu().numpy()
+            else:
+                c, o = engine.p1_correlate(blk, hist if a else None, a & 1023)
+            got[a:b], out[a:b] = c, o
+        assert np.abs(got - want).max() <= 1e-5 * peak and np.abs(out - want_out).max() <= 1e-5 * np.sqrt(peak)
+        assert np.argmax(got) == np.argmax(want)
+
+
 def test_reset_and_bad_arguments(engine):
     engine.frontend_configure(2, 5000)
     chunks = np.zeros(2, E.FE_CHUNK)

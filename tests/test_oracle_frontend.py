@@ -47,3 +47,16 @@ def test_cp_correlation_port_recovers_a_known_rotation():
     sym[n:] = sym[:g] * np.exp(-0.2j)
     est = O.port_cp_correlate(sym.astype(np.complex64), n, g)
     assert abs(est * 2 * n + 0.2) < 0.02
+
+
+@pytest.mark.skipif(not O.have_ref('libref_chain.so'), reason='compiled reference not present')
+def test_p1_correlator_port_equals_the_reference():
+    """the oracle's restatement of p1_symbol's sliding correlator against the compiled reference's, sample by sample, on the
+    head of the synthetic 16K stream (it holds a P1 symbol); 2e-6 of the peak (the reference is built -Ofast)"""
+    from tests import e2e_helpers as H
+    i16, q16, _, _ = H.make_stream('c16e')
+    x = ((i16[:30000].astype(np.float32) + 1j * q16[:30000].astype(np.float32)) / 16384).astype(np.complex64)
+    ref = O.ref_p1_trace(x)
+    corr, _ = O.PortP1().correlate(x)
+    assert ref.max() > 1000 * np.median(ref) and np.argmax(ref) == np.argmax(corr)
+    assert np.abs(ref - corr).max() <= 2e-6 * ref.max()
