@@ -135,6 +135,14 @@ extern "C" int t2b200_frontend_set_state(t2b200_ctx* ctx, int stream, const t2b2
   FeState* f = ctx->fe;
   if (!f) { ctx->err = "front-end not configured"; return T2B200_ERR_STATE; }
   if (stream < 0 || stream >= f->n_streams) { ctx->err = "t2b200_frontend_set_state: no such stream"; return T2B200_ERR_ARG; }
+  // what the kernels rely on: the resampler phase the reference can leave behind (x1 in [-0.5, 0.5 + resample), resample <= 1:
+  // the output rows are sized for it), the decimator phase 0 / 1, an NCO phase inside its wrap range
+  if (!(state->x1 >= -0.5f && state->x1 < 1.5f) || (state->parity != 0 && state->parity != 1) ||
+      !(state->frequency_nco >= -FE_TWO_PI_F && state->frequency_nco <= FE_TWO_PI_F) || !(state->dc_re == state->dc_re) ||
+      !(state->dc_im == state->dc_im)) {
+    ctx->err = "t2b200_frontend_set_state: x1 outside [-0.5, 1.5), parity not 0 / 1, or NCO phase outside +-2 pi";
+    return T2B200_ERR_ARG;
+  }
   T2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   T2_CUDA(ctx, cudaMemcpy(f->d_state[f->cur] + stream, state, sizeof(FeStream), cudaMemcpyHostToDevice));
   return T2B200_OK;

@@ -55,6 +55,35 @@ void emu_nco_run(float v, float c, int n, float* values, int* n_segments)
   *n_segments = ns;
 }
 
+// stress: `cases` random (v, c, n) triples, the jumps against n real float additions; returns the number of mismatching cases
+int emu_nco_stress(unsigned seed, int cases, float* bad_v, float* bad_c, int* bad_n)
+{
+  unsigned long long st = seed * 2654435761ull + 88172645463325252ull;
+  auto rnd = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+  int bad = 0;
+  std::vector<float> got(FE_TILE_IN);
+  for (int k = 0; k < cases; ++k) {
+    float v = rnd() < 0.7 ? (float)((rnd() * 2 - 1) * 6.2831) : (float)((rnd() * 2 - 1) * std::pow(10.0, -8.0 * rnd()));
+    if (rnd() < 0.05) v = std::ldexp(1.0f, (int)(rnd() * 6) - 3) * (rnd() < 0.5 ? 1.f : -1.f);          // exact powers of two
+    float c = (float)((rnd() < 0.5 ? 1 : -1) * std::pow(10.0, -9.0 + 7.5 * rnd()));
+    if (rnd() < 0.1) c = std::ldexp(1.0f, -(int)(rnd() * 30) - 3) * (rnd() < 0.5 ? 1.f : -1.f) * (rnd() < 0.5 ? 1.0f : 1.5f);   // ties
+    const int n = 1 + (int)(rnd() * (FE_TILE_IN - 1));
+    int ns = 0;
+    emu_nco_run(v, c, n, got.data(), &ns);
+    const float end = fe_nco_run(v, c, n, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    float w = v; bool ok = true;
+    for (int i = 0; i < n; ++i) {
+      w = fe_wrap(fe_add(w, c));
+      unsigned a, b; std::memcpy(&a, &w, 4); std::memcpy(&b, &got[i], 4);
+      if (a != b) { ok = false; break; }
+    }
+    unsigned a, b; std::memcpy(&a, &w, 4); std::memcpy(&b, &end, 4);
+    if (ok && a != b) ok = false;
+    if (!ok) { if (bad == 0) { *bad_v = v; *bad_c = c; *bad_n = n; } ++bad; }
+  }
+  return bad;
+}
+
 // the same recurrence without segments: only the end value (as fe_plan_body walks tile boundaries)
 float emu_nco_end(float v, float c, int n) { return fe_nco_run(v, c, n, 0, nullptr, nullptr, nullptr, nullptr, nullptr); }
 

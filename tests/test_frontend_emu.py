@@ -39,6 +39,7 @@ def emu():
         _lib.emu_nco_run.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         _lib.emu_nco_end.argtypes = [C.c_float, C.c_float, C.c_int]
         _lib.emu_nco_end.restype = C.c_float
+        _lib.emu_nco_stress.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
         _lib.emu_fe_chunk.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                       C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         _lib.emu_cp_correlate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -91,6 +92,14 @@ def test_nco_recurrence_random():
         emu().emu_nco_run(v, c, n, got.ctypes.data, C.byref(ns))
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (float(v), float(c), n, np.flatnonzero(got != want)[:5])
         assert np.float32(emu().emu_nco_end(v, c, n)).view(np.uint32) == want[-1].view(np.uint32)
+
+
+def test_nco_recurrence_stress():
+    """200 000 random (phase, decrement, length) triples, incl. exact ties and powers of two, against real float additions
+    (compared in C, tests/cpp/frontend_emu.cpp::emu_nco_stress; 2 000 000 cases were run once when the planner was written)"""
+    v, c, n = C.c_float(), C.c_float(), C.c_int()
+    bad = emu().emu_nco_stress(12345, 200000, C.byref(v), C.byref(c), C.byref(n))
+    assert bad == 0, (bad, v.value, c.value, n.value)
 
 
 def emu_chunk(states, chunks, i16, q16, step=1):

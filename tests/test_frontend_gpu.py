@@ -188,3 +188,9 @@ def test_reset_and_bad_arguments(engine):
         engine.frontend_execute(iq[0], iq[1], chunks, out=np.zeros((2, 100), np.complex64))
     with pytest.raises(E.T2Error):
         engine.frontend_configure(0, 100)
+    st = engine.frontend_state(0)
+    for field, v in (('x1', -3.0), ('parity', 2), ('frequency_nco', 7.0)):
+        bad_st = st.copy()
+        bad_st[field] = v
+        with pytest.raises(E.T2Error):
+            engine.frontend_set_state(0, bad_st)
