@@ -226,4 +226,42 @@ class bb_de_header {
   context& c_; ts_sink sink_; int need_plp_ = 0; std::vector<uint8_t> out_;
 };
 
+// The front-end of dvbt2_demodulator::execute (dvbt2_demodulator.cpp:178-221): the per-sample loop (int16 -> float, DC
+// removal, IQ-imbalance statistics and correction, NCO), interpolator_farrow::operator() (DSP/interpolator_farrow.hh:41-68) and
+// filter_decimator::execute (DSP/filter_decimator.h:72-131) of one chunk in one call; the arguments carry the member names
+// execute() uses.  The carried state (DC averages, frequency_nco, resampler phase, delay lines) lives in the engine.
+class frontend {
+ public:
+  explicit frontend(context& c, int max_chunk = 1 << 17) : c_(c) {
+    c_.check(t2b200_frontend_configure(c_.get(), 1, max_chunk), "t2b200_frontend_configure");
+  }
+  void reset() { c_.check(t2b200_frontend_reset(c_.get(), 0), "t2b200_frontend_reset"); }      // dvbt2_demodulator::reset
+  // returns len_out_decimator; theta1..3 are accumulated on, as est_1_bit_quantization does (:256-265)
+  int execute(int chunk, const int16_t* i_in, const int16_t* q_in, int convert_input, float short_to_float, float c1, float c2,
+              float frequency_est_filtered, float phase_nco, double arbitrary_resample, complex* out_decimator, int capacity,
+              float& theta1, float& theta2, float& theta3) {
+    t2b200_fe_chunk ck = {chunk, short_to_float, c1, c2, frequency_est_filtered, phase_nco, static_cast<float>(arbitrary_resample)};
+    t2b200_fe_result r;
+    c_.check(t2b200_frontend_execute(c_.get(), i_in, q_in, 0, convert_input, &ck, reinterpret_cast<float*>(out_decimator), capacity, &r),
+             "t2b200_frontend_execute");
+    theta1 += r.theta1; theta2 += r.theta2; theta3 += r.theta3;
+    return r.len_out;
+  }
+  // guard-interval correlation of one buffered symbol (dvbt2_demodulator.cpp:321-330) -> frequency_est
+  float cp_correlate(const complex* buffer_sym, int fft_size, int guard_interval_size) {
+    float est = 0.f;
+    c_.check(t2b200_cp_correlate(c_.get(), reinterpret_cast<const float*>(buffer_sym), 1, fft_size + guard_interval_size, fft_size,
+                                 guard_interval_size, &est), "t2b200_cp_correlate");
+    return est;
+  }
+  // p1_symbol's sliding correlator over a block (p1_symbol.cpp:141-165): correlation[n], out[n]; history = the 2046 samples
+  // in front of the block or nullptr, fq_index = the block's position in the 1024-step frequency shift
+  void p1_correlate(const complex* in, int n, const complex* history, int fq_index, float* correlation, complex* out) {
+    c_.check(t2b200_p1_correlate(c_.get(), reinterpret_cast<const float*>(in), n, reinterpret_cast<const float*>(history), fq_index,
+                                 correlation, reinterpret_cast<float*>(out)), "t2b200_p1_correlate");
+  }
+ private:
+  context& c_;
+};
+
 }  // namespace t2b200

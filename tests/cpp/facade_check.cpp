@@ -57,6 +57,18 @@ int main(int argc, char** argv)
   } catch (const std::exception& e) { std::fprintf(stderr, "facade_check: %s\n", e.what()); fclose(out); if (ts) fclose(ts); return 1; }
   fclose(out);
   if (ts) fclose(ts);
-  std::printf("bbframes %d datagrams %d\n", n_frames, n_datagrams);
+  // the front-end mirror: one chunk of a constant input -> as many decimator outputs as inputs at resample = 0.5, the DC
+  // component removed by less than a thousandth (ratio 1e-6), the in-band gain of the half-band filter close to one
+  int fe_out = 0; float fe_level = 0.f;
+  try {
+    t2b200::context ctx(0);
+    t2b200::frontend fe(ctx, 8192);
+    std::vector<int16_t> i16(4096, 4096), q16(4096, -2048);
+    std::vector<t2b200::complex> dec(4200);
+    float th1 = 0.f, th2 = 0.f, th3 = 0.f;
+    fe_out = fe.execute(4096, i16.data(), q16.data(), 1, 1.0f / (1 << 14), 0.f, 1.f, 0.f, 0.f, 0.5, dec.data(), (int)dec.size(), th1, th2, th3);
+    fe_level = dec[3000].real();
+  } catch (const std::exception& e) { std::fprintf(stderr, "facade_check (front-end): %s\n", e.what()); return 1; }
+  std::printf("bbframes %d datagrams %d frontend %d level %.3f\n", n_frames, n_datagrams, fe_out, fe_level);
   return 0;
 }

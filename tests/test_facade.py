@@ -57,6 +57,7 @@ def test_facade_decodes_config4_frame():
         r = subprocess.run([b, fin, fout, fts], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         assert 'bbframes 64' in r.stdout
+        assert 'frontend 4096 level 0.249' in r.stdout         # the front-end mirror: 4096 / 2^14 = 0.25 less the DC the averager has taken out after 3000 samples
         got = np.fromfile(fout, np.uint8).reshape(64, -1)
         ts = np.fromfile(fts, np.uint8)
     assert np.array_equal(got, fr['bb'])
