@@ -82,26 +82,30 @@ extern "C" int t2b200_frontend_configure(t2b200_ctx* ctx, int n_streams, int max
   if ((rc = t2_ensure_lut(ctx))) return rc;
   FeState* f = new FeState();
   ctx->fe = f;
+  // a failed allocation leaves no half-built state behind
+#define FE_ALLOC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); \
+                                                                              cudaGetLastError(); t2_fe_free(ctx); return e__ == cudaErrorMemoryAllocation ? T2B200_ERR_NOMEM : T2B200_ERR_CUDA; } } while (0)
   f->n_streams = n_streams; f->max_chunk = max_chunk_in;
   const size_t S = (size_t)n_streams;
-  for (auto& p : f->d_state) T2_CUDA(ctx, cudaMalloc(&p, S * sizeof(FeStream)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_chunk, S * sizeof(FeChunk)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_plan, S * sizeof(FePlan)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_dc_part, S * FE_MAX_TILES * sizeof(double2)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_theta_part, S * FE_MAX_TILES * 3 * sizeof(double)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_derot, S * ((size_t)max_chunk_in + 4) * sizeof(float2)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_result, S * sizeof(FeResult)));
-  T2_CUDA(ctx, cudaMallocHost(&f->h_chunk, S * sizeof(FeChunk)));
-  T2_CUDA(ctx, cudaMallocHost(&f->h_result, S * sizeof(FeResult)));
+  for (auto& p : f->d_state) FE_ALLOC(cudaMalloc(&p, S * sizeof(FeStream)));
+  FE_ALLOC(cudaMalloc(&f->d_chunk, S * sizeof(FeChunk)));
+  FE_ALLOC(cudaMalloc(&f->d_plan, S * sizeof(FePlan)));
+  FE_ALLOC(cudaMalloc(&f->d_dc_part, S * FE_MAX_TILES * sizeof(double2)));
+  FE_ALLOC(cudaMalloc(&f->d_theta_part, S * FE_MAX_TILES * 3 * sizeof(double)));
+  FE_ALLOC(cudaMalloc(&f->d_derot, S * ((size_t)max_chunk_in + 4) * sizeof(float2)));
+  FE_ALLOC(cudaMalloc(&f->d_result, S * sizeof(FeResult)));
+  FE_ALLOC(cudaMallocHost(&f->h_chunk, S * sizeof(FeChunk)));
+  FE_ALLOC(cudaMallocHost(&f->h_result, S * sizeof(FeResult)));
   std::vector<double> apow, ainv; std::vector<float> lut, h;
   fe_make_tables(apow, ainv, lut, h);
-  T2_CUDA(ctx, cudaMalloc(&f->d_apow, apow.size() * sizeof(double)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_ainv, ainv.size() * sizeof(double)));
-  T2_CUDA(ctx, cudaMalloc(&f->d_h, h.size() * sizeof(float)));
-  T2_CUDA(ctx, cudaMemcpy(f->d_apow, apow.data(), apow.size() * sizeof(double), cudaMemcpyHostToDevice));
-  T2_CUDA(ctx, cudaMemcpy(f->d_ainv, ainv.data(), ainv.size() * sizeof(double), cudaMemcpyHostToDevice));
-  T2_CUDA(ctx, cudaMemcpy(f->d_h, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
-  T2_CUDA(ctx, cudaMemcpyToSymbol(fe_c_h, h.data(), h.size() * sizeof(float)));
+  FE_ALLOC(cudaMalloc(&f->d_apow, apow.size() * sizeof(double)));
+  FE_ALLOC(cudaMalloc(&f->d_ainv, ainv.size() * sizeof(double)));
+  FE_ALLOC(cudaMalloc(&f->d_h, h.size() * sizeof(float)));
+  FE_ALLOC(cudaMemcpy(f->d_apow, apow.data(), apow.size() * sizeof(double), cudaMemcpyHostToDevice));
+  FE_ALLOC(cudaMemcpy(f->d_ainv, ainv.data(), ainv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  FE_ALLOC(cudaMemcpy(f->d_h, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FE_ALLOC(cudaMemcpyToSymbol(fe_c_h, h.data(), h.size() * sizeof(float)));
+#undef FE_ALLOC
   return t2b200_frontend_reset(ctx, -1);
 }
 
