@@ -35,7 +35,7 @@ struct FeState {
 __global__ void __launch_bounds__(FE_THREADS) fe_dc_partial_kernel(FeArgs A) { fe_dc_partial_body(A, blockIdx.y, blockIdx.x); }
 __global__ void __launch_bounds__(64) fe_plan_kernel(FeArgs A) { fe_plan_body(A, blockIdx.x); }
 __global__ void __launch_bounds__(FE_THREADS) fe_derotate_kernel(FeArgs A) { fe_derotate_body(A, blockIdx.y, blockIdx.x); }
-__global__ void __launch_bounds__(FE_THREADS) fe_resample_kernel(FeArgs A) { fe_resample_body(A, blockIdx.y, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(FE_THREADS, 4) fe_resample_kernel(FeArgs A) { fe_resample_body(A, blockIdx.y, blockIdx.x, gridDim.x); }
 __global__ void __launch_bounds__(FE_THREADS) fe_cp_correlate_kernel(const float2* sym, long long stride, int fft_size, int guard, float* est)
 {
   fe_cp_correlate_body(sym + blockIdx.x * stride, fft_size, guard, est + blockIdx.x);
