@@ -21,23 +21,23 @@ COL = {n: i for i, n in enumerate(['len_in', 'len_interp', 'resample', 'phase_nc
 TOL = 2e-6
 
 
-def _ref_worker(path):
+def _ref_worker(path, stream=STREAM, first=FIRST, count=COUNT):
     from oracle import pyoracle as O
     from tests import e2e_helpers as H
-    i16, q16, _, _ = H.make_stream(STREAM)
-    rx = O.RefDemod(tap_fft=False, tap_frontend=(FIRST, COUNT))
-    n = 3200000                                        # enough for FIRST + COUNT chunks
+    i16, q16, _, _ = H.make_stream(stream)
+    rx = O.RefDemod(tap_fft=False, tap_frontend=(first, count))
+    n = 3200000 if stream == STREAM else len(i16)      # enough for FIRST + COUNT chunks
     rx.feed(i16[:n], q16[:n])
     t = rx.frontend_taps()
     t['iq_sha'] = H.sha(i16) + H.sha(q16)
     np.savez(path, **t)
 
 
-def run_reference():
+def run_reference(stream=STREAM, first=FIRST, count=COUNT):
     """-> the taps of oracle.pyoracle.RefDemod.frontend_taps for the window (fresh process: the reference keeps static state)"""
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, 'taps.npz')
-        p = mp.get_context('spawn').Process(target=_ref_worker, args=(path,))
+        p = mp.get_context('spawn').Process(target=_ref_worker, args=(path, stream, first, count))
         p.start()
         p.join()
         assert p.exitcode == 0
@@ -45,11 +45,11 @@ def run_reference():
         return {k: g[k] for k in g.files}
 
 
-def window(t):
+def window(t, FIRST=FIRST, COUNT=COUNT):
     """Split the taps: chunk FIRST only provides the state in front of the window, chunks FIRST+1 .. are compared.
     -> dict(info [n][14], in_offset, state fields, derot / decim lists per chunk)"""
     info = t['info']
-    assert len(info) >= FIRST + COUNT
+    assert len(info) >= FIRST + COUNT, len(info)
     off_in = np.concatenate([[0], np.cumsum(info[:, COL['len_in']]).astype(np.int64)])
     w = info[FIRST:FIRST + COUNT]
     od = np.concatenate([[0], np.cumsum(w[:, COL['len_in']]).astype(np.int64)])
@@ -87,10 +87,10 @@ def load_golden():
                 decim=[g['decim'][oo[k]:oo[k + 1]] for k in range(len(info))])
 
 
-def stream_input(w):
+def stream_input(w, stream=STREAM):
     """the int16 I/Q of the window's chunks, regenerated by the test modulator -> (i16, q16, offsets per chunk)"""
     from tests import e2e_helpers as H
-    i16, q16, _, _ = H.make_stream(STREAM)
+    i16, q16, _, _ = H.make_stream(stream)
     if 'iq_sha' in w:
         assert H.sha(i16) + H.sha(q16) == w['iq_sha'], 'the modulator no longer produces the stream the fixture was made from'
     off = w['in_offset'] + np.concatenate([[0], np.cumsum(w['info'][:, COL['len_in']]).astype(np.int64)])

@@ -8,8 +8,8 @@ from oracle import pyoracle as O
 from tests import fe_helpers as F
 
 
-def run_port(w, keep):
-    i16, q16, off = F.stream_input(w)
+def run_port(w, keep, stream=F.STREAM):
+    i16, q16, off = F.stream_input(w, stream)
     fe = O.PortFrontend()
     for k, v in w['state'].items():
         fe.state[k] = v
@@ -38,6 +38,16 @@ def test_port_equals_the_reference_live_and_the_fixture_is_current():
     g = F.load_golden()
     assert g['iq_sha'] == w['iq_sha'] and np.array_equal(g['info'], w['info'])
     assert all(np.array_equal(a[::F.KEEP], b) for a, b in zip(w['decim'], g['decim']))
+
+
+@pytest.mark.skipif(not O.have_ref('libref_chain.so'), reason='compiled reference not present')
+def test_port_equals_the_reference_live_on_the_32k_stream():
+    """the same on the 32K / 64 800 stream (tests/e2e_helpers.py 'c32e'): 40 chunks after lock, every sample"""
+    t = F.run_reference('c32e', 330, 41)
+    w = F.window(t, 330, 41)
+    w['iq_sha'] = str(t['iq_sha'])
+    assert (w['info'][:, F.COL['frequency_est_filtered']] != 0).any() and (w['info'][:, F.COL['phase_nco']] != 0).any()
+    assert run_port(w, 1, 'c32e') == 40
 
 
 def test_cp_correlation_port_recovers_a_known_rotation():
